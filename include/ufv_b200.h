@@ -1,0 +1,153 @@
+/*
+ * ufv_b200.h -- C ABI of the B200-native object encoder (libufv_b200.so).
+ *
+ * Drop-in boundary.  The reference (Heven-Pan/UFVideo) has no FFI for this path: its object
+ * encoder is the Python module `MaskExtractor` in ufvideo/model/layer.py, built at
+ * ufvideo/model/videorefer_arch.py:39,92 and called at videorefer_arch.py:236.  Each entry
+ * point below replaces the chain of ATen library calls named beside it; the Python host side
+ * (ufvideo_b200/layer.py) keeps the reference module's constructor, forward signature,
+ * parameter names and return types and binds these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
+ *     `_host`; `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 = ok, < 0 = bad argument (UFV_E_*), > 0 = cudaError_t of a failed launch.
+ *     ufv_last_error() returns a thread-local message for the last non-zero return.
+ *   - no global mutable state, no hidden allocation: the caller owns every buffer, calls are
+ *     stream-ordered and re-entrant across streams.
+ *   - there is no CPU path: without a CUDA device every compute call returns an error.
+ */
+#ifndef UFV_B200_H
+#define UFV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UFV_ABI_VERSION 1
+
+/* element types */
+enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3 };
+
+/* argument errors */
+enum {
+  UFV_E_NULL = -1,      /* required pointer is null */
+  UFV_E_SHAPE = -2,     /* size out of the supported range */
+  UFV_E_DTYPE = -3,     /* unsupported element type */
+  UFV_E_ALIGN = -4,     /* pointer / row pitch not 16-byte aligned */
+  UFV_E_DRIVER = -5     /* CUDA driver entry point unavailable (tensor-map encode) */
+};
+
+#define UFV_BITS_WORDS 24        /* uint32 words per patch bitmask row (729 bits -> 23, padded) */
+#define UFV_MAX_PATCH_SIDE 27    /* kernels are sized for up to 27 x 27 patches              */
+#define UFV_MAX_GROUP 8          /* object-frames pooled together from one staged frame tile */
+
+int ufv_abi_version(void);
+const char* ufv_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host helper: tap table of the bilinear resize of an h x w mask to n_out x n_out.
+ * Replaces the index/weight computation inside F.interpolate(mode='bilinear',
+ * align_corners=False) at layer.py:139, evaluated in fp32 exactly as ATen does, and folds the
+ * 'pad' aspect mode (layer.py:77-86) into the indices.
+ * taps_host[4 * n_out] = h0[n_out], h1[n_out], w0[n_out], w1[n_out]; an entry is the source
+ * row / column of that tap, or -1 when the tap contributes nothing (zero weight, or it falls
+ * into the zero padding).  Pure integer output; runs on the host.
+ * -------------------------------------------------------------------------------------------*/
+int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 1: mask resize + binarise -> patch bitmask, count and index list per object-frame.
+ * Replaces F.interpolate + (mask > 0) + mask.sum at layer.py:139,143,145.  Bit-exact.
+ *   mask_addr[n_masks]   device address of element (0,0) of each object-frame's mask plane
+ *   mask_shape[n_masks]  index into shape_tab
+ *   shape_tab[n_shapes*4] {row pitch in elements, element type UFV_*, offset of the shape's tap
+ *                         table inside `taps` in int32 units, 0}
+ *   bits_out[n_masks*UFV_BITS_WORDS]  bit p%32 of word p/32 = patch p (row-major h,w) is on
+ *   cnt_out[n_masks]     number of on patches
+ *   idx_out              optional (may be null): [n_masks * idx_pitch] uint16, ascending patch
+ *                        indices of the on patches, first cnt entries valid
+ * -------------------------------------------------------------------------------------------*/
+int ufv_mask_to_patches(const uint64_t* mask_addr, const int32_t* mask_shape,
+                        const int32_t* shape_tab, const int32_t* taps, int n_masks, int n_out,
+                        uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 2: segmented mask pool.  Replaces the gather feats[ann_index], the layout permute,
+ * the fp32 upcast (layer.py:98-104) and the masked mean (layer.py:145-147).
+ *   feats [n_rows, n_patch, c] of feat_dtype (UFV_F32 / UFV_BF16 / UFV_F16), contiguous
+ *   groups: group g pools object-frames grp_member[grp_off[g] .. grp_off[g+1]) (at most
+ *           UFV_MAX_GROUP of them), all of which read feature row grp_row[g]; max_group = the
+ *           largest group size in this call (selects the 4- or 8-object kernel variant)
+ *   pooled_out fp32 [n_masks, c]:  sum over on patches in ascending patch order, divided by
+ *           (float(cnt) + 1e-8f); an all-off mask gives an exact zero row.
+ * -------------------------------------------------------------------------------------------*/
+int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, int n_patch, int c,
+                  const uint32_t* bits, const int32_t* cnt, const int32_t* grp_row,
+                  const int32_t* grp_off, const int32_t* grp_member, int n_groups,
+                  int max_group, float* pooled_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 3: fused temporal token merge.  Replaces token_merge (layer.py:6-33), its dispatch
+ * (layer.py:110-119) and the downcast (layer.py:123).
+ *   object o owns pooled rows [obj_start[o], obj_start[o] + obj_len[o]) and writes its tokens
+ *   to rows slot_off[o] .. of tokens_out, which has min(obj_len[o], k_keep) rows reserved for
+ *   it; rows past counts_out[o] are zero-filled.
+ *   tokens_out [m_pad, c] of out_dtype; tokens_f32_out (optional) the same rows before the
+ *   downcast; cuts_out (optional) [n_obj * cut_pitch_words] uint32, bit i set = run boundary
+ *   after token i; sims_out (optional) [n_obj * sims_pitch] fp32 adjacent cosine similarities.
+ * -------------------------------------------------------------------------------------------*/
+int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
+            const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
+            int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
+            int cut_pitch_words, float* sims_out, int sims_pitch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 4: one Linear (+ optional exact-erf GELU) of the object projector,
+ *   y[m, n] = act(x[m, k] . w[n, k]^T + bias[n]),  act = GELU applied to the value rounded to
+ *   `dtype` (the reference rounds the hidden activation between modules, layer.py:55-59).
+ * UFV_BF16 / UFV_F16: tcgen05 tensor-core GEMM with TMEM accumulators (fp32 accumulate);
+ * UFV_F32: fp32 CUDA-core GEMM.  x, w, y row-major, 16-byte aligned, k % 8 == 0, n % 8 == 0.
+ * -------------------------------------------------------------------------------------------*/
+int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+               int dtype, int gelu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole path in one call (kernels 1-4 chained on `stream`).  Replaces
+ * MaskExtractor.forward (layer.py:63-128) minus the host read-back of counts.
+ * -------------------------------------------------------------------------------------------*/
+typedef struct ufv_encode_args {
+  /* features */
+  const void* feats; int32_t feat_dtype; int32_t n_patch_side; int64_t n_rows; int32_t c; int32_t hid;
+  /* masks -> patches */
+  const uint64_t* mask_addr; const int32_t* mask_shape; const int32_t* shape_tab;
+  const int32_t* taps; int32_t n_masks; int32_t idx_pitch;
+  uint32_t* bits; int32_t* cnt; uint16_t* idx;            /* idx optional */
+  /* pool */
+  const int32_t* grp_row; const int32_t* grp_off; const int32_t* grp_member; int32_t n_groups;
+  int32_t max_group;
+  float* pooled;
+  /* merge */
+  const int32_t* obj_start; const int32_t* obj_len; const int32_t* slot_off;
+  int32_t n_obj; int32_t max_len; int32_t k_keep; int32_t m_pad;
+  void* merged; int32_t* counts;
+  /* projector: feat_linear.0 / feat_linear.2 (layer.py:55-59) */
+  const void* w1; const void* b1; const void* w2; const void* b2;
+  void* hidden; void* tokens_out;
+} ufv_encode_args;
+
+int ufv_encode(const ufv_encode_args* args_host, void* stream);
+
+/* Gather rows: out[i, :] = in[row_map[i], :], `row_bytes` per row (multiple of 16).  Used to
+ * compact the padded token tensor when ties at the merge threshold left an object with fewer
+ * than min(T, K) tokens. */
+int ufv_gather_rows(const void* in, const int32_t* row_map, void* out, int n_out_rows,
+                    int row_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UFV_B200_H */

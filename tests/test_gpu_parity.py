@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden
+vectors.  Needs a B200: every test is marked gpu.
+
+Bars (BASELINE.json north_star): patch indices and merge decisions bit-exact; pooled / merged
+tokens within 1e-5 in fp32; projected tokens within 1e-2 in bf16 / fp16, 1e-5 in fp32.  Against
+the oracle's canonical evaluation order the pooled rows, similarities, cuts and merged tokens are
+additionally required to be BIT-IDENTICAL.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import golden_cases as gc
+from oracle import restatement as R
+from ufvideo_b200 import layer, packer, synth
+from ufvideo_b200.layer import MaskExtractor, MaskPooling, build_region_encoder, token_merge
+
+pytestmark = pytest.mark.gpu
+
+TORCH_DT = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+TOL = {"f32": 1e-5, "bf16": 1e-2, "f16": 1e-2}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def cfg(c=1152, hid=3584):
+    import types
+    return types.SimpleNamespace(mm_hidden_size=c, hidden_size=hid)
+
+
+def make_encoder(dev, dtype="f32", k=8, aspect="square", weights=None, c=1152, hid=3584):
+    enc = build_region_encoder(cfg(c, hid), aspect)
+    enc.region_token_num = k
+    w = weights if weights is not None else synth.make_weights(0, c, hid)
+    with torch.no_grad():
+        for p, a in zip((enc.feat_linear[0].weight, enc.feat_linear[0].bias,
+                         enc.feat_linear[2].weight, enc.feat_linear[2].bias), w):
+            p.copy_(torch.from_numpy(a))
+    return enc.to(dev).to(TORCH_DT[dtype])
+
+
+def bits_to_bool(bits: torch.Tensor, n=729):
+    b = bits.cpu().numpy().view(np.uint32)
+    return ((b[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(b.shape[0], -1)[:, :n]
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel 1
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mask_dtype", [torch.uint8, torch.float32, torch.bool, torch.float16, torch.bfloat16])
+def test_patch_bits_match_reference_golden(dev, golden_dir, mask_dtype):
+    g = np.load(os.path.join(golden_dir, "resize.npz"))
+    meta = json.loads(str(g["meta"]))
+    row = 0
+    for m in meta:
+        masks = gc.resize_masks(m["h"], m["w"])
+        t = torch.from_numpy(masks).to(dev).to(mask_dtype)
+        plan = packer.build_plan([t], [[list(range(m["n"]))]], m["n"], 1, dev)
+        bits, cnt, idx = layer.mask_to_patches(plan, dev, 27, want_idx=True)
+        got = bits.cpu().numpy().view(np.uint32)[:, :23]
+        want = g["bits"][row:row + m["n"]]
+        assert np.array_equal(got, want), (m["h"], m["w"], mask_dtype)
+        on = bits_to_bool(bits)
+        assert np.array_equal(cnt.cpu().numpy(), on.sum(1))
+        idx_np = idx.cpu().numpy()
+        for j in range(m["n"]):
+            assert np.array_equal(idx_np[j, :on[j].sum()], np.flatnonzero(on[j]))
+        row += m["n"]
+
+
+def test_patch_bits_pad_mode_and_strided_masks(dev):
+    masks = synth.masks_blob(3, 2, 3, 480, 854)
+    want = np.stack([R.mask_to_patches(m, pad_square=True) for m in masks])
+    plan = packer.build_plan([torch.from_numpy(masks).to(dev)], [[list(range(6))]], 6, 1, dev, pad_square=True)
+    bits, _, _ = layer.mask_to_patches(plan, dev)
+    assert np.array_equal(bits_to_bool(bits), want)
+    # a non-contiguous view (row pitch != W) is read in place
+    big = torch.zeros((6, 480, 1000), dtype=torch.uint8, device=dev)
+    big[:, :, 100:954] = torch.from_numpy(masks).to(dev)
+    view = big[:, :, 100:954]
+    plan = packer.build_plan([view], [[list(range(6))]], 6, 1, dev)
+    bits, _, _ = layer.mask_to_patches(plan, dev)
+    assert np.array_equal(bits_to_bool(bits), np.stack([R.mask_to_patches(m) for m in masks]))
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel 2
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [c[0] for c in gc.POOL_CASES])
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+def test_pool_bit_exact_vs_oracle_and_close_to_reference(dev, golden_dir, name, dtype):
+    g = np.load(os.path.join(golden_dir, "pool.npz"))
+    feats, masks, rows = gc.pool_inputs(name)
+    feats_r = R.round_to(feats, dtype)
+    ft = torch.from_numpy(feats_r).to(dev).to(TORCH_DT[dtype])
+    n_obj = len(rows) // feats.shape[0]
+    ann = [[rows[o * feats.shape[0]:(o + 1) * feats.shape[0]].tolist() for o in range(n_obj)]]
+    plan = packer.build_plan([torch.from_numpy(masks).to(dev)], ann, feats.shape[0], 1, dev)
+    bits, cnt, _ = layer.mask_to_patches(plan, dev)
+    pooled = layer.mask_pool(ft, plan, bits, cnt).cpu().numpy()
+    on = np.stack([R.mask_to_patches(m) for m in masks])
+    want = R.mask_pool(feats_r, rows, on)
+    assert np.array_equal(pooled, want), np.abs(pooled - want).max()      # canonical order: bit-exact
+    if dtype == "f32":
+        assert np.abs(pooled - g[name]).max() <= 1e-5                     # vs the real reference
+    assert (pooled[~on.any(1)] == 0).all()
+
+
+def test_mask_pooling_module_matches_reference_signature(dev, golden_dir):
+    """MaskPooling.forward(x NCHW-view, mask [1,q,H,W]) exactly as layer.py:101,108 calls it."""
+    g = np.load(os.path.join(golden_dir, "pool.npz"))
+    feats, masks, rows = gc.pool_inputs("dense384")
+    x = torch.from_numpy(feats).to(dev)[torch.from_numpy(rows).to(dev)]
+    x = x.reshape(x.shape[0], 27, 27, -1).permute(0, 3, 1, 2)
+    out = MaskPooling()(x, torch.from_numpy(masks).to(dev).float().unsqueeze(0))
+    assert np.abs(out.cpu().numpy() - g["dense384"]).max() <= 1e-5
+
+
+def test_pool_many_objects_on_one_frame(dev):
+    """17 objects on one frame -> groups of 8, 8, 1 share the frame (PixRQA broadcast shape)."""
+    feats = synth.features(77, 1)
+    masks = synth.masks_blob(78, 17, 1, 100, 120)
+    plan = packer.build_plan([torch.from_numpy(masks).to(dev)], [[[0]]], 1, 4, dev)
+    assert plan.n_groups == 3 and plan.max_group == 8
+    bits, cnt, _ = layer.mask_to_patches(plan, dev)
+    pooled = layer.mask_pool(torch.from_numpy(feats).to(dev), plan, bits, cnt).cpu().numpy()
+    on = np.stack([R.mask_to_patches(m) for m in masks])
+    assert np.array_equal(pooled, R.mask_pool(feats, [0] * 17, on))
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel 3
+# ---------------------------------------------------------------------------------------------
+def run_ttm(dev, x, k):
+    t = x.shape[0]
+    host = {"obj_start": np.zeros(1, np.int32), "obj_len": np.full(1, t, np.int32),
+            "slot_off": np.zeros(1, np.int32)}
+    plan = packer.EncodePlan(n_masks=t, n_groups=0, max_group=1, n_obj=1, max_len=t, m_pad=min(t, k),
+                             slots=np.full(1, min(t, k), np.int32), host=host)
+    packer._upload(plan, dev)
+    tok, counts, ex = layer.ttm(torch.from_numpy(x).to(dev), plan, k, torch.float32, debug=True)
+    n = int(counts.item())
+    cut = None
+    if t > k:
+        words = ex["cuts"].cpu().numpy().view(np.uint32)[0]
+        cut = ((words[:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(-1)[: t - 1]
+    return ex["tokens_f32"].cpu().numpy(), n, cut, ex["sims"].cpu().numpy()[0, : t - 1]
+
+
+def test_ttm_decisions_bit_exact_vs_reference_golden(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ttm.npz"))
+    meta = json.loads(str(g["meta"]))
+    for idx, m in enumerate(meta):
+        x = gc.ttm_tokens(m["family"], m["t"], m["seed"])
+        tok, n, cut, sims = run_ttm(dev, x, m["k"])
+        ref_cut = np.unpackbits(g[f"case{idx}_cut"])[: m["t"] - 1].astype(bool)
+        assert np.array_equal(cut, ref_cut), m                        # the reference's own decisions
+        assert n == m["rows"]
+        o_tok, o_cut, o_sims = R.token_merge(x, m["k"])
+        assert np.array_equal(sims, o_sims), m                        # canonical order: bit-exact
+        assert np.array_equal(tok[:n], o_tok), m
+        ref_tok = g[f"case{idx}_merged"]
+        mine = tok[:n] if m["full"] else tok[:n, :64]
+        assert np.abs(mine - ref_tok).max() <= 1e-5, m
+
+
+@pytest.mark.parametrize("family", ["static", "walk", "duplicates"])
+def test_ttm_bit_exact_vs_oracle_on_coherent_tokens(dev, family):
+    """Near-tie regimes where ATen's own decisions depend on its reduction order:
+    the CUDA kernel and the oracle share one canonical order, so they still agree bit-for-bit."""
+    g = synth.rng_for(5150)
+    for t, k in [(16, 8), (32, 4), (256, 8), (300, 1)]:
+        base = g.standard_normal(1152, dtype=np.float32)
+        if family == "static":
+            x = base + 1e-3 * g.standard_normal((t, 1152), dtype=np.float32)
+        elif family == "walk":
+            x = base + np.cumsum(0.05 * g.standard_normal((t, 1152), dtype=np.float32), 0)
+        else:
+            x = np.repeat(g.standard_normal((t // 4 + 1, 1152), dtype=np.float32), 4, 0)[:t]
+        x = x.astype(np.float32)
+        tok, n, cut, sims = run_ttm(dev, x, k)
+        o_tok, o_cut, o_sims = R.token_merge(x, k)
+        assert np.array_equal(sims, o_sims) and np.array_equal(cut, o_cut)
+        assert n == o_tok.shape[0] and np.array_equal(tok[:n], o_tok)
+
+
+def test_token_merge_function_matches_reference_signature(dev):
+    x = gc.ttm_tokens("random", 16, 40003)
+    out = token_merge(torch.from_numpy(x).to(dev)[None], 8)            # r = tokens to remove
+    want, _, _ = R.token_merge(x, 8)
+    assert out.shape == (1, 8, 1152) and np.array_equal(out[0].cpu().numpy(), want)
+    zeros = token_merge(torch.zeros((1, 20, 1152), device=dev), 12)    # all sims tie -> one token
+    assert zeros.shape == (1, 1, 1152)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel 4
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+@pytest.mark.parametrize("m", [1, 8, 127, 128, 200, 256, 300])
+def test_linear_matches_torch(dev, dtype, m):
+    g = synth.rng_for(m * 7 + 1)
+    dt = TORCH_DT[dtype]
+    w1, b1, w2, b2 = [torch.from_numpy(a).to(dev).to(dt) for a in synth.make_weights(3)]
+    x = torch.from_numpy(g.standard_normal((m, 1152), dtype=np.float32) * 0.05).to(dev).to(dt)
+    h = layer.linear(x, w1, b1, gelu=True)
+    y = layer.linear(h, w2, b2, gelu=False)
+    ref_h = torch.nn.functional.gelu(torch.nn.functional.linear(x.float(), w1.float(), b1.float()).to(dt).float()).to(dt)
+    ref_y = torch.nn.functional.linear(h.float(), w2.float(), b2.float())
+    torch.cuda.synchronize()
+    assert (h.float() - ref_h.float()).abs().max().item() <= TOL[dtype]
+    assert (y.float() - ref_y).abs().max().item() <= TOL[dtype]
+
+
+def test_linear_large_m_all_tile_shapes(dev):
+    for m in (1024, 4096):                       # switches the N tile to 64 / 128
+        x = (torch.randn((m, 1152), device=dev) * 0.05).bfloat16()
+        w = (torch.randn((3584, 1152), device=dev) * 0.03).bfloat16()
+        b = (torch.randn((3584,), device=dev) * 0.03).bfloat16()
+        y = layer.linear(x, w, b)
+        ref = torch.nn.functional.linear(x.float(), w.float(), b.float())
+        assert (y.float() - ref).abs().max().item() <= 1e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# whole path
+# ---------------------------------------------------------------------------------------------
+def to_dev_masks(case, dev):
+    masks = [torch.from_numpy(m).to(dev).float() for m in case["masks"]]
+    return torch.stack(masks) if case["masks_as_tensor"] else masks
+
+
+@pytest.mark.parametrize("name", gc.E2E_NAMES)
+def test_forward_matches_reference_module_golden(dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"e2e_{name}.npz"))
+    case = gc.e2e_case(name)
+    dt = case["dtype"]
+    enc = make_encoder(dev, dt, case["k"], case["aspect"])
+    feats = torch.from_numpy(case["feats"]).to(dev).to(TORCH_DT[dt])
+    tokens, counts = enc(feats, to_dev_masks(case, dev), feats, case["ann"], None)
+    assert counts == list(g["counts"])                                  # region_token_nums: exact
+    assert tokens.dtype == TORCH_DT[dt] and tuple(tokens.shape) == g["tokens"].shape
+    assert np.abs(enc._debug["pooled"].cpu().numpy() - g["pooled"]).max() <= 1e-5
+    assert np.abs(tokens.float().cpu().numpy() - g["tokens"]).max() <= TOL[dt]
+    # and bit-exact against the oracle up to the projector input
+    w = tuple(R.round_to(a, dt) for a in synth.make_weights(0))
+    o = R.encode(R.round_to(case["feats"], dt), case["masks"], case["ann"], case["k"], dt, w,
+                 pad_square=case["aspect"] == "pad")
+    assert np.array_equal(enc._debug["pooled"].cpu().numpy(), o["pooled"])
+    if counts == list(enc.last_plan.slots):
+        assert np.array_equal(enc._debug["merged"].float().cpu().numpy(), o["merged"])
+    assert np.abs(tokens.float().cpu().numpy() - o["tokens"]).max() <= TOL[dt]
+
+
+def test_list_and_tensor_mask_forms_agree(dev):
+    case = gc.e2e_case("c1")
+    enc = make_encoder(dev, "f32", 8)
+    feats = torch.from_numpy(case["feats"]).to(dev)
+    m = torch.from_numpy(case["masks"][0]).to(dev)
+    a, na = enc(feats, [m], feats, case["ann"], None)
+    b, nb = enc(feats, m.float().unsqueeze(0), feats, case["ann"], None)
+    assert na == nb and torch.equal(a, b)
+
+
+def test_ties_compact_the_padded_rows(dev):
+    """Identical frames -> every similarity ties -> one token per object, rows compacted."""
+    feats = synth.features(9, 1).repeat(6, 0)
+    masks = np.ones((6, 27, 27), np.uint8)
+    enc = make_encoder(dev, "f32", 4)
+    tokens, counts = enc(torch.from_numpy(feats).to(dev), [torch.from_numpy(masks).to(dev)],
+                         None, [[[0, 1, 2, 3, 4, 5]]], None)
+    assert counts == [1] and tokens.shape[0] == 1
+
+
+def test_c2_shape_properties_bf16(dev):
+    """BASELINE configs[1] at full size (8 clips x 16 frames x 4 objects, bf16): size-independent
+    properties instead of an oracle run."""
+    feats, masks, ann = synth.make_batch(8, 16, 4, "dense")
+    enc = make_encoder(dev, "bf16", 8)
+    ft = torch.from_numpy(feats).to(dev).bfloat16()
+    md = [torch.from_numpy(m).to(dev) for m in masks]
+    tokens, counts = enc(ft, md, None, ann, None)
+    assert counts == [8] * 32 and tuple(tokens.shape) == (256, 3584)
+    assert torch.isfinite(tokens.float()).all()
+    # sharding invariance: each clip alone gives bit-identical rows
+    for i in (0, 5):
+        ann_i = [[[r - i * 16 for r in o] for o in ann[i]]]
+        t_i, c_i = enc(ft[i * 16:(i + 1) * 16], [md[i]], None, ann_i, None)
+        assert torch.equal(t_i, tokens[i * 32:(i + 1) * 32]) and c_i == [8] * 4
+    # pooling a constant feature map returns the constant exactly; all-on mask = plain mean
+    const = torch.full_like(ft, 0.5)
+    enc(const, md, None, ann, None)
+    assert (enc._debug["pooled"] == 0.5).all()
+    # spot-check pooled rows of one clip against the oracle (bit-exact)
+    on = np.stack([R.mask_to_patches(m) for m in masks[3]])
+    rows = [r for o in ann[3] for r in o]
+    enc(ft, md, None, ann, None)
+    want = R.mask_pool(R.round_to(feats, "bf16"), rows, on)
+    got = enc._debug["pooled"][3 * 64:4 * 64].cpu().numpy()
+    assert np.array_equal(got, want)

@@ -1,0 +1,98 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+the tap-table helper equals the oracle, and the packer restates the reference's bookkeeping."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from ufvideo_b200 import _cabi, packer, synth
+
+CPU = torch.device("cpu")
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    header = open(_cabi.HEADER).read()
+    declared = set(re.findall(r"\b(ufv_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.EXPORTED), declared ^ set(_cabi.EXPORTED)
+    lib = _cabi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ufv_abi_version() == _cabi.ABI_VERSION
+
+
+def test_argument_errors_are_reported_not_crashed():
+    lib = _cabi.lib()
+    assert lib.ufv_tap_table(0, 5, 27, 0, None) == -1            # UFV_E_NULL
+    buf = np.zeros(4 * 27, np.int32)
+    assert lib.ufv_tap_table(0, 5, 27, 0, buf.ctypes.data) == -2  # UFV_E_SHAPE
+    assert b"out of range" in lib.ufv_last_error()
+    with pytest.raises(_cabi.UfvError):
+        _cabi.check(lib.ufv_linear(None, None, None, None, 4, 8, 8, 1, 0, None))
+
+
+@pytest.mark.parametrize("hw", [(384, 384), (720, 1280), (480, 854), (100, 37), (27, 27), (81, 81),
+                                (54, 54), (13, 13), (1, 1), (2, 500), (1080, 1920)])
+@pytest.mark.parametrize("pad", [False, True])
+def test_tap_table_equals_oracle(hw, pad):
+    h, w = hw
+    t = packer.tap_table(h, w, 27, pad).reshape(4, 27)
+    side, top, left = R.pad_to_square_offsets(h, w) if pad else (None, 0, 0)
+    eh, ew = (side, side) if pad else (h, w)
+    h0, h1, u0, u1 = R.axis_taps(eh)
+    w0, w1, v0, v1 = R.axis_taps(ew)
+
+    def fold(i, use, off, ext):
+        s = i - off
+        return np.where(use & (s >= 0) & (s < ext), s, -1)
+
+    want = np.stack([fold(h0, u0, top, h), fold(h1, u1, top, h), fold(w0, v0, left, w), fold(w1, v1, left, w)])
+    assert np.array_equal(t, want)
+
+
+def test_plan_groups_objects_by_frame_and_reserves_token_slots():
+    masks = [torch.zeros((7, 20, 30), dtype=torch.uint8), torch.zeros((3, 40, 40))]
+    ann = [[[0, 1, 2], [2, 3], [1, 1]], [[4, 5, 6]]]
+    plan = packer.build_plan(masks, ann, 7, 2, CPU)
+    h = plan.host
+    assert plan.n_masks == 10 and plan.n_obj == 4 and plan.max_len == 3
+    assert h["obj_start"].tolist() == [0, 3, 5, 7] and h["obj_len"].tolist() == [3, 2, 2, 3]
+    assert plan.slots.tolist() == [2, 2, 2, 2] and h["slot_off"].tolist() == [0, 2, 4, 6] and plan.m_pad == 8
+    # groups: one per distinct feature row, members = object-frames reading it
+    rows = [0, 1, 2, 2, 3, 1, 1, 4, 5, 6]
+    got = {int(r): sorted(h["grp_member"][a:b].tolist())
+           for r, a, b in zip(h["grp_row"], h["grp_off"][:-1], h["grp_off"][1:])}
+    want = {r: [j for j, x in enumerate(rows) if x == r] for r in set(rows)}
+    assert got == want and plan.max_group == 3
+    assert h["mask_shape"].tolist() == [0] * 7 + [1] * 3
+    assert h["shape_tab"].reshape(-1, 4)[:, 1].tolist() == [_cabi.UFV_U8, _cabi.UFV_F32]
+    e0 = masks[0].data_ptr() + np.arange(7) * 600
+    assert np.array_equal(h["mask_addr"][:7], e0.astype(np.uint64))
+
+
+def test_plan_splits_frames_with_many_objects():
+    masks = [torch.zeros((19, 8, 8), dtype=torch.uint8)]
+    plan = packer.build_plan(masks, [[[0]]], 1, 4, CPU)          # PixRQA broadcast: one feature row
+    assert plan.n_groups == 3 and plan.max_group == 8
+    assert np.diff(plan.host["grp_off"]).tolist() == [8, 8, 3]
+    assert plan.host["obj_len"].tolist() == [1] and plan.m_pad == 1
+
+
+def test_plan_edge_cases():
+    empty = packer.build_plan([torch.zeros((0, 50, 50))], [[[1]]], 2, 4, CPU)   # layer.py:73-75
+    assert empty.n_masks == 1 and empty.host["shape_tab"][:2].tolist() == [336, _cabi.UFV_U8]
+    with pytest.raises(ValueError):
+        packer.build_plan([torch.zeros((3, 8, 8))], [[[0, 1]]], 2, 4, CPU)
+    with pytest.raises(IndexError):
+        packer.build_plan([torch.zeros((1, 8, 8))], [[[5]]], 2, 4, CPU)
+    none = packer.build_plan([], [], 0, 4, CPU)
+    assert none.n_masks == 0 and none.m_pad == 0
+
+
+def test_synth_is_deterministic_and_sharding_invariant():
+    f_all, m_all, a_all = synth.make_batch(3, 4, 2, "blob", 64, 64)
+    f1, m1, a1 = synth.make_batch(1, 4, 2, "blob", 64, 64, first_clip=1)
+    assert np.array_equal(f_all[4:8], f1) and np.array_equal(m_all[1], m1[0])
+    assert a_all[1] == [[r + 4 for r in o] for o in a1[0]]

@@ -1,0 +1,78 @@
+// Error plumbing, the chained whole-path entry point and the row-gather used for compaction.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace ufv {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return static_cast<int>(e);
+}
+
+__global__ void gather_rows_kernel(const uint4* __restrict__ in, const int32_t* __restrict__ row_map,
+                                   uint4* __restrict__ out, int vec_per_row) {
+  const int r = blockIdx.x;
+  const uint4* src = in + size_t(row_map[r]) * vec_per_row;
+  uint4* dst = out + size_t(r) * vec_per_row;
+  for (int i = threadIdx.x; i < vec_per_row; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace ufv
+
+extern "C" int ufv_abi_version(void) { return UFV_ABI_VERSION; }
+
+extern "C" const char* ufv_last_error(void) { return ufv::g_error; }
+
+extern "C" int ufv_gather_rows(const void* in, const int32_t* row_map, void* out, int n_out_rows,
+                               int row_bytes, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(n_out_rows >= 0 && row_bytes > 0 && row_bytes % 16 == 0, UFV_E_SHAPE,
+              "ufv_gather_rows: n_out_rows=%d row_bytes=%d", n_out_rows, row_bytes);
+  if (n_out_rows == 0) return 0;
+  UFV_REQUIRE(in && row_map && out, UFV_E_NULL, "ufv_gather_rows: null pointer");
+  UFV_REQUIRE(aligned16(in) && aligned16(out), UFV_E_ALIGN, "ufv_gather_rows: unaligned buffer");
+  gather_rows_kernel<<<n_out_rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(in), row_map, static_cast<uint4*>(out), row_bytes / 16);
+  return check_launch("ufv_gather_rows");
+}
+
+extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(a != nullptr, UFV_E_NULL, "ufv_encode: args is null");
+  const int side = a->n_patch_side;
+  int rc = ufv_mask_to_patches(a->mask_addr, a->mask_shape, a->shape_tab, a->taps, a->n_masks, side,
+                               a->bits, a->cnt, a->idx, a->idx_pitch, stream);
+  if (rc != 0) return rc;
+  rc = ufv_mask_pool(a->feats, a->feat_dtype, a->n_rows, side * side, a->c, a->bits, a->cnt,
+                     a->grp_row, a->grp_off, a->grp_member, a->n_groups, a->max_group, a->pooled, stream);
+  if (rc != 0) return rc;
+  rc = ufv_ttm(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
+               a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, nullptr, 0, stream);
+  if (rc != 0) return rc;
+  if (a->m_pad == 0) return 0;
+  rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, stream);
+  if (rc != 0) return rc;
+  return ufv_linear(a->hidden, a->w2, a->b2, a->tokens_out, a->m_pad, a->hid, a->hid, a->feat_dtype, 0,
+                    stream);
+}

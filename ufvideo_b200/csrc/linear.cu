@@ -1,0 +1,308 @@
+// Kernel 4: one Linear (+ exact GELU) of the object projector,
+//   y[m, n] = act(x[m, k] . w[n, k]^T + bias[n])
+// Replaces nn.Linear / nn.GELU of feat_linear (reference ufvideo/model/layer.py:55-59,126).
+//
+// bf16 / fp16: tcgen05 tensor-core GEMM.  x and w are both K-major, so a 128 x BN output tile
+// is D[tmem] = A[smem] . B[smem]^T with A = 128 rows of x, B = BN rows of w.  Warp roles:
+//   warp 0   TMA producer: 128B-swizzled 2-D tensor-map loads of the A / B k-blocks into a
+//            ring of shared-memory stages (mbarrier full / empty pairs)
+//   warp 1   allocates TMEM; one elected lane issues tcgen05.mma (UMMA 128 x BN x 16, fp32
+//            accumulate in TMEM) and commits stage release / accumulator-ready barriers
+//   warps 2-5  epilogue: tcgen05.ld the accumulator (thread = row), + bias, round to the model
+//            dtype, GELU(erf), round, 16-byte stores
+// fp32: CUDA-core tiled GEMM (the 1e-5 fp32 tolerance rules out bf16/tf32 tensor-core inputs).
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace ufv {
+
+int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows, uint32_t box_cols, int swizzle128);
+
+__device__ __forceinline__ float gelu_erf(float v) {
+  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+}
+
+// ================================= tcgen05 path ===================================================
+constexpr int kBM = 128;
+constexpr int kBK = 64;             // 64 x 2 B = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStages = BN <= 64 ? 8 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 format, version 1):
+// rows are 128 B apart inside an 8-row swizzle atom, atoms are 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);       // start address, 16-byte units
+  d |= uint64_t(1) << 16;                            // leading byte offset (unused for SW128 K-major)
+  d |= uint64_t(1024 >> 4) << 32;                    // stride byte offset
+  d |= uint64_t(1) << 46;                            // descriptor version (sm_100)
+  d |= uint64_t(2) << 61;                            // layout: SWIZZLE_128B
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int a_fmt, int bn) {
+  return (1u << 4)                      // accumulator format: F32
+         | (uint32_t(a_fmt) << 7)       // A format: 0 = F16, 1 = BF16
+         | (uint32_t(a_fmt) << 10)      // B format
+         | (uint32_t(bn >> 3) << 17)    // N
+         | (uint32_t(kBM >> 4) << 24);  // M
+}
+
+template <typename T> struct Pack8;
+template <> struct Pack8<__nv_bfloat16> {
+  __device__ static uint32_t two(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <> struct Pack8<__half> {
+  __device__ static uint32_t two(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+template <typename T, int BN, bool GELU>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t dyn_smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 1023) &
+                                              ~uintptr_t(1023));   // SW128 atoms need 1024-B alignment
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_bias[BN];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBM;
+  const int num_kb = (k + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(&s_tmem_base, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < BN; i += kGemmThreads - 64)
+      s_bias[i] = (n0 + i) < n ? Elem<T>::to_f32(bias[n0 + i]) : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -----------------------------------------------
+    if (elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* a_dst = tiles + size_t(s) * Cfg::kStageBytes;
+        uint8_t* b_dst = a_dst + Cfg::kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        tma_load_2d(a_dst, &tmap_x, kb * kBK, m0, &full_bar[s]);
+        tma_load_2d(b_dst, &tmap_w, kb * kBK, n0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(Elem<T>::kDtype == UFV_BF16 ? 1 : 0, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(tiles + size_t(s) * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+          const uint64_t da = smem_desc_sw128(a_addr + kk * kUmmaK * 2);
+          const uint64_t db = smem_desc_sw128(b_addr + kk * kUmmaK * 2);
+          umma_f16(tmem_base, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);   // stage reusable once these MMAs have read it
+      }
+      umma_commit(&acc_bar);          // accumulator complete
+    }
+  } else {
+    // ------------------------------- epilogue warps -------------------------------------------------
+    const int quarter = warp & 3;     // TMEM lanes a warp may read: 32 * (warp_id % 4) ..
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after_sync();
+    const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int col0 = 0; col0 < BN; col0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(col0), v);
+      tmem_ld_wait();
+      if (row < m) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a = __uint_as_float(v[i]) + s_bias[col0 + i];
+          float b = __uint_as_float(v[i + 1]) + s_bias[col0 + i + 1];
+          if (GELU) {   // the reference rounds to the model dtype before and after GELU
+            a = gelu_erf(Elem<T>::to_f32(Elem<T>::from_f32(a)));
+            b = gelu_erf(Elem<T>::to_f32(Elem<T>::from_f32(b)));
+          }
+          packed[i >> 1] = Pack8<T>::two(a, b);
+        }
+        T* dst = y + size_t(row) * n + n0 + col0;
+        if (n0 + col0 + 32 <= n) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(dst)[i] =
+                make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        } else {
+          for (int i = 0; i < 32 && n0 + col0 + i < n; ++i)
+            dst[i] = reinterpret_cast<const T*>(packed)[i];
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <typename T, int BN>
+static int launch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+                     int gelu, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tx, tw;
+  int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
+  if (rc != 0) return rc;
+  rc = make_tensor_map_2d(&tw, w, Elem<T>::kDtype, uint64_t(n), uint64_t(k), BN, kBK, 1);
+  if (rc != 0) return rc;
+  const dim3 grid((n + BN - 1) / BN, (m + kBM - 1) / kBM);
+  if (gelu) {
+    auto kernel = linear_tc_kernel<T, BN, true>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    kernel<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tx, tw, static_cast<const T*>(bias),
+                                                       static_cast<T*>(y), m, n, k);
+  } else {
+    auto kernel = linear_tc_kernel<T, BN, false>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    kernel<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tx, tw, static_cast<const T*>(bias),
+                                                       static_cast<T*>(y), m, n, k);
+  }
+  return check_launch("ufv_linear (tcgen05)");
+}
+
+template <typename T>
+static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+                       int gelu, cudaStream_t stream) {
+  // Small token counts leave few 128-row tiles: narrow N tiles keep more of the 148 SMs busy.
+  const int m_tiles = (m + kBM - 1) / kBM;
+  if (m_tiles * ((n + 127) / 128) >= 148) return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, stream);
+  if (m_tiles * ((n + 63) / 64) >= 148) return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, stream);
+  return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, stream);
+}
+
+// ================================= fp32 CUDA-core path ============================================
+constexpr int kSBM = 32, kSBN = 64, kSBK = 32, kSimtThreads = 256;
+
+template <bool GELU>
+__global__ void __launch_bounds__(kSimtThreads)
+linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ y, int m, int n, int k) {
+  __shared__ float sx[kSBK][kSBM + 1];
+  __shared__ float sw[kSBK][kSBN + 1];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * kSBM, n0 = blockIdx.x * kSBN;
+  const int tr = tid / 16, tc = tid % 16;   // thread tile: rows tr*2.., cols tc*4..
+  float acc[2][4] = {};
+  for (int k0 = 0; k0 < k; k0 += kSBK) {
+    for (int i = tid; i < kSBM * kSBK; i += kSimtThreads) {
+      const int r = i / kSBK, kk = i % kSBK;
+      sx[kk][r] = (m0 + r < m && k0 + kk < k) ? x[size_t(m0 + r) * k + k0 + kk] : 0.f;
+    }
+    for (int i = tid; i < kSBN * kSBK; i += kSimtThreads) {
+      const int r = i / kSBK, kk = i % kSBK;
+      sw[kk][r] = (n0 + r < n && k0 + kk < k) ? w[size_t(n0 + r) * k + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSBK; ++kk) {
+      float a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = sx[kk][tr * 2 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sw[kk][tc * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = m0 + tr * 2 + i;
+    if (row >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tc * 4 + j;
+      if (col >= n) continue;
+      float v = acc[i][j] + bias[col];
+      if (GELU) v = gelu_erf(v);
+      y[size_t(row) * n + col] = v;
+    }
+  }
+}
+
+}  // namespace ufv
+
+extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+                          int dtype, int gelu, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(m >= 0 && n >= 1 && k >= 1, UFV_E_SHAPE, "ufv_linear: m=%d n=%d k=%d", m, n, k);
+  if (m == 0) return 0;
+  UFV_REQUIRE(x && w && bias && y, UFV_E_NULL, "ufv_linear: null pointer");
+  UFV_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), UFV_E_ALIGN,
+              "ufv_linear: x / w / y must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == UFV_F32) {
+    const dim3 grid((n + kSBN - 1) / kSBN, (m + kSBM - 1) / kSBM);
+    if (gelu)
+      linear_f32_kernel<true><<<grid, kSimtThreads, 0, st>>>(
+          static_cast<const float*>(x), static_cast<const float*>(w), static_cast<const float*>(bias),
+          static_cast<float*>(y), m, n, k);
+    else
+      linear_f32_kernel<false><<<grid, kSimtThreads, 0, st>>>(
+          static_cast<const float*>(x), static_cast<const float*>(w), static_cast<const float*>(bias),
+          static_cast<float*>(y), m, n, k);
+    return check_launch("ufv_linear (fp32)");
+  }
+  UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "ufv_linear: unsupported dtype %d", dtype);
+  UFV_REQUIRE(k % 8 == 0 && n % 8 == 0, UFV_E_SHAPE, "ufv_linear: k=%d and n=%d must be multiples of 8", k, n);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, st);
+  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, st);
+}

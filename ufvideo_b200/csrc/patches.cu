@@ -1,0 +1,164 @@
+// Kernel 1: mask resize + binarise -> per object-frame patch bitmask, count and index list.
+//
+// Replaces F.interpolate(mask, (27, 27), 'bilinear', align_corners=False) followed by
+// (mask > 0) and mask.sum (reference ufvideo/model/layer.py:139,143,145).  With non-negative
+// masks the interpolated value is a sum of non-negative weight * value products, so
+// "interp > 0" is the OR of the (at most four) taps whose weight is non-zero: integer-exact,
+// and only 4 * n_out^2 mask elements are read instead of H * W.
+#include "common.cuh"
+
+#include <cmath>
+
+namespace ufv {
+
+// ---- host: tap table ------------------------------------------------------------------------------
+// fp32 arithmetic in the same order ATen uses (area_pixel_compute_source_index, then
+// guard_index_and_lambda): scale = in / out; src = max(scale * (i + 0.5) - 0.5, 0);
+// i0 = min(floor(src), in - 1); lambda1 = clamp(src - i0, 0, 1); lambda0 = 1 - lambda1;
+// i1 = i0 + (i0 < in - 1).  A tap is kept iff its lambda is > 0.
+static void axis_taps(int n_in, int n_out, int32_t* t0, int32_t* t1) {
+  const volatile float scale = static_cast<float>(n_in) / static_cast<float>(n_out);
+  for (int i = 0; i < n_out; ++i) {
+    volatile float a = static_cast<float>(i) + 0.5f;   // volatile: no fma contraction, no x87 excess
+    volatile float b = scale * a;
+    volatile float src = b - 0.5f;
+    if (src < 0.0f) src = 0.0f;
+    int i0 = static_cast<int>(floorf(src));
+    if (i0 > n_in - 1) i0 = n_in - 1;
+    volatile float lam1 = src - static_cast<float>(i0);
+    if (lam1 < 0.0f) lam1 = 0.0f;
+    if (lam1 > 1.0f) lam1 = 1.0f;
+    volatile float lam0 = 1.0f - lam1;
+    const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    t0[i] = lam0 > 0.0f ? i0 : -1;
+    t1[i] = lam1 > 0.0f ? i1 : -1;
+  }
+}
+
+static void shift_into_image(int32_t* t, int n, int offset, int extent) {
+  for (int i = 0; i < n; ++i) {
+    if (t[i] < 0) continue;
+    const int s = t[i] - offset;
+    t[i] = (s >= 0 && s < extent) ? s : -1;   // taps that land in the zero padding read zero
+  }
+}
+
+// ---- device ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mask_positive(uint64_t base, int64_t off, int dtype) {
+  switch (dtype) {
+    case UFV_U8:
+      return reinterpret_cast<const uint8_t*>(base)[off] != 0;
+    case UFV_F32:
+      return reinterpret_cast<const float*>(base)[off] > 0.0f;
+    case UFV_BF16:
+      return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off]) > 0.0f;
+    default:
+      return __half2float(reinterpret_cast<const __half*>(base)[off]) > 0.0f;
+  }
+}
+
+constexpr int kPatchThreads = 256;
+
+__global__ void __launch_bounds__(kPatchThreads)
+mask_to_patches_kernel(const uint64_t* __restrict__ mask_addr, const int32_t* __restrict__ mask_shape,
+                       const int32_t* __restrict__ shape_tab, const int32_t* __restrict__ taps,
+                       int n_out, uint32_t* __restrict__ bits_out, int32_t* __restrict__ cnt_out,
+                       uint16_t* __restrict__ idx_out, int idx_pitch) {
+  __shared__ int32_t s_taps[4 * UFV_MAX_PATCH_SIDE];
+  __shared__ uint32_t s_words[UFV_BITS_WORDS];
+  __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
+
+  const int j = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int shape = mask_shape[j];
+  const int pitch = shape_tab[4 * shape + 0];
+  const int dtype = shape_tab[4 * shape + 1];
+  const int tap_off = shape_tab[4 * shape + 2];
+  const uint64_t base = mask_addr[j];
+  if (tid < 4 * n_out) s_taps[tid] = taps[tap_off + tid];
+  __syncthreads();
+
+  const int n_patch = n_out * n_out;
+  const int32_t* h0 = s_taps;
+  const int32_t* h1 = s_taps + n_out;
+  const int32_t* w0 = s_taps + 2 * n_out;
+  const int32_t* w1 = s_taps + 3 * n_out;
+  for (int first = 0; first < UFV_BITS_WORDS * 32; first += kPatchThreads) {
+    const int p = first + tid;
+    bool on = false;
+    if (p < n_patch) {
+      const int i = p / n_out, jx = p - i * n_out;
+      const int ra = h0[i], rb = h1[i], ca = w0[jx], cb = w1[jx];
+      // all four taps are issued before any is consumed (memory-level parallelism)
+      const bool t00 = (ra >= 0 && ca >= 0) && mask_positive(base, int64_t(ra) * pitch + ca, dtype);
+      const bool t01 = (ra >= 0 && cb >= 0) && mask_positive(base, int64_t(ra) * pitch + cb, dtype);
+      const bool t10 = (rb >= 0 && ca >= 0) && mask_positive(base, int64_t(rb) * pitch + ca, dtype);
+      const bool t11 = (rb >= 0 && cb >= 0) && mask_positive(base, int64_t(rb) * pitch + cb, dtype);
+      on = t00 | t01 | t10 | t11;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if ((tid & 31) == 0) s_words[p >> 5] = word;
+  }
+  __syncthreads();
+  if (tid < 32) {   // exclusive prefix of the per-word popcounts with one warp scan
+    const int mine = tid < UFV_BITS_WORDS ? __popc(s_words[tid]) : 0;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (tid >= d) incl += up;
+    }
+    if (tid < UFV_BITS_WORDS) s_prefix[tid] = incl - mine;
+    if (tid == UFV_BITS_WORDS - 1) s_prefix[UFV_BITS_WORDS] = incl;
+  }
+  __syncthreads();
+  if (tid < UFV_BITS_WORDS) bits_out[size_t(j) * UFV_BITS_WORDS + tid] = s_words[tid];
+  if (tid == 0) cnt_out[j] = s_prefix[UFV_BITS_WORDS];
+  if (idx_out != nullptr) {
+    for (int p = tid; p < n_patch; p += kPatchThreads) {
+      const uint32_t word = s_words[p >> 5];
+      const uint32_t bit = 1u << (p & 31);
+      if (word & bit)
+        idx_out[size_t(j) * idx_pitch + s_prefix[p >> 5] + __popc(word & (bit - 1u))] =
+            static_cast<uint16_t>(p);
+    }
+  }
+}
+
+}  // namespace ufv
+
+extern "C" int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host) {
+  UFV_REQUIRE(taps_host != nullptr, UFV_E_NULL, "ufv_tap_table: taps_host is null");
+  UFV_REQUIRE(h >= 1 && w >= 1 && n_out >= 1 && n_out <= UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
+              "ufv_tap_table: h=%d w=%d n_out=%d out of range", h, w, n_out);
+  int eff_h = h, eff_w = w, top = 0, left = 0;
+  if (pad_square) {   // layer.py:77-86: centred zero padding of the short side
+    const int side = h > w ? h : w;
+    top = (side - h) / 2;
+    left = (side - w) / 2;
+    eff_h = eff_w = side;
+  }
+  ufv::axis_taps(eff_h, n_out, taps_host, taps_host + n_out);
+  ufv::axis_taps(eff_w, n_out, taps_host + 2 * n_out, taps_host + 3 * n_out);
+  if (pad_square) {
+    ufv::shift_into_image(taps_host, 2 * n_out, top, h);
+    ufv::shift_into_image(taps_host + 2 * n_out, 2 * n_out, left, w);
+  }
+  return 0;
+}
+
+extern "C" int ufv_mask_to_patches(const uint64_t* mask_addr, const int32_t* mask_shape,
+                                   const int32_t* shape_tab, const int32_t* taps, int n_masks,
+                                   int n_out, uint32_t* bits_out, int32_t* cnt_out,
+                                   uint16_t* idx_out, int idx_pitch, void* stream) {
+  UFV_REQUIRE(n_masks >= 0 && n_out >= 1 && n_out <= UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
+              "ufv_mask_to_patches: n_masks=%d n_out=%d out of range", n_masks, n_out);
+  if (n_masks == 0) return 0;
+  UFV_REQUIRE(mask_addr && mask_shape && shape_tab && taps && bits_out && cnt_out, UFV_E_NULL,
+              "ufv_mask_to_patches: null pointer");
+  UFV_REQUIRE(idx_out == nullptr || idx_pitch >= n_out * n_out, UFV_E_SHAPE,
+              "ufv_mask_to_patches: idx_pitch %d < %d", idx_pitch, n_out * n_out);
+  ufv::mask_to_patches_kernel<<<n_masks, ufv::kPatchThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      mask_addr, mask_shape, shape_tab, taps, n_out, bits_out, cnt_out, idx_out, idx_pitch);
+  return ufv::check_launch("ufv_mask_to_patches");
+}

@@ -1,0 +1,275 @@
+"""B200-native object (region) encoder: host-side mirror of the reference's
+``ufvideo/model/layer.py``.
+
+Same names, constructor, forward signature, parameter names and return types as the reference
+(``MaskExtractor`` layer.py:50-128, ``MaskPooling`` :131-152, ``token_merge`` :6-33,
+``build_region_encoder`` :155-161), so it drops in at ``videorefer_arch.py:39,92`` (construction)
+and ``videorefer_arch.py:236`` (call).  All arithmetic runs in the hand-written sm_100a kernels
+of ``libufv_b200.so`` through the C ABI in ``include/ufv_b200.h``; PyTorch only owns device
+memory and the stream.  There is no CPU or eager fallback: tensors must end up on a CUDA device
+and the shared library must be built.  Forward / inference only (the backward pass is listed
+under "next" in DESIGN.md).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi, packer
+
+_vp = ctypes.c_void_p
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device: ufvideo_b200 has no CPU path")
+
+
+def _feat_dtype(t: torch.Tensor) -> int:
+    try:
+        return packer.FEAT_DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported feature dtype {t.dtype} (float32, bfloat16, float16)") from None
+
+
+# ------------------------------------------------------------------------------------------------
+# stage-level operators (each one C-ABI call); the parity tests drive these directly
+# ------------------------------------------------------------------------------------------------
+def mask_to_patches(plan: packer.EncodePlan, device, n_out: int = 27, want_idx: bool = False):
+    """Kernel 1.  Returns (bits int32 [q, 24], cnt int32 [q], idx int16 [q, 736] | None)."""
+    q = plan.n_masks
+    bits = torch.empty((q, _cabi.BITS_WORDS), dtype=torch.int32, device=device)
+    cnt = torch.empty((q,), dtype=torch.int32, device=device)
+    idx = torch.zeros((q, 736), dtype=torch.int16, device=device) if want_idx else None
+    d = plan.dev
+    _cabi.check(_cabi.lib().ufv_mask_to_patches(
+        d["mask_addr"], d["mask_shape"], d["shape_tab"], d["taps"], q, n_out, bits.data_ptr(),
+        cnt.data_ptr(), idx.data_ptr() if want_idx else None, 736, _stream_ptr(device)))
+    return bits, cnt, idx
+
+
+def mask_pool(feats: torch.Tensor, plan: packer.EncodePlan, bits: torch.Tensor, cnt: torch.Tensor):
+    """Kernel 2.  feats [F, n_patch, C] -> pooled fp32 [q, C]."""
+    _require_cuda(feats, "feats")
+    f, n_patch, c = feats.shape
+    pooled = torch.empty((plan.n_masks, c), dtype=torch.float32, device=feats.device)
+    d = plan.dev
+    _cabi.check(_cabi.lib().ufv_mask_pool(
+        feats.data_ptr(), _feat_dtype(feats), f, n_patch, c, bits.data_ptr(), cnt.data_ptr(),
+        d["grp_row"], d["grp_off"], d["grp_member"], plan.n_groups, plan.max_group,
+        pooled.data_ptr(), _stream_ptr(feats.device)))
+    return pooled
+
+
+def ttm(pooled: torch.Tensor, plan: packer.EncodePlan, k_keep: int, out_dtype: torch.dtype,
+        debug: bool = False):
+    """Kernel 3.  Returns (tokens [m_pad, C] out_dtype, counts int32 [n_obj], extras dict)."""
+    device = pooled.device
+    c = pooled.shape[1]
+    tokens = torch.empty((plan.m_pad, c), dtype=out_dtype, device=device)
+    counts = torch.empty((plan.n_obj,), dtype=torch.int32, device=device)
+    extras = {}
+    f32 = cuts = sims = None
+    words = (plan.max_len + 31) // 32
+    if debug:
+        f32 = extras["tokens_f32"] = torch.empty((plan.m_pad, c), dtype=torch.float32, device=device)
+        cuts = extras["cuts"] = torch.zeros((plan.n_obj, words), dtype=torch.int32, device=device)
+        sims = extras["sims"] = torch.zeros((plan.n_obj, max(plan.max_len, 1)), dtype=torch.float32,
+                                            device=device)
+    d = plan.dev
+    _cabi.check(_cabi.lib().ufv_ttm(
+        pooled.data_ptr(), c, d["obj_start"], d["obj_len"], d["slot_off"], plan.n_obj, plan.max_len,
+        k_keep, tokens.data_ptr(), packer.FEAT_DTYPES[out_dtype],
+        f32.data_ptr() if debug else None, counts.data_ptr(), cuts.data_ptr() if debug else None,
+        words, sims.data_ptr() if debug else None, max(plan.max_len, 1), _stream_ptr(device)))
+    return tokens, counts, extras
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, gelu: bool = False):
+    """Kernel 4: act(x @ weight.T + bias) in x.dtype (tcgen05 for bf16 / fp16)."""
+    _require_cuda(x, "x")
+    if not (x.dtype == weight.dtype == bias.dtype):
+        raise TypeError(f"linear: dtype mismatch x={x.dtype} weight={weight.dtype} bias={bias.dtype}")
+    x = x.contiguous()
+    m, k = x.shape
+    n = weight.shape[0]
+    y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    _cabi.check(_cabi.lib().ufv_linear(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                       m, n, k, _feat_dtype(x), int(gelu), _stream_ptr(x.device)))
+    return y
+
+
+def gather_rows(x: torch.Tensor, row_map: torch.Tensor):
+    out = torch.empty((row_map.numel(), x.shape[1]), dtype=x.dtype, device=x.device)
+    _cabi.check(_cabi.lib().ufv_gather_rows(x.data_ptr(), row_map.data_ptr(), out.data_ptr(),
+                                            row_map.numel(), x.shape[1] * x.element_size(),
+                                            _stream_ptr(x.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-named API
+# ------------------------------------------------------------------------------------------------
+def token_merge(x: torch.Tensor, r: int) -> torch.Tensor:
+    """Drop-in for the reference's ``token_merge(x, r)`` (layer.py:6-33): x fp32 [1, n, d] on a
+    CUDA device, r = number of tokens to remove; returns [1, k, d], k <= n - r."""
+    _require_cuda(x, "x")
+    if x.dim() != 3 or x.shape[0] != 1:
+        raise ValueError("token_merge expects x of shape [1, n, d] (the reference's own use)")
+    n = x.shape[1]
+    k_keep = n - r
+    if not 1 <= k_keep < n:
+        raise ValueError("r must satisfy 1 <= n - r < n")
+    pooled = x[0].to(torch.float32).contiguous()
+    host = {"obj_start": np.zeros(1, np.int32), "obj_len": np.full(1, n, np.int32),
+            "slot_off": np.zeros(1, np.int32)}
+    plan = packer.EncodePlan(n_masks=n, n_groups=0, max_group=1, n_obj=1, max_len=n, m_pad=k_keep,
+                             slots=np.full(1, k_keep, np.int32), host=host)
+    packer._upload(plan, x.device)
+    tokens, counts, _ = ttm(pooled, plan, k_keep, torch.float32)
+    return tokens[: int(counts.item())].unsqueeze(0).to(x.dtype)
+
+
+class MaskPooling(nn.Module):
+    """Drop-in for the reference's ``MaskPooling`` (layer.py:131-152)."""
+
+    def forward(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """x [b, C, h, w] (the NCHW view the reference builds at layer.py:101, i.e. NHWC storage)
+        and mask [1, q, H, W]  ->  fp32-accurate pooled [max(b, q), C] in x.dtype."""
+        _require_cuda(x, "x")
+        b, c, h, w = x.shape
+        if h != w or h > _cabi.MAX_PATCH_SIDE:
+            raise ValueError(f"patch grid {h}x{w} unsupported (square, side <= {_cabi.MAX_PATCH_SIDE})")
+        nhwc = x.permute(0, 2, 3, 1)
+        feats = (nhwc if nhwc.is_contiguous() else nhwc.contiguous()).reshape(b, h * w, c)
+        if feats.dtype not in packer.FEAT_DTYPES:
+            feats = feats.float()
+        plan = packer.build_plan([mask[0]], [[list(range(b))]], b, 1, x.device, False, h)
+        bits, cnt, _ = mask_to_patches(plan, x.device, h)
+        return mask_pool(feats, plan, bits, cnt).to(x.dtype)
+
+
+class MaskExtractor(nn.Module):
+    """Drop-in for the reference's ``MaskExtractor`` (layer.py:50-128).
+
+    State-dict keys are the reference's (``feat_linear.0.weight`` ...), so UFVideo checkpoints
+    load unchanged (videorefer_arch.py:120-122).  ``region_token_num`` (K) defaults to 4 as in the
+    reference and can be reassigned on the instance.
+    """
+
+    def __init__(self, image_aspect_ratio, config, mask_shape=112, depth=2, region_token_num=4):
+        super().__init__()
+        self.mask_shape = mask_shape              # stored, unused -- as in the reference (layer.py:53)
+        self.mask_pooling = MaskPooling()
+        modules = [nn.Linear(config.mm_hidden_size, config.hidden_size)]
+        for _ in range(1, depth):
+            modules.append(nn.GELU())
+            modules.append(nn.Linear(config.hidden_size, config.hidden_size))
+        self.feat_linear = nn.Sequential(*modules)
+        self.image_aspect_ratio = image_aspect_ratio
+        self.region_token_num = region_token_num
+        self.last_plan = None                     # introspection for tests / bench
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _linears(self):
+        return [m for m in self.feat_linear if isinstance(m, nn.Linear)]
+
+    @torch.no_grad()
+    def encode_padded(self, feats, masks, ann_indices):
+        """Kernels 1-4 without the host read-back: returns (tokens [m_pad, hid], counts int32
+        [n_obj] on the device, plan).  Row r of an object is valid iff r < counts[object]."""
+        linears = self._linears()
+        device = linears[0].weight.device
+        if device.type != "cuda":
+            raise RuntimeError("MaskExtractor parameters must be on a CUDA device (no CPU path)")
+        if not torch.is_tensor(feats):
+            raise TypeError("feats must be a tensor [F, n_patch, C]")
+        if feats.device != device:
+            feats = feats.to(device, non_blocking=True)
+        feats = feats.contiguous()
+        if feats.dim() != 3:
+            raise ValueError(f"feats must be [F, n_patch, C], got {tuple(feats.shape)}")
+        dt = _feat_dtype(feats)
+        if linears[0].weight.dtype != feats.dtype:
+            raise TypeError(f"feature dtype {feats.dtype} != projector dtype {linears[0].weight.dtype}")
+        f, n_patch, c = feats.shape
+        side = int(round(n_patch ** 0.5))         # layer.py:100
+        if side * side != n_patch or side > _cabi.MAX_PATCH_SIDE:
+            raise ValueError(f"n_patch={n_patch} is not a square grid with side <= {_cabi.MAX_PATCH_SIDE}")
+        k_keep = int(self.region_token_num)
+        plan = packer.build_plan(masks, ann_indices, f, k_keep, device,
+                                 self.image_aspect_ratio == "pad", side)
+        self.last_plan = plan
+        hid = linears[-1].weight.shape[0]
+        q, m_pad = plan.n_masks, plan.m_pad
+        bits = torch.empty((q, _cabi.BITS_WORDS), dtype=torch.int32, device=device)
+        cnt = torch.empty((q,), dtype=torch.int32, device=device)
+        pooled = torch.empty((q, c), dtype=torch.float32, device=device)
+        merged = torch.empty((m_pad, c), dtype=feats.dtype, device=device)
+        counts = torch.empty((plan.n_obj,), dtype=torch.int32, device=device)
+        tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
+        d = plan.dev
+        stream = _stream_ptr(device)
+        if len(linears) == 2:                     # the reference's depth=2 projector: one chained call
+            hidden = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
+            a = _cabi.EncodeArgs(
+                feats=feats.data_ptr(), feat_dtype=dt, n_patch_side=side, n_rows=f, c=c, hid=hid,
+                mask_addr=d["mask_addr"], mask_shape=d["mask_shape"], shape_tab=d["shape_tab"],
+                taps=d["taps"], n_masks=q, idx_pitch=0, bits=bits.data_ptr(), cnt=cnt.data_ptr(),
+                idx=None, grp_row=d["grp_row"], grp_off=d["grp_off"], grp_member=d["grp_member"],
+                n_groups=plan.n_groups, max_group=plan.max_group, pooled=pooled.data_ptr(),
+                obj_start=d["obj_start"], obj_len=d["obj_len"], slot_off=d["slot_off"],
+                n_obj=plan.n_obj, max_len=plan.max_len, k_keep=k_keep, m_pad=m_pad,
+                merged=merged.data_ptr(), counts=counts.data_ptr(),
+                w1=linears[0].weight.data_ptr(), b1=linears[0].bias.data_ptr(),
+                w2=linears[1].weight.data_ptr(), b2=linears[1].bias.data_ptr(),
+                hidden=hidden.data_ptr(), tokens_out=tokens.data_ptr())
+            _cabi.check(_cabi.lib().ufv_encode(ctypes.byref(a), stream))
+        else:                                     # other depths: the same kernels, staged
+            lib = _cabi.lib()
+            _cabi.check(lib.ufv_mask_to_patches(d["mask_addr"], d["mask_shape"], d["shape_tab"], d["taps"],
+                                                q, side, bits.data_ptr(), cnt.data_ptr(), None, 0, stream))
+            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, n_patch, c, bits.data_ptr(),
+                                          cnt.data_ptr(), d["grp_row"], d["grp_off"], d["grp_member"],
+                                          plan.n_groups, plan.max_group, pooled.data_ptr(), stream))
+            _cabi.check(lib.ufv_ttm(pooled.data_ptr(), c, d["obj_start"], d["obj_len"], d["slot_off"],
+                                    plan.n_obj, plan.max_len, k_keep, merged.data_ptr(), dt, None,
+                                    counts.data_ptr(), None, 0, None, 0, stream))
+            x = merged
+            for i, lin in enumerate(linears):
+                x = linear(x, lin.weight, lin.bias, gelu=i < len(linears) - 1)
+            tokens = x
+        self._debug = {"bits": bits, "cnt": cnt, "pooled": pooled, "merged": merged}
+        return tokens, counts, plan
+
+    # -- the reference's forward -----------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, feats, masks, X_features, ann_indices, frame_nums):
+        """Same contract as layer.py:63-128: returns (mask_feats [N_tok, hidden], region_token_nums
+        list[int]).  ``X_features`` and ``frame_nums`` are accepted and ignored, as in the reference
+        (which reads only ``X_features.device`` in its fallbacks)."""
+        tokens, counts, plan = self.encode_padded(feats, masks, ann_indices)
+        region_token_nums = counts.cpu().numpy()   # the one unavoidable D2H: the caller slices by it
+        if not np.array_equal(region_token_nums, plan.slots):
+            # ties at the merge threshold left some object with fewer than min(T, K) tokens:
+            # drop the zero-filled slots (rare; exact ties only)
+            starts = plan.host["slot_off"]
+            row_map = np.concatenate([np.arange(s, s + n, dtype=np.int32)
+                                      for s, n in zip(starts, region_token_nums)] or [np.zeros(0, np.int32)])
+            tokens = gather_rows(tokens, torch.from_numpy(row_map).to(tokens.device))
+        return tokens, [int(n) for n in region_token_nums]
+
+
+def build_region_encoder(config, image_aspect_ratio):
+    """Drop-in for layer.py:155-161."""
+    region_encoder_type = getattr(config, "mm_region_encoder_type", "pooling")
+    if region_encoder_type == "pooling":
+        return MaskExtractor(image_aspect_ratio, config)
+    raise ValueError(f"Unknown region encoder type: {region_encoder_type}")

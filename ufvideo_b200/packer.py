@@ -1,0 +1,171 @@
+"""Host-side packer: python ``masks`` / ``ann_indices`` lists -> flat descriptor arrays.
+
+Restates the bookkeeping of the reference's forward loop (ufvideo/model/layer.py:66-119) as data:
+which mask plane pairs with which feature row (layer.py:92-98), which pooled rows belong to
+which object (layer.py:112-119) and where each object's tokens land in the output
+(layer.py:121-125).  Pure integer work on the host; everything is uploaded in one buffer.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_MASK_DTYPES = {torch.uint8: _cabi.UFV_U8, torch.bool: _cabi.UFV_U8, torch.float32: _cabi.UFV_F32,
+                torch.bfloat16: _cabi.UFV_BF16, torch.float16: _cabi.UFV_F16}
+FEAT_DTYPES = {torch.float32: _cabi.UFV_F32, torch.bfloat16: _cabi.UFV_BF16, torch.float16: _cabi.UFV_F16}
+
+_tap_cache: dict = {}
+
+
+def tap_table(h: int, w: int, n_out: int, pad_square: bool) -> np.ndarray:
+    """int32 [4 * n_out] tap table of an h x w mask (ufv_tap_table; replaces ATen's bilinear
+    index computation, layer.py:139, plus the 'pad' mode of layer.py:77-86)."""
+    key = (h, w, n_out, bool(pad_square))
+    hit = _tap_cache.get(key)
+    if hit is None:
+        hit = np.empty(4 * n_out, dtype=np.int32)
+        _cabi.check(_cabi.lib().ufv_tap_table(h, w, n_out, int(pad_square),
+                                              hit.ctypes.data_as(ctypes.c_void_p)))
+        _tap_cache[key] = hit
+    return hit
+
+
+@dataclass
+class EncodePlan:
+    """Everything the kernels need to know about one batch, as host arrays + one device copy."""
+    n_masks: int                 # object-frames q (pooled rows)
+    n_groups: int
+    max_group: int
+    n_obj: int
+    max_len: int
+    m_pad: int                   # token rows reserved: sum over objects of min(T_o, K)
+    slots: np.ndarray            # int32 [n_obj] = min(T_o, K): token count unless the merge ties
+    host: dict = field(default_factory=dict)      # name -> numpy array
+    dev: dict = field(default_factory=dict)       # name -> device pointer (int)
+    buffer: torch.Tensor | None = None            # owns the device memory behind ``dev``
+    keepalive: list = field(default_factory=list)  # mask tensors the descriptors point into
+
+
+def _as_mask_list(masks, device):
+    """Reference contract: list of [q_i, H_i, W_i] tensors, or one
+    [B, q, H, W] tensor whose len() is the sample count."""
+    out = []
+    for i in range(len(masks)):
+        m = masks[i]
+        if not torch.is_tensor(m):
+            m = torch.as_tensor(m)
+        if m.dim() != 3:
+            raise ValueError(f"masks[{i}] must be [q, H, W], got {tuple(m.shape)}")
+        if m.shape[0] == 0:                      # layer.py:73-75: substitute one all-zero mask
+            m = torch.zeros((1, 336, 336), dtype=torch.uint8, device=device)
+        if m.dtype not in _MASK_DTYPES:          # exotic dtypes: binarise once on the device
+            m = (m.to(device) > 0).to(torch.uint8)
+        if m.device != device:
+            m = m.to(device, non_blocking=True)
+        if m.stride(-1) != 1:
+            m = m.contiguous()
+        out.append(m)
+    return out
+
+
+def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_square: bool = False,
+               n_out: int = _cabi.MAX_PATCH_SIDE) -> EncodePlan:
+    masks = _as_mask_list(masks, device)
+    if len(ann_indices) != len(masks):
+        raise ValueError("ann_indices and masks disagree on the number of samples")
+
+    addr, shape_id, rows_all = [], [], []
+    shapes, shape_rows, tap_chunks, tap_len = {}, [], [], 0
+    obj_start, obj_len = [], []
+    base = 0
+    for i, m in enumerate(masks):
+        q, h, w = m.shape
+        esize = m.element_size()
+        key = (h, w, m.dtype, m.stride(1), pad_square)
+        sid = shapes.get(key)
+        if sid is None:
+            sid = shapes[key] = len(shapes)
+            shape_rows.append((m.stride(1), _MASK_DTYPES[m.dtype], tap_len, 0))
+            tap_chunks.append(tap_table(h, w, n_out, pad_square))
+            tap_len += 4 * n_out
+        rows = [int(r) for obj in ann_indices[i] for r in obj]            # layer.py:92-95
+        b = len(rows)
+        planes = np.arange(q, dtype=np.int64)
+        if b != q:                               # torch broadcasting of x * mask, layer.py:147
+            if b == 1:
+                rows = rows * q
+            elif q == 1:
+                planes = np.zeros(b, dtype=np.int64)
+            else:
+                raise ValueError(f"sample {i}: {b} feature rows cannot pair with {q} masks")
+        n_i = len(rows)
+        addr.append(m.data_ptr() + planes * (m.stride(0) * esize))
+        shape_id.append(np.full(n_i, sid, dtype=np.int32))
+        rows_all.append(np.asarray(rows, dtype=np.int64))
+        start = 0
+        for obj in ann_indices[i]:               # running offset over pooled rows, layer.py:112-119
+            t = max(0, min(len(obj), n_i - start))
+            obj_start.append(base + start)
+            obj_len.append(t)
+            start += len(obj)
+        base += n_i
+
+    q_total = base
+    rows_all = np.concatenate(rows_all) if rows_all else np.zeros(0, np.int64)
+    if q_total and (rows_all.min() < 0 or rows_all.max() >= n_feat_rows):
+        raise IndexError(f"ann_indices refer to feature rows outside [0, {n_feat_rows})")
+
+    # groups: object-frames that read the same feature row share one staged copy of it
+    order = np.argsort(rows_all, kind="stable")
+    sorted_rows = rows_all[order]
+    run_start = np.flatnonzero(np.r_[True, sorted_rows[1:] != sorted_rows[:-1]]) if q_total else np.zeros(0, np.int64)
+    run_len = np.diff(np.r_[run_start, q_total])
+    if q_total and run_len.max() > _cabi.MAX_GROUP:
+        pieces = [(s + o, min(_cabi.MAX_GROUP, l - o)) for s, l in zip(run_start, run_len)
+                  for o in range(0, l, _cabi.MAX_GROUP)]
+        run_start = np.array([p[0] for p in pieces], dtype=np.int64)
+        run_len = np.array([p[1] for p in pieces], dtype=np.int64)
+    n_groups = int(run_start.size)
+
+    obj_len_a = np.asarray(obj_len, dtype=np.int32)
+    slots = np.minimum(obj_len_a, k_keep).astype(np.int32)
+    slot_off = np.concatenate([[0], np.cumsum(slots)[:-1]]).astype(np.int32) if slots.size else np.zeros(0, np.int32)
+
+    host = {
+        "mask_addr": (np.concatenate(addr) if addr else np.zeros(0, np.int64)).astype(np.uint64),
+        "mask_shape": np.concatenate(shape_id) if shape_id else np.zeros(0, np.int32),
+        "shape_tab": np.asarray(shape_rows, dtype=np.int32).reshape(-1),
+        "taps": np.concatenate(tap_chunks) if tap_chunks else np.zeros(0, np.int32),
+        "grp_row": sorted_rows[run_start].astype(np.int32) if n_groups else np.zeros(0, np.int32),
+        "grp_off": np.r_[run_start, q_total].astype(np.int32),
+        "grp_member": order.astype(np.int32),
+        "obj_start": np.asarray(obj_start, dtype=np.int32),
+        "obj_len": obj_len_a,
+        "slot_off": slot_off,
+    }
+    plan = EncodePlan(n_masks=q_total, n_groups=n_groups,
+                      max_group=int(run_len.max()) if n_groups else 1,
+                      n_obj=len(obj_len), max_len=int(obj_len_a.max()) if len(obj_len) else 1,
+                      m_pad=int(slots.sum()), slots=slots, host=host, keepalive=masks)
+    _upload(plan, device)
+    return plan
+
+
+def _upload(plan: EncodePlan, device) -> None:
+    """One pinned staging buffer, one H2D copy; every array starts 16-byte aligned."""
+    offsets, total = {}, 0
+    for name, arr in plan.host.items():
+        offsets[name] = total
+        total += (arr.nbytes + 15) // 16 * 16
+    staging = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=device.type == "cuda")
+    view = staging.numpy()
+    for name, arr in plan.host.items():
+        view[offsets[name]:offsets[name] + arr.nbytes] = arr.view(np.uint8).reshape(-1)
+    plan.buffer = staging.to(device, non_blocking=True)
+    p0 = plan.buffer.data_ptr()
+    plan.dev = {name: p0 + off for name, off in offsets.items()}
