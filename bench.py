@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- object-frames/s of the object-encoder hot path (mask-pool + TTM + projector).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path (mask resize/binarise -> mask pool -> temporal token
+merge -> projector) over one batch of BASELINE.json's configs[1]:
+8 clips x 16 frames x 4 objects per GPU, bf16 features [128, 729, 1152], 384x384 float32 masks
+(dense family), K = 8, projector 1152 -> 3584 -> 3584.  Synthetic seeded data (ufvideo_b200/synth.py).
+
+value   device-resident inputs, CUDA events around exactly K steps, max over ranks.
+e2e     the same step through the module's public forward() with HOST (pinned) feats and masks:
+        the H2D of the inputs and the D2H of the projected tokens are inside the timed region.
+roofline  the dominant kernel (segmented mask pool, HBM-bound) timed alone with CUDA events.
+cpu_baseline  the oracle's torch-CPU port of the reference on a bounded sample (rank 0, N=1).
+--impl reference  times that CPU port alone (the reference is Python and cannot travel to the GPU
+        box; oracle/reference_port.py issues the reference's ATen calls op for op).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "object_frames_per_s"
+UNIT = "object-frames/s"
+WORKLOAD = dict(clips_per_gpu=8, frames=16, objects=4, k=8, family="dense", mask_hw=(384, 384))
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=WORKLOAD["clips_per_gpu"])
+    ap.add_argument("--frames", type=int, default=WORKLOAD["frames"])
+    ap.add_argument("--objects", type=int, default=WORKLOAD["objects"])
+    ap.add_argument("--family", default=WORKLOAD["family"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"configs[1]: {a.clips} clips x {a.frames} frames x {a.objects} objects per GPU, bf16, "
+            f"K={WORKLOAD['k']}, projector 1152->3584->3584")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed regions)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.file = None
+
+    def __enter__(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.proc.wait()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.file is None:
+            return out
+        self.file.flush()
+        rows = [r.strip().split(", ") for r in open(self.file.name) if r.strip()]
+        os.unlink(self.file.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.strip().lower() == "active":
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's torch-CPU port of the reference on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(a, steps: int, warmup: int, sample_clips: int = 2, min_seconds: float = 0.0):
+    import torch
+
+    from oracle import reference_port
+    from ufvideo_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    feats, masks, ann = synth.make_batch(sample_clips, a.frames, a.objects, a.family)
+    weights = [torch.from_numpy(w) for w in synth.make_weights(0)]
+    ft = torch.from_numpy(feats)                       # fp32: CPU bf16 kernels are not the reference's CPU path
+    mt = [torch.from_numpy(m).float() for m in masks]
+    q = sum(m.shape[0] for m in masks)
+    with torch.no_grad():
+        for _ in range(warmup):
+            reference_port.encode(ft, mt, ann, WORKLOAD["k"], *weights)
+        t0 = time.perf_counter()
+        done = 0
+        while done < steps or time.perf_counter() - t0 < min_seconds:
+            reference_port.encode(ft, mt, ann, WORKLOAD["k"], *weights)
+            done += 1
+        dt = time.perf_counter() - t0
+    sample = (f"{sample_clips} of the workload's clips ({q} object-frames: {sample_clips} x {a.frames} frames x "
+              f"{a.objects} objects), fp32, {done} timed passes after {warmup} warm-up")
+    return q * done / dt, dt / done, cores, sample, done
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, sec, cores, sample, done = cpu_reference_run(a, a.steps, a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "step": "bounded CPU sample: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from ufvideo_b200 import build_region_encoder, layer, packer, sharding, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device -- the object-encoder path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    k = WORKLOAD["k"]
+    h, w = WORKLOAD["mask_hw"]
+
+    # ---- data: this rank's clips (weak scaling: clips_per_gpu fixed) -----------------------------
+    feats_np, masks_np, ann = synth.make_batch(a.clips, a.frames, a.objects, a.family, h, w,
+                                               first_clip=rank * a.clips)
+    feats_host = torch.from_numpy(feats_np).bfloat16().pin_memory()
+    masks_host = [torch.from_numpy(m).float().pin_memory() for m in masks_np]     # reference contract: float32 0/1
+    feats_dev = feats_host.to(dev)
+    masks_dev = [m.to(dev) for m in masks_host]
+    q = sum(m.shape[0] for m in masks_np)
+    n_obj = sum(len(x) for x in ann)
+
+    enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
+    enc.region_token_num = k
+    with torch.no_grad():
+        for p, wt in zip((enc.feat_linear[0].weight, enc.feat_linear[0].bias,
+                          enc.feat_linear[2].weight, enc.feat_linear[2].bias), synth.make_weights(0)):
+            p.copy_(torch.from_numpy(wt))
+    enc = enc.to(dev).bfloat16()
+    pad_rows, pad_objs = n_obj * k, n_obj
+
+    def collect(tokens, counts):
+        if world > 1:   # the one collective: NCCL all-gather of the per-rank object tokens
+            return sharding.all_gather_tokens(tokens, torch.tensor(counts, dtype=torch.int32, device=dev),
+                                              pad_rows, pad_objs)
+        return tokens
+
+    def step_resident():
+        tokens, counts = enc(feats_dev, masks_dev, None, ann, None)
+        return collect(tokens, counts)
+
+    def step_e2e():
+        tokens, counts = enc(feats_host, masks_host, None, ann, None)       # H2D inside forward
+        out = collect(tokens, counts)
+        return out.cpu()                                                     # D2H of the result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    with ClockSampler(local) as clocks:
+        ms_step = timed(step_resident, a.steps, max(a.warmup, 3))
+        ms_e2e = timed(step_e2e, a.steps, max(a.warmup, 3))
+    clock_summary = clocks.summary()
+
+    # ---- roofline of the dominant kernel: segmented mask pool, timed alone ------------------------
+    plan = packer.build_plan(masks_dev, ann, feats_dev.shape[0], k, dev)
+    bits, cnt, _ = layer.mask_to_patches(plan, dev)
+    union = 0
+    b = bits.cpu().numpy().view(np.uint32)
+    go, gm = plan.host["grp_off"], plan.host["grp_member"]
+    for g in range(plan.n_groups):
+        u = np.bitwise_or.reduce(b[gm[go[g]:go[g + 1]]], axis=0)
+        union += int(np.unpackbits(u.view(np.uint8)).sum())
+    pool_bytes = union * 1152 * 2 + q * 1152 * 4 + q * 96        # feature rows + pooled write + bitmasks
+    pooled = torch.empty((q, 1152), dtype=torch.float32, device=dev)
+    lib_call = lambda: layer.mask_pool(feats_dev, plan, bits, cnt)  # noqa: E731
+    ms_pool = timed(lib_call, max(a.steps, 20), 3)
+    del pooled
+    peak, peak_src = peaks()
+    achieved = pool_bytes / (ms_pool * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "pool_traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        v, sec, cores, sample, done = cpu_reference_run(a, steps=3, warmup=1, min_seconds=10.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    total_q = q * world
+    h2d = feats_host.numel() * 2 + sum(m.numel() * 4 for m in masks_host) + int(plan.buffer.numel())
+    d2h = n_obj * k * 3584 * 2 * (world if world > 1 else 1) + n_obj * 4
+    line = {
+        "metric": METRIC, "value": total_q / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(a), "object_frames_per_step": total_q,
+                   "mask_family": a.family, "mask_dtype": "float32", "mask_hw": [h, w],
+                   "l2": f"inputs larger than L2: {feats_dev.numel() * 2 / 1e6:.0f} MB of features per step vs 126 MB",
+                   "collective": "one NCCL all-gather of object tokens per step" if world > 1 else "none (1 GPU)"},
+        "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+        "gpu_launches": 5 * a.steps,
+        "roofline": {"kernel": "mask_pool_kernel<bf16>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": pool_bytes, "us_per_launch": ms_pool * 1e3,
+                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "clocks": clock_summary,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()
