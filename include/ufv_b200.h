@@ -43,6 +43,17 @@ enum {
 #define UFV_BITS_WORDS 24        /* uint32 words per patch bitmask row (729 bits -> 23, padded) */
 #define UFV_MAX_PATCH_SIDE 27    /* kernels are sized for up to 27 x 27 patches              */
 #define UFV_MAX_GROUP 8          /* object-frames pooled together from one staged frame tile */
+#define UFV_PLAN_PITCH 736       /* entries per group in the union-plan arrays (>= 729, % 16 == 0) */
+
+/* One object-frame's mask plane (32 bytes). */
+typedef struct ufv_mask_desc {
+  uint64_t addr;      /* device address of element (0,0) of the mask plane                     */
+  int32_t pitch;      /* row pitch in elements                                                  */
+  int32_t dtype;      /* UFV_U8 (also bool) / UFV_F32 / UFV_BF16 / UFV_F16                      */
+  int32_t tap_off;    /* offset of the plane's tap table inside `taps`, in int32 units          */
+  int32_t group;      /* pool group this object-frame belongs to (index into grp_off)           */
+  int32_t reserved[2];
+} ufv_mask_desc;
 
 int ufv_abi_version(void);
 const char* ufv_last_error(void);
@@ -59,21 +70,25 @@ const char* ufv_last_error(void);
 int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
 
 /* ---------------------------------------------------------------------------------------------
- * Kernel 1: mask resize + binarise -> patch bitmask, count and index list per object-frame.
+ * Kernel 1: mask resize + binarise -> patch bitmask, count and index list per object-frame,
+ * plus the union plan of every pool group.
  * Replaces F.interpolate + (mask > 0) + mask.sum at layer.py:139,143,145.  Bit-exact.
- *   mask_addr[n_masks]   device address of element (0,0) of each object-frame's mask plane
- *   mask_shape[n_masks]  index into shape_tab
- *   shape_tab[n_shapes*4] {row pitch in elements, element type UFV_*, offset of the shape's tap
- *                         table inside `taps` in int32 units, 0}
+ *   desc[n_masks]        one ufv_mask_desc per object-frame
+ *   taps                 concatenated tap tables (ufv_tap_table) the descriptors point into
  *   bits_out[n_masks*UFV_BITS_WORDS]  bit p%32 of word p/32 = patch p (row-major h,w) is on
  *   cnt_out[n_masks]     number of on patches
  *   idx_out              optional (may be null): [n_masks * idx_pitch] uint16, ascending patch
  *                        indices of the on patches, first cnt entries valid
+ *   group plan (all optional together; pass grp_ticket = null to skip): for group g with members
+ *   grp_member[grp_off[g] .. grp_off[g+1]) the kernel writes grp_nu[g] = number of patches on in
+ *   any member, grp_ulist[g*UFV_PLAN_PITCH ..] = those patches ascending, grp_omask[...] = per
+ *   listed patch the bitmask of members that pool it (tail zero-filled).  grp_ticket[n_groups]
+ *   must be zero on entry and is zero again on completion.
  * -------------------------------------------------------------------------------------------*/
-int ufv_mask_to_patches(const uint64_t* mask_addr, const int32_t* mask_shape,
-                        const int32_t* shape_tab, const int32_t* taps, int n_masks, int n_out,
+int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
                         uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
-                        void* stream);
+                        const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
+                        int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 2: segmented mask pool.  Replaces the gather feats[ann_index], the layout permute,
@@ -81,14 +96,17 @@ int ufv_mask_to_patches(const uint64_t* mask_addr, const int32_t* mask_shape,
  *   feats [n_rows, n_patch, c] of feat_dtype (UFV_F32 / UFV_BF16 / UFV_F16), contiguous
  *   groups: group g pools object-frames grp_member[grp_off[g] .. grp_off[g+1]) (at most
  *           UFV_MAX_GROUP of them), all of which read feature row grp_row[g]; max_group = the
- *           largest group size in this call (selects the 4- or 8-object kernel variant)
+ *           largest group size in this call (selects the 4- or 8-object kernel variant);
+ *           grp_nu / grp_ulist / grp_omask = the union plan written by ufv_mask_to_patches
+ *   cnt[n_masks] on-patch counts from ufv_mask_to_patches
  *   pooled_out fp32 [n_masks, c]:  sum over on patches in ascending patch order, divided by
  *           (float(cnt) + 1e-8f); an all-off mask gives an exact zero row.
  * -------------------------------------------------------------------------------------------*/
 int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, int n_patch, int c,
-                  const uint32_t* bits, const int32_t* cnt, const int32_t* grp_row,
-                  const int32_t* grp_off, const int32_t* grp_member, int n_groups,
-                  int max_group, float* pooled_out, void* stream);
+                  const int32_t* cnt, const int32_t* grp_row, const int32_t* grp_off,
+                  const int32_t* grp_member, const int32_t* grp_nu, const uint16_t* grp_ulist,
+                  const uint8_t* grp_omask, int n_groups, int max_group, float* pooled_out,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 3: fused temporal token merge.  Replaces token_merge (layer.py:6-33), its dispatch
@@ -123,9 +141,9 @@ typedef struct ufv_encode_args {
   /* features */
   const void* feats; int32_t feat_dtype; int32_t n_patch_side; int64_t n_rows; int32_t c; int32_t hid;
   /* masks -> patches */
-  const uint64_t* mask_addr; const int32_t* mask_shape; const int32_t* shape_tab;
-  const int32_t* taps; int32_t n_masks; int32_t idx_pitch;
+  const ufv_mask_desc* mask_desc; const int32_t* taps; int32_t n_masks; int32_t idx_pitch;
   uint32_t* bits; int32_t* cnt; uint16_t* idx;            /* idx optional */
+  uint32_t* grp_ticket; int32_t* grp_nu; uint16_t* grp_ulist; uint8_t* grp_omask;
   /* pool */
   const int32_t* grp_row; const int32_t* grp_off; const int32_t* grp_member; int32_t n_groups;
   int32_t max_group;

@@ -43,6 +43,7 @@ def make_encoder(dev, dtype="f32", k=8, aspect="square", weights=None, c=1152, h
         for p, a in zip((enc.feat_linear[0].weight, enc.feat_linear[0].bias,
                          enc.feat_linear[2].weight, enc.feat_linear[2].bias), w):
             p.copy_(torch.from_numpy(a))
+    enc.keep_debug = True
     return enc.to(dev).to(TORCH_DT[dtype])
 
 
@@ -63,7 +64,8 @@ def test_patch_bits_match_reference_golden(dev, golden_dir, mask_dtype):
         masks = gc.resize_masks(m["h"], m["w"])
         t = torch.from_numpy(masks).to(dev).to(mask_dtype)
         plan = packer.build_plan([t], [[list(range(m["n"]))]], m["n"], 1, dev)
-        bits, cnt, idx = layer.mask_to_patches(plan, dev, 27, want_idx=True)
+        out = layer.mask_to_patches(plan, dev, 27, want_idx=True)
+        bits, cnt, idx = out["bits"], out["cnt"], out["idx"]
         got = bits.cpu().numpy().view(np.uint32)[:, :23]
         want = g["bits"][row:row + m["n"]]
         assert np.array_equal(got, want), (m["h"], m["w"], mask_dtype)
@@ -79,20 +81,39 @@ def test_patch_bits_pad_mode_and_strided_masks(dev):
     masks = synth.masks_blob(3, 2, 3, 480, 854)
     want = np.stack([R.mask_to_patches(m, pad_square=True) for m in masks])
     plan = packer.build_plan([torch.from_numpy(masks).to(dev)], [[list(range(6))]], 6, 1, dev, pad_square=True)
-    bits, _, _ = layer.mask_to_patches(plan, dev)
+    bits = layer.mask_to_patches(plan, dev)["bits"]
     assert np.array_equal(bits_to_bool(bits), want)
     # a non-contiguous view (row pitch != W) is read in place
     big = torch.zeros((6, 480, 1000), dtype=torch.uint8, device=dev)
     big[:, :, 100:954] = torch.from_numpy(masks).to(dev)
     view = big[:, :, 100:954]
     plan = packer.build_plan([view], [[list(range(6))]], 6, 1, dev)
-    bits, _, _ = layer.mask_to_patches(plan, dev)
+    bits = layer.mask_to_patches(plan, dev)["bits"]
     assert np.array_equal(bits_to_bool(bits), np.stack([R.mask_to_patches(m) for m in masks]))
 
 
 # ---------------------------------------------------------------------------------------------
 # kernel 2
 # ---------------------------------------------------------------------------------------------
+def check_group_plan(plan, patches):
+    """The union plan kernel 1 writes for kernel 2: ascending union patches + member masks,
+    zero tail, and the arrival tickets back at zero."""
+    on = bits_to_bool(patches["bits"], 736)
+    nu = patches["grp_nu"].cpu().numpy()
+    ulist = patches["grp_ulist"].cpu().numpy().view(np.uint16)
+    omask = patches["grp_omask"].cpu().numpy()
+    go, gm = plan.host["grp_off"], plan.host["grp_member"]
+    for g in range(plan.n_groups):
+        members = gm[go[g]:go[g + 1]]
+        union = np.flatnonzero(on[members].any(0))
+        assert nu[g] == union.size
+        assert np.array_equal(ulist[g, :nu[g]], union)
+        want = sum((on[m, union].astype(np.uint8) << o) for o, m in enumerate(members))
+        assert np.array_equal(omask[g, :nu[g]], want)
+        assert not omask[g, nu[g]:].any() and not ulist[g, nu[g]:].any()
+    assert not plan.ticket.cpu().numpy().any()
+
+
 @pytest.mark.parametrize("name", [c[0] for c in gc.POOL_CASES])
 @pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
 def test_pool_bit_exact_vs_oracle_and_close_to_reference(dev, golden_dir, name, dtype):
@@ -103,8 +124,9 @@ def test_pool_bit_exact_vs_oracle_and_close_to_reference(dev, golden_dir, name, 
     n_obj = len(rows) // feats.shape[0]
     ann = [[rows[o * feats.shape[0]:(o + 1) * feats.shape[0]].tolist() for o in range(n_obj)]]
     plan = packer.build_plan([torch.from_numpy(masks).to(dev)], ann, feats.shape[0], 1, dev)
-    bits, cnt, _ = layer.mask_to_patches(plan, dev)
-    pooled = layer.mask_pool(ft, plan, bits, cnt).cpu().numpy()
+    patches = layer.mask_to_patches(plan, dev)
+    pooled = layer.mask_pool(ft, plan, patches).cpu().numpy()
+    check_group_plan(plan, patches)
     on = np.stack([R.mask_to_patches(m) for m in masks])
     want = R.mask_pool(feats_r, rows, on)
     assert np.array_equal(pooled, want), np.abs(pooled - want).max()      # canonical order: bit-exact
@@ -129,8 +151,9 @@ def test_pool_many_objects_on_one_frame(dev):
     masks = synth.masks_blob(78, 17, 1, 100, 120)
     plan = packer.build_plan([torch.from_numpy(masks).to(dev)], [[[0]]], 1, 4, dev)
     assert plan.n_groups == 3 and plan.max_group == 8
-    bits, cnt, _ = layer.mask_to_patches(plan, dev)
-    pooled = layer.mask_pool(torch.from_numpy(feats).to(dev), plan, bits, cnt).cpu().numpy()
+    patches = layer.mask_to_patches(plan, dev)
+    check_group_plan(plan, patches)
+    pooled = layer.mask_pool(torch.from_numpy(feats).to(dev), plan, patches).cpu().numpy()
     on = np.stack([R.mask_to_patches(m) for m in masks])
     assert np.array_equal(pooled, R.mask_pool(feats, [0] * 17, on))
 

@@ -66,10 +66,15 @@ def test_plan_groups_objects_by_frame_and_reserves_token_slots():
            for r, a, b in zip(h["grp_row"], h["grp_off"][:-1], h["grp_off"][1:])}
     want = {r: [j for j, x in enumerate(rows) if x == r] for r in set(rows)}
     assert got == want and plan.max_group == 3
-    assert h["mask_shape"].tolist() == [0] * 7 + [1] * 3
-    assert h["shape_tab"].reshape(-1, 4)[:, 1].tolist() == [_cabi.UFV_U8, _cabi.UFV_F32]
+    d = h["mask_desc"]
+    assert d["dtype"].tolist() == [_cabi.UFV_U8] * 7 + [_cabi.UFV_F32] * 3
+    assert d["pitch"].tolist() == [30] * 7 + [40] * 3 and d["tap_off"].tolist() == [0] * 7 + [108] * 3
     e0 = masks[0].data_ptr() + np.arange(7) * 600
-    assert np.array_equal(h["mask_addr"][:7], e0.astype(np.uint64))
+    assert np.array_equal(d["addr"][:7], e0.astype(np.uint64))
+    assert d["addr"][7] == masks[1].data_ptr()
+    for j in range(10):                                          # every mask knows its pool group
+        g = d["group"][j]
+        assert j in h["grp_member"][h["grp_off"][g]:h["grp_off"][g + 1]]
 
 
 def test_plan_splits_frames_with_many_objects():
@@ -82,7 +87,7 @@ def test_plan_splits_frames_with_many_objects():
 
 def test_plan_edge_cases():
     empty = packer.build_plan([torch.zeros((0, 50, 50))], [[[1]]], 2, 4, CPU)   # layer.py:73-75
-    assert empty.n_masks == 1 and empty.host["shape_tab"][:2].tolist() == [336, _cabi.UFV_U8]
+    assert empty.n_masks == 1 and empty.host["mask_desc"]["pitch"].tolist() == [336]
     with pytest.raises(ValueError):
         packer.build_plan([torch.zeros((3, 8, 8))], [[[0, 1]]], 2, 4, CPU)
     with pytest.raises(IndexError):
@@ -96,3 +101,17 @@ def test_synth_is_deterministic_and_sharding_invariant():
     f1, m1, a1 = synth.make_batch(1, 4, 2, "blob", 64, 64, first_clip=1)
     assert np.array_equal(f_all[4:8], f1) and np.array_equal(m_all[1], m1[0])
     assert a_all[1] == [[r + 4 for r in o] for o in a1[0]]
+
+
+def test_plan_cache_reuses_structure_and_patches_mask_addresses():
+    ann = [[[0, 1], [1]]]
+    a = torch.zeros((3, 16, 16), dtype=torch.uint8)
+    b = torch.zeros((3, 16, 16), dtype=torch.uint8)
+    p1 = packer.build_plan([a], ann, 2, 4, CPU)
+    assert packer.build_plan([a], [[[0, 1], [1]]], 2, 4, CPU) is p1          # equal content -> same plan
+    p2 = packer.build_plan([b], ann, 2, 4, CPU)
+    assert p2 is p1 and p1.host["mask_desc"]["addr"][0] == b.data_ptr()     # addresses re-pointed
+    off = p1.dev["mask_desc"] - p1.buffer.data_ptr()
+    on_dev = p1.buffer[off:off + 96].numpy().view(packer.MASK_DESC)
+    assert on_dev["addr"].tolist() == [b.data_ptr() + i * 256 for i in range(3)]
+    assert packer.build_plan([a], [[[0, 1], [0]]], 2, 4, CPU) is not p1     # different structure

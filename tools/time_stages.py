@@ -44,8 +44,9 @@ def main():
     enc = enc.to(dev).to(dt)
     plan = packer.build_plan(md, ann, ft.shape[0], a.k, dev)
     q = plan.n_masks
-    bits, cnt, _ = layer.mask_to_patches(plan, dev)
-    pooled = layer.mask_pool(ft, plan, bits, cnt)
+    patches = layer.mask_to_patches(plan, dev)
+    bits = patches["bits"]
+    pooled = layer.mask_pool(ft, plan, patches)
     merged, counts, _ = layer.ttm(pooled, plan, a.k, dt)
     l0, l2 = enc.feat_linear[0], enc.feat_linear[2]
     hid = layer.linear(merged, l0.weight, l0.bias, True)
@@ -60,7 +61,7 @@ def main():
     feat_bytes = on_union * 1152 * ft.element_size()
     res = {}
     res["k1 patches"] = timed(lambda: layer.mask_to_patches(plan, dev))
-    res["k2 pool"] = timed(lambda: layer.mask_pool(ft, plan, bits, cnt))
+    res["k2 pool"] = timed(lambda: layer.mask_pool(ft, plan, patches))
     res["k3 ttm"] = timed(lambda: layer.ttm(pooled, plan, a.k, dt))
     res["k4a linear1+gelu"] = timed(lambda: layer.linear(merged, l0.weight, l0.bias, True))
     res["k4b linear2"] = timed(lambda: layer.linear(hid, l2.weight, l2.bias, False))

@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libufv_b200.so")
+LIB_PATH = os.environ.get("UFV_B200_LIB") or os.path.join(HERE, "libufv_b200.so")   # env: developer sweeps
 CSRC = os.path.join(HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ufv_b200.h")
 
@@ -20,6 +20,7 @@ UFV_F32, UFV_BF16, UFV_F16, UFV_U8 = 0, 1, 2, 3
 BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8
+PLAN_PITCH = 736
 ABI_VERSION = 1
 
 _p = C.c_void_p
@@ -32,9 +33,9 @@ class EncodeArgs(C.Structure):
     _fields_ = [
         ("feats", _p), ("feat_dtype", _i32), ("n_patch_side", _i32), ("n_rows", _i64),
         ("c", _i32), ("hid", _i32),
-        ("mask_addr", _p), ("mask_shape", _p), ("shape_tab", _p), ("taps", _p),
-        ("n_masks", _i32), ("idx_pitch", _i32),
+        ("mask_desc", _p), ("taps", _p), ("n_masks", _i32), ("idx_pitch", _i32),
         ("bits", _p), ("cnt", _p), ("idx", _p),
+        ("grp_ticket", _p), ("grp_nu", _p), ("grp_ulist", _p), ("grp_omask", _p),
         ("grp_row", _p), ("grp_off", _p), ("grp_member", _p), ("n_groups", _i32),
         ("max_group", _i32),
         ("pooled", _p),
@@ -50,8 +51,9 @@ _SIGNATURES = {
     "ufv_abi_version": (C.c_int, []),
     "ufv_last_error": (C.c_char_p, []),
     "ufv_tap_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
-    "ufv_mask_to_patches": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p]),
-    "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, C.c_int,
+    "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p,
+                                      _p, _p]),
+    "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_int,
                                 C.c_int, _p, _p]),
     "ufv_ttm": (C.c_int, [_p, C.c_int, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p,
                           _p, C.c_int, _p, C.c_int, _p]),

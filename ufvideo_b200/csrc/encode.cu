@@ -61,11 +61,13 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
   using namespace ufv;
   UFV_REQUIRE(a != nullptr, UFV_E_NULL, "ufv_encode: args is null");
   const int side = a->n_patch_side;
-  int rc = ufv_mask_to_patches(a->mask_addr, a->mask_shape, a->shape_tab, a->taps, a->n_masks, side,
-                               a->bits, a->cnt, a->idx, a->idx_pitch, stream);
+  int rc = ufv_mask_to_patches(a->mask_desc, a->taps, a->n_masks, side, a->bits, a->cnt, a->idx,
+                               a->idx_pitch, a->grp_off, a->grp_member, a->grp_ticket, a->grp_nu,
+                               a->grp_ulist, a->grp_omask, stream);
   if (rc != 0) return rc;
-  rc = ufv_mask_pool(a->feats, a->feat_dtype, a->n_rows, side * side, a->c, a->bits, a->cnt,
-                     a->grp_row, a->grp_off, a->grp_member, a->n_groups, a->max_group, a->pooled, stream);
+  rc = ufv_mask_pool(a->feats, a->feat_dtype, a->n_rows, side * side, a->c, a->cnt, a->grp_row, a->grp_off,
+                     a->grp_member, a->grp_nu, a->grp_ulist, a->grp_omask, a->n_groups, a->max_group,
+                     a->pooled, stream);
   if (rc != 0) return rc;
   rc = ufv_ttm(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
                a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, nullptr, 0, stream);

@@ -1,10 +1,15 @@
-// Kernel 1: mask resize + binarise -> per object-frame patch bitmask, count and index list.
+// Kernel 1: mask resize + binarise -> per object-frame patch bitmask, count and index list,
+// plus the per-group "union plan" the pool kernel streams from.
 //
 // Replaces F.interpolate(mask, (27, 27), 'bilinear', align_corners=False) followed by
 // (mask > 0) and mask.sum (reference ufvideo/model/layer.py:139,143,145).  With non-negative
 // masks the interpolated value is a sum of non-negative weight * value products, so
 // "interp > 0" is the OR of the (at most four) taps whose weight is non-zero: integer-exact,
 // and only 4 * n_out^2 mask elements are read instead of H * W.
+//
+// One CTA per object-frame.  The CTA that finishes a group last (atomic ticket) also builds the
+// group's plan: the ascending list of patches that are on in ANY member mask (only those feature
+// rows are ever fetched by kernel 2) and, per listed patch, the bitmask of members that pool it.
 #include "common.cuh"
 
 #include <cmath>
@@ -57,50 +62,9 @@ __device__ __forceinline__ bool mask_positive(uint64_t base, int64_t off, int dt
   }
 }
 
-constexpr int kPatchThreads = 256;
-
-__global__ void __launch_bounds__(kPatchThreads)
-mask_to_patches_kernel(const uint64_t* __restrict__ mask_addr, const int32_t* __restrict__ mask_shape,
-                       const int32_t* __restrict__ shape_tab, const int32_t* __restrict__ taps,
-                       int n_out, uint32_t* __restrict__ bits_out, int32_t* __restrict__ cnt_out,
-                       uint16_t* __restrict__ idx_out, int idx_pitch) {
-  __shared__ int32_t s_taps[4 * UFV_MAX_PATCH_SIDE];
-  __shared__ uint32_t s_words[UFV_BITS_WORDS];
-  __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
-
-  const int j = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int shape = mask_shape[j];
-  const int pitch = shape_tab[4 * shape + 0];
-  const int dtype = shape_tab[4 * shape + 1];
-  const int tap_off = shape_tab[4 * shape + 2];
-  const uint64_t base = mask_addr[j];
-  if (tid < 4 * n_out) s_taps[tid] = taps[tap_off + tid];
-  __syncthreads();
-
-  const int n_patch = n_out * n_out;
-  const int32_t* h0 = s_taps;
-  const int32_t* h1 = s_taps + n_out;
-  const int32_t* w0 = s_taps + 2 * n_out;
-  const int32_t* w1 = s_taps + 3 * n_out;
-  for (int first = 0; first < UFV_BITS_WORDS * 32; first += kPatchThreads) {
-    const int p = first + tid;
-    bool on = false;
-    if (p < n_patch) {
-      const int i = p / n_out, jx = p - i * n_out;
-      const int ra = h0[i], rb = h1[i], ca = w0[jx], cb = w1[jx];
-      // all four taps are issued before any is consumed (memory-level parallelism)
-      const bool t00 = (ra >= 0 && ca >= 0) && mask_positive(base, int64_t(ra) * pitch + ca, dtype);
-      const bool t01 = (ra >= 0 && cb >= 0) && mask_positive(base, int64_t(ra) * pitch + cb, dtype);
-      const bool t10 = (rb >= 0 && ca >= 0) && mask_positive(base, int64_t(rb) * pitch + ca, dtype);
-      const bool t11 = (rb >= 0 && cb >= 0) && mask_positive(base, int64_t(rb) * pitch + cb, dtype);
-      on = t00 | t01 | t10 | t11;
-    }
-    const uint32_t word = __ballot_sync(0xffffffffu, on);
-    if ((tid & 31) == 0) s_words[p >> 5] = word;
-  }
-  __syncthreads();
-  if (tid < 32) {   // exclusive prefix of the per-word popcounts with one warp scan
+// exclusive prefix of per-word popcounts, computed by warp 0; s_prefix[UFV_BITS_WORDS] = total
+__device__ __forceinline__ void word_prefix(const uint32_t* s_words, int32_t* s_prefix, int tid) {
+  if (tid < 32) {
     const int mine = tid < UFV_BITS_WORDS ? __popc(s_words[tid]) : 0;
     int incl = mine;
 #pragma unroll
@@ -111,6 +75,57 @@ mask_to_patches_kernel(const uint64_t* __restrict__ mask_addr, const int32_t* __
     if (tid < UFV_BITS_WORDS) s_prefix[tid] = incl - mine;
     if (tid == UFV_BITS_WORDS - 1) s_prefix[UFV_BITS_WORDS] = incl;
   }
+}
+
+constexpr int kPatchThreads = 256;
+
+__global__ void __launch_bounds__(kPatchThreads)
+mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __restrict__ taps, int n_out,
+                       uint32_t* __restrict__ bits_out, int32_t* __restrict__ cnt_out,
+                       uint16_t* __restrict__ idx_out, int idx_pitch,
+                       const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member,
+                       uint32_t* __restrict__ grp_ticket, int32_t* __restrict__ grp_nu,
+                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask) {
+  __shared__ int32_t s_taps[4 * UFV_MAX_PATCH_SIDE];
+  __shared__ uint32_t s_words[UFV_BITS_WORDS];
+  __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
+  __shared__ uint32_t s_member_bits[UFV_MAX_GROUP][UFV_BITS_WORDS];
+  __shared__ int s_last;
+
+  const int j = blockIdx.x;
+  const int tid = threadIdx.x;
+  const ufv_mask_desc d = desc[j];
+  if (tid < 4 * n_out) s_taps[tid] = taps[d.tap_off + tid];
+  __syncthreads();
+
+  const int n_patch = n_out * n_out;
+  const int32_t* h0 = s_taps;
+  const int32_t* h1 = s_taps + n_out;
+  const int32_t* w0 = s_taps + 2 * n_out;
+  const int32_t* w1 = s_taps + 3 * n_out;
+  constexpr int kIters = UFV_BITS_WORDS * 32 / kPatchThreads;
+  bool on[kIters];
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {   // every tap of every iteration is in flight before the ballots
+    const int p = it * kPatchThreads + tid;
+    on[it] = false;
+    if (p < n_patch) {
+      const int i = p / n_out, jx = p - i * n_out;
+      const int ra = h0[i], rb = h1[i], ca = w0[jx], cb = w1[jx];
+      const bool t00 = (ra >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + ca, d.dtype);
+      const bool t01 = (ra >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + cb, d.dtype);
+      const bool t10 = (rb >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + ca, d.dtype);
+      const bool t11 = (rb >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + cb, d.dtype);
+      on[it] = t00 | t01 | t10 | t11;
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    const uint32_t word = __ballot_sync(0xffffffffu, on[it]);
+    if ((tid & 31) == 0) s_words[(it * kPatchThreads + tid) >> 5] = word;
+  }
+  __syncthreads();
+  word_prefix(s_words, s_prefix, tid);
   __syncthreads();
   if (tid < UFV_BITS_WORDS) bits_out[size_t(j) * UFV_BITS_WORDS + tid] = s_words[tid];
   if (tid == 0) cnt_out[j] = s_prefix[UFV_BITS_WORDS];
@@ -122,6 +137,56 @@ mask_to_patches_kernel(const uint64_t* __restrict__ mask_addr, const int32_t* __
         idx_out[size_t(j) * idx_pitch + s_prefix[p >> 5] + __popc(word & (bit - 1u))] =
             static_cast<uint16_t>(p);
     }
+  }
+  if (grp_ticket == nullptr) return;
+
+  // ---- group plan, built by whichever member CTA arrives last ---------------------------------------
+  const int g = d.group;
+  const int m0 = grp_off[g];
+  const int n_mem = grp_off[g + 1] - m0;
+  __threadfence();                      // publish this CTA's bits before taking a ticket
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&grp_ticket[g], 1u) == uint32_t(n_mem - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < UFV_MAX_GROUP * UFV_BITS_WORDS; i += kPatchThreads) {
+    const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
+    s_member_bits[o][w] = o < n_mem ? __ldcg(bits_out + size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w) : 0u;
+  }
+  __syncthreads();
+  if (tid < UFV_BITS_WORDS) {
+    uint32_t u = 0;
+#pragma unroll
+    for (int o = 0; o < UFV_MAX_GROUP; ++o) u |= s_member_bits[o][tid];
+    s_words[tid] = u;
+  }
+  __syncthreads();
+  word_prefix(s_words, s_prefix, tid);
+  __syncthreads();
+  const int n_u = s_prefix[UFV_BITS_WORDS];
+  uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
+  uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
+  for (int p = tid; p < UFV_PLAN_PITCH; p += kPatchThreads) {
+    const int w = p >> 5;
+    const uint32_t bit = 1u << (p & 31);
+    const uint32_t u = w < UFV_BITS_WORDS ? s_words[w] : 0u;
+    if (u & bit) {
+      const int pos = s_prefix[w] + __popc(u & (bit - 1u));
+      uint32_t m = 0;
+#pragma unroll
+      for (int o = 0; o < UFV_MAX_GROUP; ++o) m |= ((s_member_bits[o][w] >> (p & 31)) & 1u) << o;
+      ulist[pos] = static_cast<uint16_t>(p);
+      omask[pos] = static_cast<uint8_t>(m);
+    }
+    if (p >= n_u) {                     // tail: no member pools these slots
+      ulist[p] = 0;
+      omask[p] = 0;
+    }
+  }
+  if (tid == 0) {
+    grp_nu[g] = n_u;
+    grp_ticket[g] = 0u;                 // self-reset: the ticket buffer is reusable by the next call
   }
 }
 
@@ -147,18 +212,21 @@ extern "C" int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* t
   return 0;
 }
 
-extern "C" int ufv_mask_to_patches(const uint64_t* mask_addr, const int32_t* mask_shape,
-                                   const int32_t* shape_tab, const int32_t* taps, int n_masks,
-                                   int n_out, uint32_t* bits_out, int32_t* cnt_out,
-                                   uint16_t* idx_out, int idx_pitch, void* stream) {
+extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
+                                   uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
+                                   const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
+                                   int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, void* stream) {
   UFV_REQUIRE(n_masks >= 0 && n_out >= 1 && n_out <= UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
               "ufv_mask_to_patches: n_masks=%d n_out=%d out of range", n_masks, n_out);
   if (n_masks == 0) return 0;
-  UFV_REQUIRE(mask_addr && mask_shape && shape_tab && taps && bits_out && cnt_out, UFV_E_NULL,
-              "ufv_mask_to_patches: null pointer");
+  UFV_REQUIRE(desc && taps && bits_out && cnt_out, UFV_E_NULL, "ufv_mask_to_patches: null pointer");
   UFV_REQUIRE(idx_out == nullptr || idx_pitch >= n_out * n_out, UFV_E_SHAPE,
               "ufv_mask_to_patches: idx_pitch %d < %d", idx_pitch, n_out * n_out);
+  if (grp_ticket != nullptr)
+    UFV_REQUIRE(grp_off && grp_member && grp_nu && grp_ulist && grp_omask, UFV_E_NULL,
+                "ufv_mask_to_patches: group plan requested but a plan pointer is null");
   ufv::mask_to_patches_kernel<<<n_masks, ufv::kPatchThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      mask_addr, mask_shape, shape_tab, taps, n_out, bits_out, cnt_out, idx_out, idx_pitch);
+      desc, taps, n_out, bits_out, cnt_out, idx_out, idx_pitch, grp_off, grp_member, grp_ticket, grp_nu,
+      grp_ulist, grp_omask);
   return ufv::check_launch("ufv_mask_to_patches");
 }

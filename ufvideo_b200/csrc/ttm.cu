@@ -20,6 +20,7 @@ namespace ufv {
 
 constexpr int kTtmThreads = 512;
 constexpr int kTtmWarps = kTtmThreads / 32;
+constexpr int kTtmBatch = 5;   // float4 loads in flight per lane while a row is reduced
 
 __device__ __forceinline__ float butterfly_sum(float v) {
 #pragma unroll
@@ -74,16 +75,24 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
     return;
   }
 
-  // ---- 1. norms: one warp per token -----------------------------------------------------------
+  // ---- 1. norms: one warp per token (kTtmBatch float4 loads in flight per lane) -----------------
   for (int t = warp; t < t_len; t += kTtmWarps) {
     const float* row = x + size_t(t) * c;
     float acc = 0.f;
-    for (int e = lane * 4; e < c; e += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(row + e);
-      acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
-      acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
-      acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
-      acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+    for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
+      float4 v[kTtmBatch];
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u)
+        if (e0 + u * 128 < c) v[u] = *reinterpret_cast<const float4*>(row + e0 + u * 128);
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u) {
+        if (e0 + u * 128 < c) {
+          acc = __fadd_rn(acc, __fmul_rn(v[u].x, v[u].x));
+          acc = __fadd_rn(acc, __fmul_rn(v[u].y, v[u].y));
+          acc = __fadd_rn(acc, __fmul_rn(v[u].z, v[u].z));
+          acc = __fadd_rn(acc, __fmul_rn(v[u].w, v[u].w));
+        }
+      }
     }
     acc = butterfly_sum(acc);
     if (lane == 0) s_norm[t] = fmaxf(__fsqrt_rn(acc), 1e-12f);
@@ -97,13 +106,24 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
     const float* rb = ra + c;
     const float ma = s_norm[i], mb = s_norm[i + 1];
     float acc = 0.f;
-    for (int e = lane * 4; e < c; e += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(ra + e);
-      const float4 b = *reinterpret_cast<const float4*>(rb + e);
-      acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a.x, ma), __fdiv_rn(b.x, mb)));
-      acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a.y, ma), __fdiv_rn(b.y, mb)));
-      acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a.z, ma), __fdiv_rn(b.z, mb)));
-      acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a.w, ma), __fdiv_rn(b.w, mb)));
+    for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
+      float4 a[kTtmBatch], b[kTtmBatch];
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u) {
+        if (e0 + u * 128 < c) {
+          a[u] = *reinterpret_cast<const float4*>(ra + e0 + u * 128);
+          b[u] = *reinterpret_cast<const float4*>(rb + e0 + u * 128);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u) {
+        if (e0 + u * 128 < c) {
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].x, ma), __fdiv_rn(b[u].x, mb)));
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].y, ma), __fdiv_rn(b[u].y, mb)));
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].z, ma), __fdiv_rn(b[u].z, mb)));
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].w, ma), __fdiv_rn(b[u].w, mb)));
+        }
+      }
     }
     acc = butterfly_sum(acc);
     if (lane == 0) {

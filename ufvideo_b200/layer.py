@@ -21,6 +21,7 @@ import torch.nn as nn
 from . import _cabi, packer
 
 _vp = ctypes.c_void_p
+_ELEM_BYTES = {torch.float32: 4, torch.int32: 4, torch.bfloat16: 2, torch.float16: 2, torch.uint8: 1}
 
 
 def _stream_ptr(device) -> int:
@@ -42,28 +43,41 @@ def _feat_dtype(t: torch.Tensor) -> int:
 # ------------------------------------------------------------------------------------------------
 # stage-level operators (each one C-ABI call); the parity tests drive these directly
 # ------------------------------------------------------------------------------------------------
+def _plan_buffers(plan: packer.EncodePlan, device):
+    """Device buffers of the per-group union plan written by kernel 1 and read by kernel 2."""
+    g = max(plan.n_groups, 1)
+    nu = torch.empty((g,), dtype=torch.int32, device=device)
+    ulist = torch.empty((g, _cabi.PLAN_PITCH), dtype=torch.int16, device=device)
+    omask = torch.empty((g, _cabi.PLAN_PITCH), dtype=torch.uint8, device=device)
+    return nu, ulist, omask
+
+
 def mask_to_patches(plan: packer.EncodePlan, device, n_out: int = 27, want_idx: bool = False):
-    """Kernel 1.  Returns (bits int32 [q, 24], cnt int32 [q], idx int16 [q, 736] | None)."""
+    """Kernel 1.  Returns a dict: bits int32 [q, 24], cnt int32 [q], idx int16 [q, 736] | None and
+    the group plan (grp_nu, grp_ulist, grp_omask)."""
     q = plan.n_masks
     bits = torch.empty((q, _cabi.BITS_WORDS), dtype=torch.int32, device=device)
     cnt = torch.empty((q,), dtype=torch.int32, device=device)
     idx = torch.zeros((q, 736), dtype=torch.int16, device=device) if want_idx else None
+    nu, ulist, omask = _plan_buffers(plan, device)
     d = plan.dev
     _cabi.check(_cabi.lib().ufv_mask_to_patches(
-        d["mask_addr"], d["mask_shape"], d["shape_tab"], d["taps"], q, n_out, bits.data_ptr(),
-        cnt.data_ptr(), idx.data_ptr() if want_idx else None, 736, _stream_ptr(device)))
-    return bits, cnt, idx
+        d["mask_desc"], d["taps"], q, n_out, bits.data_ptr(), cnt.data_ptr(),
+        idx.data_ptr() if want_idx else None, 736, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
+        nu.data_ptr(), ulist.data_ptr(), omask.data_ptr(), _stream_ptr(device)))
+    return {"bits": bits, "cnt": cnt, "idx": idx, "grp_nu": nu, "grp_ulist": ulist, "grp_omask": omask}
 
 
-def mask_pool(feats: torch.Tensor, plan: packer.EncodePlan, bits: torch.Tensor, cnt: torch.Tensor):
-    """Kernel 2.  feats [F, n_patch, C] -> pooled fp32 [q, C]."""
+def mask_pool(feats: torch.Tensor, plan: packer.EncodePlan, patches: dict):
+    """Kernel 2.  feats [F, n_patch, C] + the output of ``mask_to_patches`` -> pooled fp32 [q, C]."""
     _require_cuda(feats, "feats")
     f, n_patch, c = feats.shape
     pooled = torch.empty((plan.n_masks, c), dtype=torch.float32, device=feats.device)
     d = plan.dev
     _cabi.check(_cabi.lib().ufv_mask_pool(
-        feats.data_ptr(), _feat_dtype(feats), f, n_patch, c, bits.data_ptr(), cnt.data_ptr(),
-        d["grp_row"], d["grp_off"], d["grp_member"], plan.n_groups, plan.max_group,
+        feats.data_ptr(), _feat_dtype(feats), f, n_patch, c, patches["cnt"].data_ptr(),
+        d["grp_row"], d["grp_off"], d["grp_member"], patches["grp_nu"].data_ptr(),
+        patches["grp_ulist"].data_ptr(), patches["grp_omask"].data_ptr(), plan.n_groups, plan.max_group,
         pooled.data_ptr(), _stream_ptr(feats.device)))
     return pooled
 
@@ -152,8 +166,7 @@ class MaskPooling(nn.Module):
         if feats.dtype not in packer.FEAT_DTYPES:
             feats = feats.float()
         plan = packer.build_plan([mask[0]], [[list(range(b))]], b, 1, x.device, False, h)
-        bits, cnt, _ = mask_to_patches(plan, x.device, h)
-        return mask_pool(feats, plan, bits, cnt).to(x.dtype)
+        return mask_pool(feats, plan, mask_to_patches(plan, x.device, h)).to(x.dtype)
 
 
 class MaskExtractor(nn.Module):
@@ -176,6 +189,7 @@ class MaskExtractor(nn.Module):
         self.image_aspect_ratio = image_aspect_ratio
         self.region_token_num = region_token_num
         self.last_plan = None                     # introspection for tests / bench
+        self.keep_debug = False                   # expose intermediates of the last call as _debug
 
     # -- helpers -------------------------------------------------------------------------------
     def _linears(self):
@@ -208,45 +222,64 @@ class MaskExtractor(nn.Module):
                                  self.image_aspect_ratio == "pad", side)
         self.last_plan = plan
         hid = linears[-1].weight.shape[0]
-        q, m_pad = plan.n_masks, plan.m_pad
-        bits = torch.empty((q, _cabi.BITS_WORDS), dtype=torch.int32, device=device)
-        cnt = torch.empty((q,), dtype=torch.int32, device=device)
-        pooled = torch.empty((q, c), dtype=torch.float32, device=device)
-        merged = torch.empty((m_pad, c), dtype=feats.dtype, device=device)
-        counts = torch.empty((plan.n_obj,), dtype=torch.int32, device=device)
+        q, m_pad, g = plan.n_masks, plan.m_pad, max(plan.n_groups, 1)
+        es = feats.element_size()
+        # one workspace allocation, carved into 256-byte aligned pieces
+        sizes = (("bits", q * _cabi.BITS_WORDS * 4), ("cnt", q * 4), ("pooled", q * c * 4),
+                 ("merged", m_pad * c * es), ("hidden", m_pad * hid * es), ("counts", plan.n_obj * 4),
+                 ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.PLAN_PITCH))
+        off, total = {}, 0
+        for name, nbytes in sizes:
+            off[name] = total
+            total += (nbytes + 255) // 256 * 256
+        ws = torch.empty((max(total, 256),), dtype=torch.uint8, device=device)
+        base = ws.data_ptr()
+        ptr = {name: base + o for name, o in off.items()}
         tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
         d = plan.dev
         stream = _stream_ptr(device)
+        lib = _cabi.lib()
         if len(linears) == 2:                     # the reference's depth=2 projector: one chained call
-            hidden = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
-            a = _cabi.EncodeArgs(
-                feats=feats.data_ptr(), feat_dtype=dt, n_patch_side=side, n_rows=f, c=c, hid=hid,
-                mask_addr=d["mask_addr"], mask_shape=d["mask_shape"], shape_tab=d["shape_tab"],
-                taps=d["taps"], n_masks=q, idx_pitch=0, bits=bits.data_ptr(), cnt=cnt.data_ptr(),
-                idx=None, grp_row=d["grp_row"], grp_off=d["grp_off"], grp_member=d["grp_member"],
-                n_groups=plan.n_groups, max_group=plan.max_group, pooled=pooled.data_ptr(),
-                obj_start=d["obj_start"], obj_len=d["obj_len"], slot_off=d["slot_off"],
-                n_obj=plan.n_obj, max_len=plan.max_len, k_keep=k_keep, m_pad=m_pad,
-                merged=merged.data_ptr(), counts=counts.data_ptr(),
-                w1=linears[0].weight.data_ptr(), b1=linears[0].bias.data_ptr(),
-                w2=linears[1].weight.data_ptr(), b2=linears[1].bias.data_ptr(),
-                hidden=hidden.data_ptr(), tokens_out=tokens.data_ptr())
-            _cabi.check(_cabi.lib().ufv_encode(ctypes.byref(a), stream))
+            a = plan.args
+            if a is None:
+                a = plan.args = _cabi.EncodeArgs(
+                    n_patch_side=side, mask_desc=d["mask_desc"], taps=d["taps"], n_masks=q, idx_pitch=0,
+                    idx=None, grp_ticket=plan.ticket.data_ptr(), grp_row=d["grp_row"], grp_off=d["grp_off"],
+                    grp_member=d["grp_member"], n_groups=plan.n_groups, max_group=plan.max_group,
+                    obj_start=d["obj_start"], obj_len=d["obj_len"], slot_off=d["slot_off"],
+                    n_obj=plan.n_obj, max_len=plan.max_len, k_keep=k_keep, m_pad=m_pad)
+            a.feats, a.feat_dtype, a.n_rows, a.c, a.hid = feats.data_ptr(), dt, f, c, hid
+            a.bits, a.cnt, a.pooled, a.merged = ptr["bits"], ptr["cnt"], ptr["pooled"], ptr["merged"]
+            a.grp_nu, a.grp_ulist, a.grp_omask = ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"]
+            a.counts, a.hidden, a.tokens_out = ptr["counts"], ptr["hidden"], tokens.data_ptr()
+            a.w1, a.b1 = linears[0].weight.data_ptr(), linears[0].bias.data_ptr()
+            a.w2, a.b2 = linears[1].weight.data_ptr(), linears[1].bias.data_ptr()
+            _cabi.check(lib.ufv_encode(ctypes.byref(a), stream))
         else:                                     # other depths: the same kernels, staged
-            lib = _cabi.lib()
-            _cabi.check(lib.ufv_mask_to_patches(d["mask_addr"], d["mask_shape"], d["shape_tab"], d["taps"],
-                                                q, side, bits.data_ptr(), cnt.data_ptr(), None, 0, stream))
-            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, n_patch, c, bits.data_ptr(),
-                                          cnt.data_ptr(), d["grp_row"], d["grp_off"], d["grp_member"],
-                                          plan.n_groups, plan.max_group, pooled.data_ptr(), stream))
-            _cabi.check(lib.ufv_ttm(pooled.data_ptr(), c, d["obj_start"], d["obj_len"], d["slot_off"],
-                                    plan.n_obj, plan.max_len, k_keep, merged.data_ptr(), dt, None,
-                                    counts.data_ptr(), None, 0, None, 0, stream))
-            x = merged
+            _cabi.check(lib.ufv_mask_to_patches(d["mask_desc"], d["taps"], q, side, ptr["bits"], ptr["cnt"],
+                                                None, 0, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
+                                                ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], stream))
+            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, n_patch, c, ptr["cnt"], d["grp_row"],
+                                          d["grp_off"], d["grp_member"], ptr["grp_nu"], ptr["grp_ulist"],
+                                          ptr["grp_omask"], plan.n_groups, plan.max_group, ptr["pooled"], stream))
+            _cabi.check(lib.ufv_ttm(ptr["pooled"], c, d["obj_start"], d["obj_len"], d["slot_off"],
+                                    plan.n_obj, plan.max_len, k_keep, ptr["merged"], dt, None,
+                                    ptr["counts"], None, 0, None, 0, stream))
+            x = ws[off["merged"]:off["merged"] + m_pad * c * es].view(feats.dtype).view(m_pad, c)
             for i, lin in enumerate(linears):
                 x = linear(x, lin.weight, lin.bias, gelu=i < len(linears) - 1)
             tokens = x
-        self._debug = {"bits": bits, "cnt": cnt, "pooled": pooled, "merged": merged}
+
+        def view(name, dtype, shape):
+            n = int(np.prod(shape)) * _ELEM_BYTES[dtype]
+            return ws[off[name]:off[name] + n].view(dtype).view(shape)
+
+        counts = view("counts", torch.int32, (plan.n_obj,))
+        if self.keep_debug:
+            self._debug = {"bits": view("bits", torch.int32, (q, _cabi.BITS_WORDS)),
+                           "cnt": view("cnt", torch.int32, (q,)),
+                           "pooled": view("pooled", torch.float32, (q, c)),
+                           "merged": view("merged", feats.dtype, (m_pad, c))}
         return tokens, counts, plan
 
     # -- the reference's forward -----------------------------------------------------------------
@@ -257,13 +290,14 @@ class MaskExtractor(nn.Module):
         (which reads only ``X_features.device`` in its fallbacks)."""
         tokens, counts, plan = self.encode_padded(feats, masks, ann_indices)
         region_token_nums = counts.cpu().numpy()   # the one unavoidable D2H: the caller slices by it
-        if not np.array_equal(region_token_nums, plan.slots):
-            # ties at the merge threshold left some object with fewer than min(T, K) tokens:
-            # drop the zero-filled slots (rare; exact ties only)
-            starts = plan.host["slot_off"]
-            row_map = np.concatenate([np.arange(s, s + n, dtype=np.int32)
-                                      for s, n in zip(starts, region_token_nums)] or [np.zeros(0, np.int32)])
-            tokens = gather_rows(tokens, torch.from_numpy(row_map).to(tokens.device))
+        if np.array_equal(region_token_nums, plan.slots):
+            return tokens, list(plan.expect_counts)
+        # ties at the merge threshold left some object with fewer than min(T, K) tokens:
+        # drop the zero-filled slots (rare; exact ties only)
+        starts = plan.host["slot_off"]
+        row_map = np.concatenate([np.arange(s, s + n, dtype=np.int32)
+                                  for s, n in zip(starts, region_token_nums)] or [np.zeros(0, np.int32)])
+        tokens = gather_rows(tokens, torch.from_numpy(row_map).to(tokens.device))
         return tokens, [int(n) for n in region_token_nums]
 
 

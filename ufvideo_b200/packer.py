@@ -3,11 +3,14 @@
 Restates the bookkeeping of the reference's forward loop (ufvideo/model/layer.py:66-119) as data:
 which mask plane pairs with which feature row (layer.py:92-98), which pooled rows belong to
 which object (layer.py:112-119) and where each object's tokens land in the output
-(layer.py:121-125).  Pure integer work on the host; everything is uploaded in one buffer.
+(layer.py:121-125).  Pure integer work on the host; everything is uploaded in one buffer, and a
+plan is reused when the same batch structure comes back (only the mask base addresses are
+patched).
 """
 from __future__ import annotations
 
 import ctypes
+from collections import OrderedDict
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -19,7 +22,14 @@ _MASK_DTYPES = {torch.uint8: _cabi.UFV_U8, torch.bool: _cabi.UFV_U8, torch.float
                 torch.bfloat16: _cabi.UFV_BF16, torch.float16: _cabi.UFV_F16}
 FEAT_DTYPES = {torch.float32: _cabi.UFV_F32, torch.bfloat16: _cabi.UFV_BF16, torch.float16: _cabi.UFV_F16}
 
+# mirror of struct ufv_mask_desc (include/ufv_b200.h), 32 bytes
+MASK_DESC = np.dtype([("addr", "<u8"), ("pitch", "<i4"), ("dtype", "<i4"), ("tap_off", "<i4"),
+                      ("group", "<i4"), ("reserved", "<i4", (2,))])
+assert MASK_DESC.itemsize == 32
+
 _tap_cache: dict = {}
+_plan_cache: "OrderedDict[tuple, EncodePlan]" = OrderedDict()
+PLAN_CACHE_SIZE = 16
 
 
 def tap_table(h: int, w: int, n_out: int, pad_square: bool) -> np.ndarray:
@@ -48,7 +58,12 @@ class EncodePlan:
     host: dict = field(default_factory=dict)      # name -> numpy array
     dev: dict = field(default_factory=dict)       # name -> device pointer (int)
     buffer: torch.Tensor | None = None            # owns the device memory behind ``dev``
-    keepalive: list = field(default_factory=list)  # mask tensors the descriptors point into
+    ticket: torch.Tensor | None = None            # zeroed per-group arrival counters (self-resetting)
+    sample_of: np.ndarray | None = None           # int32 [q] sample each object-frame came from
+    plane_off: np.ndarray | None = None           # int64 [q] byte offset of its plane in that sample
+    base_ptrs: tuple = ()                         # mask tensor base addresses baked into ``buffer``
+    args: object = None                           # cached ctypes EncodeArgs
+    expect_counts: list = field(default_factory=list)
 
 
 def _as_mask_list(masks, device):
@@ -74,23 +89,43 @@ def _as_mask_list(masks, device):
 
 
 def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_square: bool = False,
-               n_out: int = _cabi.MAX_PATCH_SIDE) -> EncodePlan:
+               n_out: int = _cabi.MAX_PATCH_SIDE, use_cache: bool = True) -> EncodePlan:
     masks = _as_mask_list(masks, device)
     if len(ann_indices) != len(masks):
         raise ValueError("ann_indices and masks disagree on the number of samples")
+    ptrs = tuple(m.data_ptr() for m in masks)
+    key = None
+    if use_cache:
+        key = (tuple(tuple(tuple(o) for o in s) for s in ann_indices),
+               tuple((tuple(m.shape), m.stride(), m.dtype) for m in masks),
+               n_feat_rows, k_keep, bool(pad_square), n_out, str(device))
+        plan = _plan_cache.get(key)
+        if plan is not None:
+            _plan_cache.move_to_end(key)
+            if plan.base_ptrs != ptrs:           # same structure, new mask tensors: patch addresses
+                _patch_addresses(plan, ptrs, device)
+            return plan
+    plan = _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out)
+    plan.base_ptrs = ptrs
+    if key is not None:
+        _plan_cache[key] = plan
+        while len(_plan_cache) > PLAN_CACHE_SIZE:
+            _plan_cache.popitem(last=False)
+    return plan
 
-    addr, shape_id, rows_all = [], [], []
-    shapes, shape_rows, tap_chunks, tap_len = {}, [], [], 0
+
+def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out) -> EncodePlan:
+    pitch, dtype_id, tap_off, sample_of, plane_off, rows_all = [], [], [], [], [], []
+    taps, tap_chunks, tap_len = {}, [], 0
     obj_start, obj_len = [], []
     base = 0
     for i, m in enumerate(masks):
         q, h, w = m.shape
         esize = m.element_size()
-        key = (h, w, m.dtype, m.stride(1), pad_square)
-        sid = shapes.get(key)
-        if sid is None:
-            sid = shapes[key] = len(shapes)
-            shape_rows.append((m.stride(1), _MASK_DTYPES[m.dtype], tap_len, 0))
+        tkey = (h, w)
+        toff = taps.get(tkey)
+        if toff is None:
+            toff = taps[tkey] = tap_len
             tap_chunks.append(tap_table(h, w, n_out, pad_square))
             tap_len += 4 * n_out
         rows = [int(r) for obj in ann_indices[i] for r in obj]            # layer.py:92-95
@@ -104,8 +139,11 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
             else:
                 raise ValueError(f"sample {i}: {b} feature rows cannot pair with {q} masks")
         n_i = len(rows)
-        addr.append(m.data_ptr() + planes * (m.stride(0) * esize))
-        shape_id.append(np.full(n_i, sid, dtype=np.int32))
+        plane_off.append(planes * (m.stride(0) * esize))
+        sample_of.append(np.full(n_i, i, dtype=np.int32))
+        pitch.append(np.full(n_i, m.stride(1), dtype=np.int32))
+        dtype_id.append(np.full(n_i, _MASK_DTYPES[m.dtype], dtype=np.int32))
+        tap_off.append(np.full(n_i, toff, dtype=np.int32))
         rows_all.append(np.asarray(rows, dtype=np.int64))
         start = 0
         for obj in ann_indices[i]:               # running offset over pooled rows, layer.py:112-119
@@ -116,14 +154,18 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
         base += n_i
 
     q_total = base
-    rows_all = np.concatenate(rows_all) if rows_all else np.zeros(0, np.int64)
+    cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)  # noqa: E731
+    rows_all = cat(rows_all, np.int64)
     if q_total and (rows_all.min() < 0 or rows_all.max() >= n_feat_rows):
         raise IndexError(f"ann_indices refer to feature rows outside [0, {n_feat_rows})")
 
     # groups: object-frames that read the same feature row share one staged copy of it
     order = np.argsort(rows_all, kind="stable")
     sorted_rows = rows_all[order]
-    run_start = np.flatnonzero(np.r_[True, sorted_rows[1:] != sorted_rows[:-1]]) if q_total else np.zeros(0, np.int64)
+    if q_total:
+        run_start = np.flatnonzero(np.r_[True, sorted_rows[1:] != sorted_rows[:-1]])
+    else:
+        run_start = np.zeros(0, np.int64)
     run_len = np.diff(np.r_[run_start, q_total])
     if q_total and run_len.max() > _cabi.MAX_GROUP:
         pieces = [(s + o, min(_cabi.MAX_GROUP, l - o)) for s, l in zip(run_start, run_len)
@@ -131,16 +173,22 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
         run_start = np.array([p[0] for p in pieces], dtype=np.int64)
         run_len = np.array([p[1] for p in pieces], dtype=np.int64)
     n_groups = int(run_start.size)
+    group_of = np.empty(q_total, dtype=np.int32)
+    group_of[order] = np.repeat(np.arange(n_groups, dtype=np.int32), run_len)
+
+    desc = np.zeros(q_total, dtype=MASK_DESC)
+    desc["pitch"] = cat(pitch, np.int32)
+    desc["dtype"] = cat(dtype_id, np.int32)
+    desc["tap_off"] = cat(tap_off, np.int32)
+    desc["group"] = group_of
 
     obj_len_a = np.asarray(obj_len, dtype=np.int32)
     slots = np.minimum(obj_len_a, k_keep).astype(np.int32)
-    slot_off = np.concatenate([[0], np.cumsum(slots)[:-1]]).astype(np.int32) if slots.size else np.zeros(0, np.int32)
-
+    slot_off = (np.concatenate([[0], np.cumsum(slots)[:-1]]).astype(np.int32) if slots.size
+                else np.zeros(0, np.int32))
     host = {
-        "mask_addr": (np.concatenate(addr) if addr else np.zeros(0, np.int64)).astype(np.uint64),
-        "mask_shape": np.concatenate(shape_id) if shape_id else np.zeros(0, np.int32),
-        "shape_tab": np.asarray(shape_rows, dtype=np.int32).reshape(-1),
-        "taps": np.concatenate(tap_chunks) if tap_chunks else np.zeros(0, np.int32),
+        "mask_desc": desc,
+        "taps": cat(tap_chunks, np.int32),
         "grp_row": sorted_rows[run_start].astype(np.int32) if n_groups else np.zeros(0, np.int32),
         "grp_off": np.r_[run_start, q_total].astype(np.int32),
         "grp_member": order.astype(np.int32),
@@ -151,9 +199,30 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
     plan = EncodePlan(n_masks=q_total, n_groups=n_groups,
                       max_group=int(run_len.max()) if n_groups else 1,
                       n_obj=len(obj_len), max_len=int(obj_len_a.max()) if len(obj_len) else 1,
-                      m_pad=int(slots.sum()), slots=slots, host=host, keepalive=masks)
+                      m_pad=int(slots.sum()), slots=slots, host=host,
+                      sample_of=cat(sample_of, np.int32), plane_off=cat(plane_off, np.int64),
+                      expect_counts=[int(s) for s in slots])
+    plan.ticket = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)
+    _fill_addresses(plan, tuple(m.data_ptr() for m in masks))
     _upload(plan, device)
     return plan
+
+
+def _fill_addresses(plan: EncodePlan, ptrs) -> None:
+    if plan.n_masks:
+        base = np.asarray(ptrs, dtype=np.uint64)
+        plan.host["mask_desc"]["addr"] = base[plan.sample_of] + plan.plane_off.astype(np.uint64)
+    plan.base_ptrs = tuple(ptrs)
+
+
+def _patch_addresses(plan: EncodePlan, ptrs, device) -> None:
+    _fill_addresses(plan, ptrs)
+    desc = plan.host["mask_desc"]
+    staging = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy())
+    if device.type == "cuda":
+        staging = staging.pin_memory()
+    off = plan.dev["mask_desc"] - plan.buffer.data_ptr()
+    plan.buffer[off:off + staging.numel()].copy_(staging, non_blocking=True)   # stream-ordered
 
 
 def _upload(plan: EncodePlan, device) -> None:
@@ -169,3 +238,4 @@ def _upload(plan: EncodePlan, device) -> None:
     plan.buffer = staging.to(device, non_blocking=True)
     p0 = plan.buffer.data_ptr()
     plan.dev = {name: p0 + off for name, off in offsets.items()}
+    plan.args = None
