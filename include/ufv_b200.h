@@ -152,6 +152,10 @@ typedef struct ufv_encode_args {
   const int32_t* obj_start; const int32_t* obj_len; const int32_t* slot_off;
   int32_t n_obj; int32_t max_len; int32_t k_keep; int32_t m_pad;
   void* merged; int32_t* counts;
+  /* optional early read-back of the token counts: right after the merge kernel, `counts` is
+   * copied to the pinned HOST buffer counts_host and counts_event (a cudaEvent_t) is recorded, so
+   * the caller can build the reference's list[int] while the projector is still running */
+  int32_t* counts_host; void* counts_event;
   /* projector: feat_linear.0 / feat_linear.2 (layer.py:55-59) */
   const void* w1; const void* b1; const void* w2; const void* b2;
   void* hidden; void* tokens_out;

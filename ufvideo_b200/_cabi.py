@@ -41,7 +41,7 @@ class EncodeArgs(C.Structure):
         ("pooled", _p),
         ("obj_start", _p), ("obj_len", _p), ("slot_off", _p),
         ("n_obj", _i32), ("max_len", _i32), ("k_keep", _i32), ("m_pad", _i32),
-        ("merged", _p), ("counts", _p),
+        ("merged", _p), ("counts", _p), ("counts_host", _p), ("counts_event", _p),
         ("w1", _p), ("b1", _p), ("w2", _p), ("b2", _p),
         ("hidden", _p), ("tokens_out", _p),
     ]

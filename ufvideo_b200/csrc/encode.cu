@@ -72,6 +72,16 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
   rc = ufv_ttm(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
                a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, nullptr, 0, stream);
   if (rc != 0) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->counts_host != nullptr && a->n_obj > 0) {
+    const cudaError_t e = cudaMemcpyAsync(a->counts_host, a->counts, size_t(a->n_obj) * sizeof(int32_t),
+                                          cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return fail(int(e), "ufv_encode: counts read-back: %s", cudaGetErrorString(e));
+  }
+  if (a->counts_event != nullptr) {
+    const cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(a->counts_event), st);
+    if (e != cudaSuccess) return fail(int(e), "ufv_encode: event record: %s", cudaGetErrorString(e));
+  }
   if (a->m_pad == 0) return 0;
   rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, stream);
   if (rc != 0) return rc;

@@ -219,10 +219,22 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
 template <typename T>
 static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
                        int gelu, cudaStream_t stream) {
-  // Small token counts leave few 128-row tiles: narrow N tiles keep more of the 148 SMs busy.
+  // N-tile choice.  At small token counts a CTA's time is what it must pull through its SM's
+  // L2->shared-memory path, (128 + BN) * K * 2 bytes, times the number of waves over the 148 SMs
+  // (one CTA per SM: the stage ring fills shared memory).  Pick the BN with the smallest product.
   const int m_tiles = (m + kBM - 1) / kBM;
-  if (m_tiles * ((n + 127) / 128) >= 148) return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, stream);
-  if (m_tiles * ((n + 63) / 64) >= 148) return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, stream);
+  int best_bn = 32;
+  long best_cost = -1;
+  for (int bn : {32, 64, 128}) {
+    const long ctas = long(m_tiles) * ((n + bn - 1) / bn);
+    const long cost = ((ctas + 147) / 148) * (kBM + bn);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_bn = bn;
+    }
+  }
+  if (best_bn == 128) return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, stream);
+  if (best_bn == 64) return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, stream);
   return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, stream);
 }
 

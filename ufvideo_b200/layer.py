@@ -248,6 +248,11 @@ class MaskExtractor(nn.Module):
                     grp_member=d["grp_member"], n_groups=plan.n_groups, max_group=plan.max_group,
                     obj_start=d["obj_start"], obj_len=d["obj_len"], slot_off=d["slot_off"],
                     n_obj=plan.n_obj, max_len=plan.max_len, k_keep=k_keep, m_pad=m_pad)
+                plan.counts_pinned = torch.empty((max(plan.n_obj, 1),), dtype=torch.int32, pin_memory=True)
+                plan.counts_event = torch.cuda.Event()
+                plan.counts_event.record(torch.cuda.current_stream(device))   # forces creation of the handle
+                a.counts_host = plan.counts_pinned.data_ptr()
+                a.counts_event = plan.counts_event.cuda_event
             a.feats, a.feat_dtype, a.n_rows, a.c, a.hid = feats.data_ptr(), dt, f, c, hid
             a.bits, a.cnt, a.pooled, a.merged = ptr["bits"], ptr["cnt"], ptr["pooled"], ptr["merged"]
             a.grp_nu, a.grp_ulist, a.grp_omask = ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"]
@@ -289,7 +294,12 @@ class MaskExtractor(nn.Module):
         list[int]).  ``X_features`` and ``frame_nums`` are accepted and ignored, as in the reference
         (which reads only ``X_features.device`` in its fallbacks)."""
         tokens, counts, plan = self.encode_padded(feats, masks, ann_indices)
-        region_token_nums = counts.cpu().numpy()   # the one unavoidable D2H: the caller slices by it
+        # the one unavoidable D2H: the caller slices rows by these counts (videorefer_arch.py:307-311)
+        if plan.counts_event is not None and len(self._linears()) == 2:
+            plan.counts_event.synchronize()        # merge kernel done; the projector may still be running
+            region_token_nums = plan.counts_pinned.numpy()[:plan.n_obj].copy()
+        else:
+            region_token_nums = counts.cpu().numpy()
         if np.array_equal(region_token_nums, plan.slots):
             return tokens, list(plan.expect_counts)
         # ties at the merge threshold left some object with fewer than min(T, K) tokens:

@@ -63,6 +63,8 @@ class EncodePlan:
     plane_off: np.ndarray | None = None           # int64 [q] byte offset of its plane in that sample
     base_ptrs: tuple = ()                         # mask tensor base addresses baked into ``buffer``
     args: object = None                           # cached ctypes EncodeArgs
+    counts_pinned: torch.Tensor | None = None     # pinned int32 [n_obj]: early read-back of the counts
+    counts_event: object = None                   # torch.cuda.Event recorded right after the merge kernel
     expect_counts: list = field(default_factory=list)
 
 
