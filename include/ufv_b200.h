@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define UFV_ABI_VERSION 1
+#define UFV_ABI_VERSION 2
 
 /* element types */
 enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3 };
@@ -45,18 +45,26 @@ enum {
 #define UFV_MAX_GROUP 8          /* object-frames pooled together from one staged frame tile */
 #define UFV_PLAN_PITCH 736       /* entries per group in the union-plan arrays (>= 729, % 16 == 0) */
 
-/* One object-frame's mask plane (32 bytes). */
+/* One object-frame's mask plane (32 bytes).  `addr` may point into device memory or into pinned,
+ * device-mapped HOST memory (ufv_device_address): the kernel then reads the mask in place over
+ * PCIe, touching only the rows its taps need. */
 typedef struct ufv_mask_desc {
   uint64_t addr;      /* device address of element (0,0) of the mask plane                     */
   int32_t pitch;      /* row pitch in elements                                                  */
   int32_t dtype;      /* UFV_U8 (also bool) / UFV_F32 / UFV_BF16 / UFV_F16                      */
   int32_t tap_off;    /* offset of the plane's tap table inside `taps`, in int32 units          */
   int32_t group;      /* pool group this object-frame belongs to (index into grp_off)           */
-  int32_t reserved[2];
+  int32_t flags;      /* bit 0: force tap mode (see ufv_mask_to_patches)                        */
+  int32_t reserved;
 } ufv_mask_desc;
 
 int ufv_abi_version(void);
 const char* ufv_last_error(void);
+
+/* Device-visible address of a pinned (page-locked, mapped) host buffer, so that kernels can read
+ * host-resident masks in place.  Returns 0 and sets *dev_addr, or the cudaError_t when `host_ptr`
+ * is not mapped pinned memory. */
+int ufv_device_address(const void* host_ptr, uint64_t* dev_addr_host);
 
 /* ---------------------------------------------------------------------------------------------
  * Host helper: tap table of the bilinear resize of an h x w mask to n_out x n_out.
@@ -73,6 +81,11 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  * Kernel 1: mask resize + binarise -> patch bitmask, count and index list per object-frame,
  * plus the union plan of every pool group.
  * Replaces F.interpolate + (mask > 0) + mask.sum at layer.py:139,143,145.  Bit-exact.
+ * Per object-frame the kernel picks row mode (the two source rows of every output row are read
+ * with coalesced 16-byte loads; used when the tap columns of a row span <= ~2 KB) or tap mode
+ * (every tap gathered individually; wide masks, or desc.flags bit 0).  Both give the same bits.
+ * The 16-byte chunks read in row mode are aligned down/up around the tap span, so a mask plane
+ * must not begin or end closer than 16 bytes to an unmapped page (true for any allocator).
  *   desc[n_masks]        one ufv_mask_desc per object-frame
  *   taps                 concatenated tap tables (ufv_tap_table) the descriptors point into
  *   bits_out[n_masks*UFV_BITS_WORDS]  bit p%32 of word p/32 = patch p (row-major h,w) is on

@@ -55,8 +55,16 @@ def bits_to_bool(bits: torch.Tensor, n=729):
 # ---------------------------------------------------------------------------------------------
 # kernel 1
 # ---------------------------------------------------------------------------------------------
+@pytest.fixture(params=["auto", "taps"])
+def read_mode(request):
+    """Kernel 1 picks row mode or tap mode per mask; 'taps' forces the gather path everywhere."""
+    packer.FORCE_TAP_MODE = request.param == "taps"
+    yield request.param
+    packer.FORCE_TAP_MODE = False
+
+
 @pytest.mark.parametrize("mask_dtype", [torch.uint8, torch.float32, torch.bool, torch.float16, torch.bfloat16])
-def test_patch_bits_match_reference_golden(dev, golden_dir, mask_dtype):
+def test_patch_bits_match_reference_golden(dev, golden_dir, mask_dtype, read_mode):
     g = np.load(os.path.join(golden_dir, "resize.npz"))
     meta = json.loads(str(g["meta"]))
     row = 0
@@ -90,6 +98,25 @@ def test_patch_bits_pad_mode_and_strided_masks(dev):
     plan = packer.build_plan([view], [[list(range(6))]], 6, 1, dev)
     bits = layer.mask_to_patches(plan, dev)["bits"]
     assert np.array_equal(bits_to_bool(bits), np.stack([R.mask_to_patches(m) for m in masks]))
+
+
+@pytest.mark.parametrize("hw", [(384, 384), (480, 854), (720, 1280), (100, 37), (61, 509)])
+@pytest.mark.parametrize("mask_dtype", [torch.float32, torch.uint8, torch.float16])
+def test_pinned_host_masks_are_read_in_place(dev, hw, mask_dtype):
+    """A pinned host mask tensor is not copied: kernel 1 reads it over PCIe through its mapped
+    address (row mode for narrow masks, tap mode for wide ones) and gives the same bits."""
+    h, w = hw
+    masks = synth.masks_sparse(h * 7 + w, 5, h, w, p=0.01)
+    host = torch.from_numpy(masks).to(mask_dtype).pin_memory()
+    # an odd element offset: rows of the view are not 16-byte aligned
+    wide = torch.zeros((5, h, w + 7), dtype=mask_dtype).pin_memory()
+    wide[:, :, 3:3 + w] = host
+    want = np.stack([R.mask_to_patches(m) for m in masks])
+    for t in (host, wide[:, :, 3:3 + w]):
+        plan = packer.build_plan([t], [[list(range(5))]], 5, 1, dev, use_cache=False)
+        assert plan.host["mask_desc"]["addr"][0] != 0
+        bits = layer.mask_to_patches(plan, dev)["bits"]
+        assert np.array_equal(bits_to_bool(bits), want)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -280,6 +307,17 @@ def test_forward_matches_reference_module_golden(dev, golden_dir, name):
     if counts == list(enc.last_plan.slots):
         assert np.array_equal(enc._debug["merged"].float().cpu().numpy(), o["merged"])
     assert np.abs(tokens.float().cpu().numpy() - o["tokens"]).max() <= TOL[dt]
+
+
+def test_forward_with_pinned_host_inputs_equals_device_inputs(dev):
+    """The e2e path: pinned host feats (copied) and pinned host masks (read in place)."""
+    case = gc.e2e_case("bf16")
+    enc = make_encoder(dev, "bf16", 8)
+    feats = torch.from_numpy(case["feats"]).bfloat16()
+    masks = [torch.from_numpy(m).float() for m in case["masks"]]
+    a, na = enc(feats.to(dev), [m.to(dev) for m in masks], None, case["ann"], None)
+    b, nb = enc(feats.pin_memory(), [m.pin_memory() for m in masks], None, case["ann"], None)
+    assert na == nb and torch.equal(a, b)
 
 
 def test_list_and_tensor_mask_forms_agree(dev):

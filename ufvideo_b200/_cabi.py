@@ -21,7 +21,7 @@ BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8
 PLAN_PITCH = 736
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -50,6 +50,7 @@ class EncodeArgs(C.Structure):
 _SIGNATURES = {
     "ufv_abi_version": (C.c_int, []),
     "ufv_last_error": (C.c_char_p, []),
+    "ufv_device_address": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "ufv_tap_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p,
                                       _p, _p]),

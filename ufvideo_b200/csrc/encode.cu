@@ -44,6 +44,19 @@ extern "C" int ufv_abi_version(void) { return UFV_ABI_VERSION; }
 
 extern "C" const char* ufv_last_error(void) { return ufv::g_error; }
 
+extern "C" int ufv_device_address(const void* host_ptr, uint64_t* dev_addr_host) {
+  using namespace ufv;
+  UFV_REQUIRE(host_ptr && dev_addr_host, UFV_E_NULL, "ufv_device_address: null pointer");
+  void* dev = nullptr;
+  const cudaError_t e = cudaHostGetDevicePointer(&dev, const_cast<void*>(host_ptr), 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();   // clear the sticky-less error state
+    return fail(int(e), "ufv_device_address: %s (not mapped pinned memory?)", cudaGetErrorString(e));
+  }
+  *dev_addr_host = reinterpret_cast<uint64_t>(dev);
+  return 0;
+}
+
 extern "C" int ufv_gather_rows(const void* in, const int32_t* row_map, void* out, int n_out_rows,
                                int row_bytes, void* stream) {
   using namespace ufv;

@@ -62,6 +62,41 @@ __device__ __forceinline__ bool mask_positive(uint64_t base, int64_t off, int dt
   }
 }
 
+// "element > 0" flags of one 16-byte chunk, bit e = element e of the chunk
+__device__ __forceinline__ uint32_t chunk_flags(uint4 v, int dtype) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t f = 0;
+  switch (dtype) {
+    case UFV_F32:
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f |= uint32_t(__uint_as_float(w[e]) > 0.0f) << e;
+      break;
+    case UFV_U8:
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t t = __vcmpne4(w[e], 0u);   // 0xff per non-zero byte
+        f |= ((t & 1u) | ((t >> 7) & 2u) | ((t >> 14) & 4u) | ((t >> 21) & 8u)) << (4 * e);
+      }
+      break;
+    case UFV_BF16:
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f |= uint32_t(__uint_as_float(w[e] << 16) > 0.0f) << (2 * e);
+        f |= uint32_t(__uint_as_float(w[e] & 0xffff0000u) > 0.0f) << (2 * e + 1);
+      }
+      break;
+    default:
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+        f |= uint32_t(h.x > 0.0f) << (2 * e);
+        f |= uint32_t(h.y > 0.0f) << (2 * e + 1);
+      }
+      break;
+  }
+  return f;
+}
+
 // exclusive prefix of per-word popcounts, computed by warp 0; s_prefix[UFV_BITS_WORDS] = total
 __device__ __forceinline__ void word_prefix(const uint32_t* s_words, int32_t* s_prefix, int tid) {
   if (tid < 32) {
@@ -77,9 +112,17 @@ __device__ __forceinline__ void word_prefix(const uint32_t* s_words, int32_t* s_
   }
 }
 
-constexpr int kPatchThreads = 256;
+constexpr int kPatchThreads = 384;
+constexpr int kRowChunks = 256;                  // 16-byte chunks of one staged row span (4 KB)
+constexpr int kRowUnroll = 4;                    // chunk loads in flight per thread
 
-__global__ void __launch_bounds__(kPatchThreads)
+// Two ways to read a mask, chosen per object-frame:
+//   row mode  (column span of the taps <= ~4 KB per row): the CTA pulls the 2 * n_out source rows with
+//             coalesced 16-byte loads, reduces every chunk to "element > 0" flags in shared memory and
+//             picks the tap columns out of the flags.  Few, wide requests: this is what keeps PCIe
+//             efficient when the mask lives in pinned HOST memory and is read in place.
+//   tap mode  (wide masks): every thread gathers the four taps of its patches directly.
+__global__ void __launch_bounds__(kPatchThreads, 4)
 mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __restrict__ taps, int n_out,
                        uint32_t* __restrict__ bits_out, int32_t* __restrict__ cnt_out,
                        uint16_t* __restrict__ idx_out, int idx_pitch,
@@ -90,10 +133,13 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   __shared__ uint32_t s_words[UFV_BITS_WORDS];
   __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
   __shared__ uint32_t s_member_bits[UFV_MAX_GROUP][UFV_BITS_WORDS];
+  __shared__ uint16_t s_flags[2 * UFV_MAX_PATCH_SIDE][kRowChunks];
+  __shared__ int s_span[2];
   __shared__ int s_last;
 
   const int j = blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const ufv_mask_desc d = desc[j];
   if (tid < 4 * n_out) s_taps[tid] = taps[d.tap_off + tid];
   __syncthreads();
@@ -103,26 +149,98 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   const int32_t* h1 = s_taps + n_out;
   const int32_t* w0 = s_taps + 2 * n_out;
   const int32_t* w1 = s_taps + 3 * n_out;
-  constexpr int kIters = UFV_BITS_WORDS * 32 / kPatchThreads;
-  bool on[kIters];
+  const int es_shift = d.dtype == UFV_F32 ? 2 : d.dtype == UFV_U8 ? 0 : 1;
+  const int es = 1 << es_shift;
+  if (warp == 0) {   // column span [cmin, cmax] of the valid taps
+    int lo = 0x7fffffff, hi = -1;
+    if (lane < n_out) {
+      const int a = w0[lane], b = w1[lane];
+      if (a >= 0) { lo = min(lo, a); hi = max(hi, a); }
+      if (b >= 0) { lo = min(lo, b); hi = max(hi, b); }
+    }
 #pragma unroll
-  for (int it = 0; it < kIters; ++it) {   // every tap of every iteration is in flight before the ballots
-    const int p = it * kPatchThreads + tid;
-    on[it] = false;
-    if (p < n_patch) {
-      const int i = p / n_out, jx = p - i * n_out;
-      const int ra = h0[i], rb = h1[i], ca = w0[jx], cb = w1[jx];
-      const bool t00 = (ra >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + ca, d.dtype);
-      const bool t01 = (ra >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + cb, d.dtype);
-      const bool t10 = (rb >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + ca, d.dtype);
-      const bool t11 = (rb >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + cb, d.dtype);
-      on[it] = t00 | t01 | t10 | t11;
+    for (int off = 16; off >= 1; off >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if (lane == 0) { s_span[0] = lo; s_span[1] = hi; }
+  }
+  __syncthreads();
+  const int cmin = s_span[0], cmax = s_span[1];
+  const bool row_mode = (d.flags & 1) == 0 && cmax >= 0 && ((cmax - cmin + 1) * es + 30) >> 4 <= kRowChunks;
+
+  constexpr int kIters = (UFV_BITS_WORDS * 32 + kPatchThreads - 1) / kPatchThreads;
+  bool on[kIters];
+  if (row_mode) {
+    const int span_bytes = (cmax - cmin + 1) * es;
+    const int nch = (span_bytes + 30) >> 4;        // chunks per source row, whatever its misalignment
+    const int total = 2 * n_out * nch;             // s_taps[0 .. 2 * n_out) = h0 then h1: one slot per source row
+    for (int f0 = tid; f0 < total; f0 += kRowUnroll * kPatchThreads) {
+      uint4 v[kRowUnroll];
+      int slot[kRowUnroll], chunk[kRowUnroll];
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) {       // all loads of the round in flight before any flag
+        const int f = f0 + u * kPatchThreads;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        slot[u] = -1;
+        if (f < total) {
+          slot[u] = f / nch;
+          chunk[u] = f - slot[u] * nch;
+          const int r = s_taps[slot[u]];
+          const uint64_t first = d.addr + uint64_t(int64_t(max(r, 0)) * d.pitch + cmin) * es;
+          const int mis = int(first & 15u);
+          if (r >= 0 && chunk[u] < ((mis + span_bytes + 15) >> 4))
+            v[u] = reinterpret_cast<const uint4*>(first - mis)[chunk[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u)
+        if (slot[u] >= 0) s_flags[slot[u]][chunk[u]] = uint16_t(chunk_flags(v[u], d.dtype));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int p = it * kPatchThreads + tid;
+      bool hit = false;
+      if (p < n_patch) {
+        const int i = p / n_out, jx = p - i * n_out;
+        const int c[2] = {w0[jx], w1[jx]};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int r = s_taps[s * n_out + i];
+          if (r < 0) continue;
+          const int mis = int((d.addr + uint64_t(int64_t(r) * d.pitch + cmin) * es) & 15u);
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (c[u] >= 0) {
+              const int off = mis + (c[u] - cmin) * es;
+              hit |= (s_flags[s * n_out + i][off >> 4] >> ((off & 15) >> es_shift)) & 1u;
+            }
+        }
+      }
+      on[it] = hit;
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {   // every tap of every iteration is in flight before the ballots
+      const int p = it * kPatchThreads + tid;
+      on[it] = false;
+      if (p < n_patch) {
+        const int i = p / n_out, jx = p - i * n_out;
+        const int ra = h0[i], rb = h1[i], ca = w0[jx], cb = w1[jx];
+        const bool t00 = (ra >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + ca, d.dtype);
+        const bool t01 = (ra >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + cb, d.dtype);
+        const bool t10 = (rb >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + ca, d.dtype);
+        const bool t11 = (rb >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + cb, d.dtype);
+        on[it] = t00 | t01 | t10 | t11;
+      }
     }
   }
 #pragma unroll
   for (int it = 0; it < kIters; ++it) {
     const uint32_t word = __ballot_sync(0xffffffffu, on[it]);
-    if ((tid & 31) == 0) s_words[(it * kPatchThreads + tid) >> 5] = word;
+    const int wi = (it * kPatchThreads + tid) >> 5;
+    if (lane == 0 && wi < UFV_BITS_WORDS) s_words[wi] = word;
   }
   __syncthreads();
   word_prefix(s_words, s_prefix, tid);

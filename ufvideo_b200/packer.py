@@ -24,8 +24,13 @@ FEAT_DTYPES = {torch.float32: _cabi.UFV_F32, torch.bfloat16: _cabi.UFV_BF16, tor
 
 # mirror of struct ufv_mask_desc (include/ufv_b200.h), 32 bytes
 MASK_DESC = np.dtype([("addr", "<u8"), ("pitch", "<i4"), ("dtype", "<i4"), ("tap_off", "<i4"),
-                      ("group", "<i4"), ("reserved", "<i4", (2,))])
+                      ("group", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
 assert MASK_DESC.itemsize == 32
+
+# A pinned host mask tensor is not copied: kernel 1 reads it through its mapped device address and
+# touches only the rows its taps need (384x384 fp32: 83 KB of 590 KB).  Developer knobs below.
+READ_PINNED_MASKS_IN_PLACE = True
+FORCE_TAP_MODE = False
 
 _tap_cache: dict = {}
 _plan_cache: "OrderedDict[tuple, EncodePlan]" = OrderedDict()
@@ -82,7 +87,9 @@ def _as_mask_list(masks, device):
             m = torch.zeros((1, 336, 336), dtype=torch.uint8, device=device)
         if m.dtype not in _MASK_DTYPES:          # exotic dtypes: binarise once on the device
             m = (m.to(device) > 0).to(torch.uint8)
-        if m.device != device:
+        in_place = m.device == device or (READ_PINNED_MASKS_IN_PLACE and device.type == "cuda"
+                                          and m.device.type == "cpu" and m.is_pinned())
+        if not in_place:                         # pageable host memory / another device: copy
             m = m.to(device, non_blocking=True)
         if m.stride(-1) != 1:
             m = m.contiguous()
@@ -90,25 +97,34 @@ def _as_mask_list(masks, device):
     return out
 
 
+def _device_address(m: torch.Tensor) -> int:
+    """Address kernel 1 reads the mask at: the tensor's own pointer on the device, the mapped
+    device alias of a pinned host tensor otherwise (the kernel then reads it in place over PCIe)."""
+    if m.device.type != "cpu" or not m.is_pinned():
+        return m.data_ptr()
+    dev = ctypes.c_uint64(0)
+    _cabi.check(_cabi.lib().ufv_device_address(ctypes.c_void_p(m.data_ptr()), ctypes.byref(dev)))
+    return int(dev.value)
+
+
 def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_square: bool = False,
                n_out: int = _cabi.MAX_PATCH_SIDE, use_cache: bool = True) -> EncodePlan:
     masks = _as_mask_list(masks, device)
     if len(ann_indices) != len(masks):
         raise ValueError("ann_indices and masks disagree on the number of samples")
-    ptrs = tuple(m.data_ptr() for m in masks)
+    ptrs = tuple(_device_address(m) for m in masks)
     key = None
     if use_cache:
         key = (tuple(tuple(tuple(o) for o in s) for s in ann_indices),
                tuple((tuple(m.shape), m.stride(), m.dtype) for m in masks),
-               n_feat_rows, k_keep, bool(pad_square), n_out, str(device))
+               n_feat_rows, k_keep, bool(pad_square), n_out, str(device), FORCE_TAP_MODE)
         plan = _plan_cache.get(key)
         if plan is not None:
             _plan_cache.move_to_end(key)
             if plan.base_ptrs != ptrs:           # same structure, new mask tensors: patch addresses
                 _patch_addresses(plan, ptrs, device)
             return plan
-    plan = _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out)
-    plan.base_ptrs = ptrs
+    plan = _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, ptrs)
     if key is not None:
         _plan_cache[key] = plan
         while len(_plan_cache) > PLAN_CACHE_SIZE:
@@ -116,7 +132,7 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
     return plan
 
 
-def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out) -> EncodePlan:
+def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, ptrs) -> EncodePlan:
     pitch, dtype_id, tap_off, sample_of, plane_off, rows_all = [], [], [], [], [], []
     taps, tap_chunks, tap_len = {}, [], 0
     obj_start, obj_len = [], []
@@ -183,6 +199,7 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out) -
     desc["dtype"] = cat(dtype_id, np.int32)
     desc["tap_off"] = cat(tap_off, np.int32)
     desc["group"] = group_of
+    desc["flags"] = 1 if FORCE_TAP_MODE else 0
 
     obj_len_a = np.asarray(obj_len, dtype=np.int32)
     slots = np.minimum(obj_len_a, k_keep).astype(np.int32)
@@ -205,7 +222,7 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out) -
                       sample_of=cat(sample_of, np.int32), plane_off=cat(plane_off, np.int64),
                       expect_counts=[int(s) for s in slots])
     plan.ticket = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)
-    _fill_addresses(plan, tuple(m.data_ptr() for m in masks))
+    _fill_addresses(plan, ptrs)
     _upload(plan, device)
     return plan
 
