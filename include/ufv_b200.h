@@ -15,6 +15,9 @@
  *     ufv_last_error() returns a thread-local message for the last non-zero return.
  *   - no global mutable state, no hidden allocation: the caller owns every buffer, calls are
  *     stream-ordered and re-entrant across streams.
+ *   - kernels are launched with programmatic stream serialization and open with
+ *     griddepcontrol.wait, so back-to-back calls overlap their launch latency and prologues but
+ *     never their data dependencies.
  *   - there is no CPU path: without a CUDA device every compute call returns an error.
  */
 #ifndef UFV_B200_H
@@ -26,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UFV_ABI_VERSION 2
+#define UFV_ABI_VERSION 3
 
 /* element types */
 enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3 };
@@ -54,7 +57,7 @@ typedef struct ufv_mask_desc {
   int32_t dtype;      /* UFV_U8 (also bool) / UFV_F32 / UFV_BF16 / UFV_F16                      */
   int32_t tap_off;    /* offset of the plane's tap table inside `taps`, in int32 units          */
   int32_t group;      /* pool group this object-frame belongs to (index into grp_off)           */
-  int32_t flags;      /* bit 0: force tap mode (see ufv_mask_to_patches)                        */
+  int32_t flags;      /* bit 0: read in row mode when the tap span fits (see ufv_mask_to_patches) */
   int32_t reserved;
 } ufv_mask_desc;
 
@@ -81,9 +84,10 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  * Kernel 1: mask resize + binarise -> patch bitmask, count and index list per object-frame,
  * plus the union plan of every pool group.
  * Replaces F.interpolate + (mask > 0) + mask.sum at layer.py:139,143,145.  Bit-exact.
- * Per object-frame the kernel picks row mode (the two source rows of every output row are read
- * with coalesced 16-byte loads; used when the tap columns of a row span <= ~2 KB) or tap mode
- * (every tap gathered individually; wide masks, or desc.flags bit 0).  Both give the same bits.
+ * Per object-frame the kernel reads in tap mode (every tap gathered individually: lowest latency
+ * for masks in HBM) or, when desc.flags bit 0 is set and the tap columns of a row span <= 4 KB,
+ * in row mode (the source rows of every output row are read with coalesced 16-byte loads: few,
+ * wide requests, the efficient pattern over PCIe for pinned host masks).  Both give the same bits.
  * The 16-byte chunks read in row mode are aligned down/up around the tap span, so a mask plane
  * must not begin or end closer than 16 bytes to an unmapped page (true for any allocator).
  *   desc[n_masks]        one ufv_mask_desc per object-frame
@@ -130,11 +134,16 @@ int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, int n_patch
  *   tokens_out [m_pad, c] of out_dtype; tokens_f32_out (optional) the same rows before the
  *   downcast; cuts_out (optional) [n_obj * cut_pitch_words] uint32, bit i set = run boundary
  *   after token i; sims_out (optional) [n_obj * sims_pitch] fp32 adjacent cosine similarities.
+ *   Early read-back of the counts (optional, pass counts_host = null to skip): counts_host is the
+ *   device-visible address (ufv_device_address) of a pinned int32[n_obj + 1]; every object's
+ *   count is also stored there and the last CTA then writes `epoch` into element n_obj, which the
+ *   host can poll.  done_ticket is one zeroed uint32 in device memory (zero again on completion).
  * -------------------------------------------------------------------------------------------*/
 int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
             const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
             int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
-            int cut_pitch_words, float* sims_out, int sims_pitch, void* stream);
+            int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
+            uint32_t* done_ticket, int32_t epoch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 4: one Linear (+ optional exact-erf GELU) of the object projector,
@@ -165,10 +174,10 @@ typedef struct ufv_encode_args {
   const int32_t* obj_start; const int32_t* obj_len; const int32_t* slot_off;
   int32_t n_obj; int32_t max_len; int32_t k_keep; int32_t m_pad;
   void* merged; int32_t* counts;
-  /* optional early read-back of the token counts: right after the merge kernel, `counts` is
-   * copied to the pinned HOST buffer counts_host and counts_event (a cudaEvent_t) is recorded, so
-   * the caller can build the reference's list[int] while the projector is still running */
-  int32_t* counts_host; void* counts_event;
+  /* optional early read-back of the token counts (see ufv_ttm): the merge kernel stores them into
+   * the pinned buffer behind counts_host and stamps `epoch` after them, so the caller can build the
+   * reference's list[int] while the projector is still running */
+  int32_t* counts_host; uint32_t* ttm_ticket; int32_t epoch; int32_t reserved;
   /* projector: feat_linear.0 / feat_linear.2 (layer.py:55-59) */
   const void* w1; const void* b1; const void* w2; const void* b2;
   void* hidden; void* tokens_out;

@@ -55,12 +55,12 @@ def bits_to_bool(bits: torch.Tensor, n=729):
 # ---------------------------------------------------------------------------------------------
 # kernel 1
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(params=["auto", "taps"])
+@pytest.fixture(params=["rows", "taps"])
 def read_mode(request):
-    """Kernel 1 picks row mode or tap mode per mask; 'taps' forces the gather path everywhere."""
-    packer.FORCE_TAP_MODE = request.param == "taps"
+    """Kernel 1 reads a mask in row mode or tap mode (packer.READ_MODE 'auto' picks by residence)."""
+    packer.READ_MODE = request.param
     yield request.param
-    packer.FORCE_TAP_MODE = False
+    packer.READ_MODE = "auto"
 
 
 @pytest.mark.parametrize("mask_dtype", [torch.uint8, torch.float32, torch.bool, torch.float16, torch.bfloat16])
@@ -102,7 +102,7 @@ def test_patch_bits_pad_mode_and_strided_masks(dev):
 
 @pytest.mark.parametrize("hw", [(384, 384), (480, 854), (720, 1280), (100, 37), (61, 509)])
 @pytest.mark.parametrize("mask_dtype", [torch.float32, torch.uint8, torch.float16])
-def test_pinned_host_masks_are_read_in_place(dev, hw, mask_dtype):
+def test_pinned_host_masks_are_read_in_place(dev, hw, mask_dtype, read_mode):
     """A pinned host mask tensor is not copied: kernel 1 reads it over PCIe through its mapped
     address (row mode for narrow masks, tap mode for wide ones) and gives the same bits."""
     h, w = hw

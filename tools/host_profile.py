@@ -1,0 +1,49 @@
+"""Developer tool: where the host time of MaskExtractor.forward goes (cProfile + wall clock)."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+import types
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ufvideo_b200 import build_region_encoder, synth  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda:0")
+    feats, masks, ann = synth.make_batch(8, 16, 4, "dense")
+    ft = torch.from_numpy(feats).to(dev).bfloat16()
+    md = [torch.from_numpy(m).to(dev).float() for m in masks]
+    enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
+    enc.region_token_num = 8
+    enc = enc.to(dev).bfloat16()
+    for _ in range(20):
+        enc(ft, md, None, ann, None)
+    torch.cuda.synchronize()
+    n = 2000
+    t0 = time.perf_counter()
+    for _ in range(n):
+        enc(ft, md, None, ann, None)
+    torch.cuda.synchronize()
+    print(f"forward wall: {(time.perf_counter() - t0) / n * 1e6:.1f} us/call")
+    t0 = time.perf_counter()
+    for _ in range(n):
+        enc.encode_padded(ft, md, ann)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print(f"encode_padded host-only: {(t1 - t0) / n * 1e6:.1f} us/call, with drain {(time.perf_counter() - t0) / n * 1e6:.1f}")
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(n):
+        enc(ft, md, None, ann, None)
+    pr.disable()
+    torch.cuda.synchronize()
+    st = pstats.Stats(pr)
+    st.sort_stats("cumulative").print_stats(25)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,13 +64,12 @@ def main():
     for mdt, mname in ((torch.float32, "f32"), (torch.uint8, "u8")):
         mh = [torch.from_numpy(m).to(mdt).pin_memory() for m in masks]
         mdv = [m.to(dev) for m in mh]
-        for force in (False, True):
-            packer.FORCE_TAP_MODE = force
+        for mode in ("rows", "taps"):
+            packer.READ_MODE = mode
             for where, mm in (("dev", mdv), ("host", mh)):
                 pl = packer.build_plan(mm, ann, ft.shape[0], a.k, dev, use_cache=False)
-                res[f"k1 {mname} {where} {'taps' if force else 'auto'}"] = timed(
-                    lambda: layer.mask_to_patches(pl, dev), iters=10)
-        packer.FORCE_TAP_MODE = False
+                res[f"k1 {mname} {where} {mode}"] = timed(lambda: layer.mask_to_patches(pl, dev), iters=10)
+        packer.READ_MODE = "auto"
     res["k2 pool"] = timed(lambda: layer.mask_pool(ft, plan, patches))
     res["k3 ttm"] = timed(lambda: layer.ttm(pooled, plan, a.k, dt))
     res["k4a linear1+gelu"] = timed(lambda: layer.linear(merged, l0.weight, l0.bias, True))

@@ -21,7 +21,7 @@ BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8
 PLAN_PITCH = 736
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -41,7 +41,8 @@ class EncodeArgs(C.Structure):
         ("pooled", _p),
         ("obj_start", _p), ("obj_len", _p), ("slot_off", _p),
         ("n_obj", _i32), ("max_len", _i32), ("k_keep", _i32), ("m_pad", _i32),
-        ("merged", _p), ("counts", _p), ("counts_host", _p), ("counts_event", _p),
+        ("merged", _p), ("counts", _p), ("counts_host", _p), ("ttm_ticket", _p), ("epoch", _i32),
+        ("reserved", _i32),
         ("w1", _p), ("b1", _p), ("w2", _p), ("b2", _p),
         ("hidden", _p), ("tokens_out", _p),
     ]
@@ -57,7 +58,7 @@ _SIGNATURES = {
     "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_int,
                                 C.c_int, _p, _p]),
     "ufv_ttm": (C.c_int, [_p, C.c_int, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p,
-                          _p, C.c_int, _p, C.c_int, _p]),
+                          _p, C.c_int, _p, C.c_int, _p, _p, _i32, _p]),
     "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "ufv_encode": (C.c_int, [C.POINTER(EncodeArgs), _p]),
     "ufv_gather_rows": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p]),

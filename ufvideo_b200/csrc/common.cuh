@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/ufv_b200.h"
 
 namespace ufv {
@@ -14,7 +16,7 @@ namespace ufv {
 // ---- error plumbing ---------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
-int check_launch(const char* what);   // cudaGetLastError() -> 0 or the cudaError_t (message set)
+int check_launch(const char* what, cudaError_t launch_rc = cudaSuccess);   // 0 or the cudaError_t (message set)
 
 #define UFV_REQUIRE(cond, code, ...)                      \
   do {                                                    \
@@ -23,7 +25,37 @@ int check_launch(const char* what);   // cudaGetLastError() -> 0 or the cudaErro
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- launches -----------------------------------------------------------------------------------
+// Every kernel of the path is launched with programmatic stream serialization (PDL): the next
+// kernel's CTAs become resident and run their prologue (barrier init, TMEM allocation, descriptor
+// prefetch) while the previous kernel drains, and block in pdl_wait() until its results are
+// complete and visible.  UFV_NO_PDL=1 in the environment disables the attribute (A/B knob).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- small device utilities ---------------------------------------------------------------------
+// Block until every kernel this one depends on has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Allow the next kernel in the stream to start launching (it still waits in its own pdl_wait()).
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

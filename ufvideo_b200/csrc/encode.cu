@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 namespace ufv {
 
@@ -23,8 +24,14 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-int check_launch(const char* what) {
-  const cudaError_t e = cudaGetLastError();
+bool pdl_enabled() {
+  static const bool on = getenv("UFV_NO_PDL") == nullptr;
+  return on;
+}
+
+int check_launch(const char* what, cudaError_t launch_rc) {
+  const cudaError_t e = launch_rc != cudaSuccess ? launch_rc : cudaGetLastError();
+  if (launch_rc != cudaSuccess) cudaGetLastError();
   if (e == cudaSuccess) return 0;
   set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
   return static_cast<int>(e);
@@ -32,6 +39,8 @@ int check_launch(const char* what) {
 
 __global__ void gather_rows_kernel(const uint4* __restrict__ in, const int32_t* __restrict__ row_map,
                                    uint4* __restrict__ out, int vec_per_row) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int r = blockIdx.x;
   const uint4* src = in + size_t(row_map[r]) * vec_per_row;
   uint4* dst = out + size_t(r) * vec_per_row;
@@ -65,9 +74,10 @@ extern "C" int ufv_gather_rows(const void* in, const int32_t* row_map, void* out
   if (n_out_rows == 0) return 0;
   UFV_REQUIRE(in && row_map && out, UFV_E_NULL, "ufv_gather_rows: null pointer");
   UFV_REQUIRE(aligned16(in) && aligned16(out), UFV_E_ALIGN, "ufv_gather_rows: unaligned buffer");
-  gather_rows_kernel<<<n_out_rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(in), row_map, static_cast<uint4*>(out), row_bytes / 16);
-  return check_launch("ufv_gather_rows");
+  return check_launch("ufv_gather_rows",
+                      launch_kernel(gather_rows_kernel, dim3(n_out_rows), dim3(128), 0,
+                                    static_cast<cudaStream_t>(stream), static_cast<const uint4*>(in), row_map,
+                                    static_cast<uint4*>(out), row_bytes / 16));
 }
 
 extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
@@ -83,18 +93,9 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
                      a->pooled, stream);
   if (rc != 0) return rc;
   rc = ufv_ttm(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
-               a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, nullptr, 0, stream);
+               a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, nullptr, 0, a->counts_host,
+               a->ttm_ticket, a->epoch, stream);
   if (rc != 0) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->counts_host != nullptr && a->n_obj > 0) {
-    const cudaError_t e = cudaMemcpyAsync(a->counts_host, a->counts, size_t(a->n_obj) * sizeof(int32_t),
-                                          cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return fail(int(e), "ufv_encode: counts read-back: %s", cudaGetErrorString(e));
-  }
-  if (a->counts_event != nullptr) {
-    const cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(a->counts_event), st);
-    if (e != cudaSuccess) return fail(int(e), "ufv_encode: event record: %s", cudaGetErrorString(e));
-  }
   if (a->m_pad == 0) return 0;
   rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, stream);
   if (rc != 0) return rc;

@@ -107,6 +107,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tmem_alloc(&s_tmem_base, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_wait();                  // x (and, transitively, the parameters) come from earlier kernels
+  pdl_launch_dependents();
   if (threadIdx.x >= 64) {
     for (int i = threadIdx.x - 64; i < BN; i += kGemmThreads - 64)
       s_bias[i] = (n0 + i) < n ? Elem<T>::to_f32(bias[n0 + i]) : 0.f;
@@ -205,15 +207,16 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
   if (gelu) {
     auto kernel = linear_tc_kernel<T, BN, true>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    kernel<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tx, tw, static_cast<const T*>(bias),
-                                                       static_cast<T*>(y), m, n, k);
+    return check_launch("ufv_linear (tcgen05)",
+                        launch_kernel(kernel, grid, dim3(kGemmThreads), Cfg::kSmem, stream, tx, tw,
+                                      static_cast<const T*>(bias), static_cast<T*>(y), m, n, k));
   } else {
     auto kernel = linear_tc_kernel<T, BN, false>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    kernel<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tx, tw, static_cast<const T*>(bias),
-                                                       static_cast<T*>(y), m, n, k);
+    return check_launch("ufv_linear (tcgen05)",
+                        launch_kernel(kernel, grid, dim3(kGemmThreads), Cfg::kSmem, stream, tx, tw,
+                                      static_cast<const T*>(bias), static_cast<T*>(y), m, n, k));
   }
-  return check_launch("ufv_linear (tcgen05)");
 }
 
 template <typename T>
@@ -251,6 +254,8 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
   const int m0 = blockIdx.y * kSBM, n0 = blockIdx.x * kSBN;
   const int tr = tid / 16, tc = tid % 16;   // thread tile: rows tr*2.., cols tc*4..
   float acc[2][4] = {};
+  pdl_wait();
+  pdl_launch_dependents();
   for (int k0 = 0; k0 < k; k0 += kSBK) {
     for (int i = tid; i < kSBM * kSBK; i += kSimtThreads) {
       const int r = i / kSBK, kk = i % kSBK;
@@ -303,15 +308,11 @@ extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == UFV_F32) {
     const dim3 grid((n + kSBN - 1) / kSBN, (m + kSBM - 1) / kSBM);
-    if (gelu)
-      linear_f32_kernel<true><<<grid, kSimtThreads, 0, st>>>(
-          static_cast<const float*>(x), static_cast<const float*>(w), static_cast<const float*>(bias),
-          static_cast<float*>(y), m, n, k);
-    else
-      linear_f32_kernel<false><<<grid, kSimtThreads, 0, st>>>(
-          static_cast<const float*>(x), static_cast<const float*>(w), static_cast<const float*>(bias),
-          static_cast<float*>(y), m, n, k);
-    return check_launch("ufv_linear (fp32)");
+    auto kernel = gelu ? linear_f32_kernel<true> : linear_f32_kernel<false>;
+    return check_launch("ufv_linear (fp32)",
+                        launch_kernel(kernel, grid, dim3(kSimtThreads), 0, st, static_cast<const float*>(x),
+                                      static_cast<const float*>(w), static_cast<const float*>(bias),
+                                      static_cast<float*>(y), m, n, k));
   }
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "ufv_linear: unsupported dtype %d", dtype);
   UFV_REQUIRE(k % 8 == 0 && n % 8 == 0, UFV_E_SHAPE, "ufv_linear: k=%d and n=%d must be multiples of 8", k, n);

@@ -33,13 +33,31 @@ __device__ __forceinline__ bool ranks_above(float a, float b) {
   return a > b || (a != a && b == b);
 }
 
+// Token count of object o: to the device array and, when the caller asked for it, straight into
+// pinned host memory.  The CTA that publishes last stamps `epoch` behind the counts, which is what
+// the host polls: the reference's list[int] is ready as soon as the merge decisions are, with no
+// copy, event or stream synchronisation in between.
+__device__ __forceinline__ void publish_count(int32_t* counts_out, int32_t* counts_host,
+                                              uint32_t* done_ticket, int32_t epoch, int o, int count) {
+  counts_out[o] = count;
+  if (counts_host == nullptr) return;
+  counts_host[o] = count;
+  __threadfence_system();
+  if (atomicAdd(done_ticket, 1u) == gridDim.x - 1) {
+    *done_ticket = 0u;                    // self-reset for the next call
+    __threadfence_system();
+    *reinterpret_cast<volatile int32_t*>(counts_host + gridDim.x) = epoch;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kTtmThreads)
 ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ obj_start,
            const int32_t* __restrict__ obj_len, const int32_t* __restrict__ slot_off, int k_keep,
            int max_len, T* __restrict__ tokens_out, float* __restrict__ tokens_f32_out,
            int32_t* __restrict__ counts_out, uint32_t* __restrict__ cuts_out, int cut_pitch_words,
-           float* __restrict__ sims_out, int sims_pitch) {
+           float* __restrict__ sims_out, int sims_pitch, int32_t* __restrict__ counts_host,
+           uint32_t* __restrict__ done_ticket, int32_t epoch) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const int len_words = (max_len + 31) / 32;
   float* s_norm = reinterpret_cast<float*>(dyn_smem);          // [max_len]
@@ -51,6 +69,8 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
 
   const int o = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();                  // pooled rows come from kernel 2
+  pdl_launch_dependents();
   const int t_len = obj_len[o];
   const int slot = slot_off[o];
   const float* x = pooled + size_t(obj_start[o]) * c;
@@ -71,7 +91,7 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
       tokens_out[dst + 2] = Elem<T>::from_f32(v.z);
       tokens_out[dst + 3] = Elem<T>::from_f32(v.w);
     }
-    if (tid == 0) counts_out[o] = t_len;
+    if (tid == 0) publish_count(counts_out, counts_host, done_ticket, epoch, o, t_len);
     return;
   }
 
@@ -182,7 +202,7 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
   }
   if (tid == 0) {
     s_gend[n_cut] = t_len - 1;            // the last run always ends at the last token (:29-31)
-    counts_out[o] = count;
+    publish_count(counts_out, counts_host, done_ticket, epoch, o, count);
   }
   if (cuts_out != nullptr)
     for (int w = tid; w < min(len_words, cut_pitch_words); w += kTtmThreads)
@@ -224,16 +244,18 @@ template <typename T>
 static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
                       const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
                       float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
-                      int cut_pitch_words, float* sims_out, int sims_pitch, cudaStream_t stream) {
+                      int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
+                      uint32_t* done_ticket, int32_t epoch, cudaStream_t stream) {
   const int len_words = (max_len + 31) / 32;
   const size_t smem = size_t(max_len) * 8 + size_t(len_words) * 4 + size_t(len_words + 1) * 4 +
                       size_t(k_keep + 1) * 4;
   auto kernel = ttm_kernel<T>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  kernel<<<n_obj, kTtmThreads, smem, stream>>>(pooled, c, obj_start, obj_len, slot_off, k_keep, max_len,
-                                               static_cast<T*>(tokens_out), tokens_f32_out, counts_out,
-                                               cuts_out, cut_pitch_words, sims_out, sims_pitch);
-  return check_launch("ufv_ttm");
+  return check_launch("ufv_ttm",
+                      launch_kernel(kernel, dim3(n_obj), dim3(kTtmThreads), smem, stream, pooled, c, obj_start,
+                                    obj_len, slot_off, k_keep, max_len, static_cast<T*>(tokens_out),
+                                    tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out,
+                                    sims_pitch, counts_host, done_ticket, epoch));
 }
 
 }  // namespace ufv
@@ -241,7 +263,8 @@ static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, cons
 extern "C" int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
                        const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
                        int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
-                       int cut_pitch_words, float* sims_out, int sims_pitch, void* stream) {
+                       int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
+                       uint32_t* done_ticket, int32_t epoch, void* stream) {
   using namespace ufv;
   UFV_REQUIRE(n_obj >= 0, UFV_E_SHAPE, "ufv_ttm: n_obj=%d", n_obj);
   if (n_obj == 0) return 0;
@@ -255,18 +278,20 @@ extern "C" int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, con
   UFV_REQUIRE(cuts_out == nullptr || cut_pitch_words >= (max_len + 31) / 32, UFV_E_SHAPE,
               "ufv_ttm: cut_pitch_words too small");
   UFV_REQUIRE(sims_out == nullptr || sims_pitch >= max_len - 1, UFV_E_SHAPE, "ufv_ttm: sims_pitch too small");
+  UFV_REQUIRE(counts_host == nullptr || done_ticket != nullptr, UFV_E_NULL,
+              "ufv_ttm: counts_host needs done_ticket");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (out_dtype) {
     case UFV_F32:
       return launch_ttm<float>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep, tokens_out,
-                               tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, st);
+                               tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, done_ticket, epoch, st);
     case UFV_BF16:
       return launch_ttm<__nv_bfloat16>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep,
                                        tokens_out, tokens_f32_out, counts_out, cuts_out, cut_pitch_words,
-                                       sims_out, sims_pitch, st);
+                                       sims_out, sims_pitch, counts_host, done_ticket, epoch, st);
     case UFV_F16:
       return launch_ttm<__half>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep, tokens_out,
-                                tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, st);
+                                tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, done_ticket, epoch, st);
     default:
       return fail(UFV_E_DTYPE, "ufv_ttm: unsupported output dtype %d", out_dtype);
   }

@@ -102,7 +102,8 @@ def ttm(pooled: torch.Tensor, plan: packer.EncodePlan, k_keep: int, out_dtype: t
         pooled.data_ptr(), c, d["obj_start"], d["obj_len"], d["slot_off"], plan.n_obj, plan.max_len,
         k_keep, tokens.data_ptr(), packer.FEAT_DTYPES[out_dtype],
         f32.data_ptr() if debug else None, counts.data_ptr(), cuts.data_ptr() if debug else None,
-        words, sims.data_ptr() if debug else None, max(plan.max_len, 1), _stream_ptr(device)))
+        words, sims.data_ptr() if debug else None, max(plan.max_len, 1), None, None, 0,
+        _stream_ptr(device)))
     return tokens, counts, extras
 
 
@@ -126,6 +127,20 @@ def gather_rows(x: torch.Tensor, row_map: torch.Tensor):
                                             row_map.numel(), x.shape[1] * x.element_size(),
                                             _stream_ptr(x.device)))
     return out
+
+
+def _await_counts(plan: packer.EncodePlan, device) -> np.ndarray:
+    """Poll the epoch stamp kernel 3 writes behind the counts in pinned host memory."""
+    flag, n, epoch = plan.counts_np, plan.n_obj, plan.epoch
+    spins = 0
+    while flag[n] != epoch:
+        spins += 1
+        if spins & 0xffff == 0:                  # every ~10 ms: surface a failed launch instead of hanging
+            stream = torch.cuda.current_stream(device)
+            if stream.query() and flag[n] != epoch:
+                torch.cuda.synchronize(device)
+                raise RuntimeError("ufvideo_b200: the merge kernel finished without publishing its counts")
+    return flag[:n]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -195,24 +210,29 @@ class MaskExtractor(nn.Module):
     def _linears(self):
         return [m for m in self.feat_linear if isinstance(m, nn.Linear)]
 
-    @torch.no_grad()
     def encode_padded(self, feats, masks, ann_indices):
         """Kernels 1-4 without the host read-back: returns (tokens [m_pad, hid], counts int32
-        [n_obj] on the device, plan).  Row r of an object is valid iff r < counts[object]."""
+        [n_obj] on the device, plan).  Row r of an object is valid iff r < counts[object].
+
+        Host work per call is kept to the plan lookup and ONE C call: the workspace, the argument
+        struct and the pinned counts buffer live in the cached plan and are reused as long as the
+        same pointers come back on the same stream (stream order makes the reuse safe)."""
         linears = self._linears()
-        device = linears[0].weight.device
+        w1 = linears[0].weight
+        device = w1.device
         if device.type != "cuda":
             raise RuntimeError("MaskExtractor parameters must be on a CUDA device (no CPU path)")
         if not torch.is_tensor(feats):
             raise TypeError("feats must be a tensor [F, n_patch, C]")
         if feats.device != device:
             feats = feats.to(device, non_blocking=True)
-        feats = feats.contiguous()
+        if not feats.is_contiguous():
+            feats = feats.contiguous()
         if feats.dim() != 3:
             raise ValueError(f"feats must be [F, n_patch, C], got {tuple(feats.shape)}")
         dt = _feat_dtype(feats)
-        if linears[0].weight.dtype != feats.dtype:
-            raise TypeError(f"feature dtype {feats.dtype} != projector dtype {linears[0].weight.dtype}")
+        if w1.dtype != feats.dtype:
+            raise TypeError(f"feature dtype {feats.dtype} != projector dtype {w1.dtype}")
         f, n_patch, c = feats.shape
         side = int(round(n_patch ** 0.5))         # layer.py:100
         if side * side != n_patch or side > _cabi.MAX_PATCH_SIDE:
@@ -222,6 +242,49 @@ class MaskExtractor(nn.Module):
                                  self.image_aspect_ratio == "pad", side)
         self.last_plan = plan
         hid = linears[-1].weight.shape[0]
+        q, m_pad = plan.n_masks, plan.m_pad
+        stream = torch._C._cuda_getCurrentRawStream(device.index)
+        two = len(linears) == 2
+        sig = (feats.data_ptr(), dt, f, c, hid, stream, two,
+               tuple(p.data_ptr() for lin in linears for p in (lin.weight, lin.bias)))
+        run = plan.run
+        if run is None or run["sig"] != sig:
+            run = plan.run = self._prepare_run(plan, sig, feats, linears, side, k_keep, device)
+        tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
+        lib = _cabi.lib()
+        ptr = run["ptr"]
+        d = plan.dev
+        if two:                                   # the reference's depth=2 projector: one chained call
+            a = run["args"]
+            a.tokens_out = tokens.data_ptr()
+            a.epoch = plan.epoch = (plan.epoch + 1) & 0x3fffffff
+            _cabi.check(lib.ufv_encode(run["args_ref"], stream))
+        else:                                     # other depths: the same kernels, staged
+            _cabi.check(lib.ufv_mask_to_patches(d["mask_desc"], d["taps"], q, side, ptr["bits"], ptr["cnt"],
+                                                None, 0, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
+                                                ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], stream))
+            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, n_patch, c, ptr["cnt"], d["grp_row"],
+                                          d["grp_off"], d["grp_member"], ptr["grp_nu"], ptr["grp_ulist"],
+                                          ptr["grp_omask"], plan.n_groups, plan.max_group, ptr["pooled"], stream))
+            _cabi.check(lib.ufv_ttm(ptr["pooled"], c, d["obj_start"], d["obj_len"], d["slot_off"],
+                                    plan.n_obj, plan.max_len, k_keep, ptr["merged"], dt, None,
+                                    ptr["counts"], None, 0, None, 0, None, None, 0, stream))
+            x = run["view"]("merged", feats.dtype, (m_pad, c))
+            for i, lin in enumerate(linears):
+                x = linear(x, lin.weight, lin.bias, gelu=i < len(linears) - 1)
+            tokens = x
+        counts = run["counts"]
+        if self.keep_debug:
+            view = run["view"]
+            self._debug = {"bits": view("bits", torch.int32, (q, _cabi.BITS_WORDS)),
+                           "cnt": view("cnt", torch.int32, (q,)),
+                           "pooled": view("pooled", torch.float32, (q, c)),
+                           "merged": view("merged", feats.dtype, (m_pad, c))}
+        return tokens, counts, plan
+
+    def _prepare_run(self, plan, sig, feats, linears, side, k_keep, device):
+        """Workspace + argument struct of one (plan, pointers, stream) combination."""
+        _, dt, f, c, hid, stream, two, _ = sig
         q, m_pad, g = plan.n_masks, plan.m_pad, max(plan.n_groups, 1)
         es = feats.element_size()
         # one workspace allocation, carved into 256-byte aligned pieces
@@ -235,75 +298,56 @@ class MaskExtractor(nn.Module):
         ws = torch.empty((max(total, 256),), dtype=torch.uint8, device=device)
         base = ws.data_ptr()
         ptr = {name: base + o for name, o in off.items()}
-        tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
-        d = plan.dev
-        stream = _stream_ptr(device)
-        lib = _cabi.lib()
-        if len(linears) == 2:                     # the reference's depth=2 projector: one chained call
-            a = plan.args
-            if a is None:
-                a = plan.args = _cabi.EncodeArgs(
-                    n_patch_side=side, mask_desc=d["mask_desc"], taps=d["taps"], n_masks=q, idx_pitch=0,
-                    idx=None, grp_ticket=plan.ticket.data_ptr(), grp_row=d["grp_row"], grp_off=d["grp_off"],
-                    grp_member=d["grp_member"], n_groups=plan.n_groups, max_group=plan.max_group,
-                    obj_start=d["obj_start"], obj_len=d["obj_len"], slot_off=d["slot_off"],
-                    n_obj=plan.n_obj, max_len=plan.max_len, k_keep=k_keep, m_pad=m_pad)
-                plan.counts_pinned = torch.empty((max(plan.n_obj, 1),), dtype=torch.int32, pin_memory=True)
-                plan.counts_event = torch.cuda.Event()
-                plan.counts_event.record(torch.cuda.current_stream(device))   # forces creation of the handle
-                a.counts_host = plan.counts_pinned.data_ptr()
-                a.counts_event = plan.counts_event.cuda_event
-            a.feats, a.feat_dtype, a.n_rows, a.c, a.hid = feats.data_ptr(), dt, f, c, hid
-            a.bits, a.cnt, a.pooled, a.merged = ptr["bits"], ptr["cnt"], ptr["pooled"], ptr["merged"]
-            a.grp_nu, a.grp_ulist, a.grp_omask = ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"]
-            a.counts, a.hidden, a.tokens_out = ptr["counts"], ptr["hidden"], tokens.data_ptr()
-            a.w1, a.b1 = linears[0].weight.data_ptr(), linears[0].bias.data_ptr()
-            a.w2, a.b2 = linears[1].weight.data_ptr(), linears[1].bias.data_ptr()
-            _cabi.check(lib.ufv_encode(ctypes.byref(a), stream))
-        else:                                     # other depths: the same kernels, staged
-            _cabi.check(lib.ufv_mask_to_patches(d["mask_desc"], d["taps"], q, side, ptr["bits"], ptr["cnt"],
-                                                None, 0, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
-                                                ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], stream))
-            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, n_patch, c, ptr["cnt"], d["grp_row"],
-                                          d["grp_off"], d["grp_member"], ptr["grp_nu"], ptr["grp_ulist"],
-                                          ptr["grp_omask"], plan.n_groups, plan.max_group, ptr["pooled"], stream))
-            _cabi.check(lib.ufv_ttm(ptr["pooled"], c, d["obj_start"], d["obj_len"], d["slot_off"],
-                                    plan.n_obj, plan.max_len, k_keep, ptr["merged"], dt, None,
-                                    ptr["counts"], None, 0, None, 0, stream))
-            x = ws[off["merged"]:off["merged"] + m_pad * c * es].view(feats.dtype).view(m_pad, c)
-            for i, lin in enumerate(linears):
-                x = linear(x, lin.weight, lin.bias, gelu=i < len(linears) - 1)
-            tokens = x
 
         def view(name, dtype, shape):
             n = int(np.prod(shape)) * _ELEM_BYTES[dtype]
             return ws[off[name]:off[name] + n].view(dtype).view(shape)
 
-        counts = view("counts", torch.int32, (plan.n_obj,))
-        if self.keep_debug:
-            self._debug = {"bits": view("bits", torch.int32, (q, _cabi.BITS_WORDS)),
-                           "cnt": view("cnt", torch.int32, (q,)),
-                           "pooled": view("pooled", torch.float32, (q, c)),
-                           "merged": view("merged", feats.dtype, (m_pad, c))}
-        return tokens, counts, plan
+        run = {"sig": sig, "ws": ws, "ptr": ptr, "view": view,
+               "counts": view("counts", torch.int32, (plan.n_obj,))}
+        if two:
+            d = plan.dev
+            if plan.counts_pinned is None:        # pinned int32 [n_obj + 1]: counts, then the epoch stamp
+                plan.counts_pinned = torch.zeros((plan.n_obj + 1,), dtype=torch.int32).pin_memory()
+                plan.counts_np = plan.counts_pinned.numpy()
+                plan.counts_dev_addr = packer._device_address(plan.counts_pinned)
+            a = _cabi.EncodeArgs(
+                feats=feats.data_ptr(), feat_dtype=dt, n_patch_side=side, n_rows=f, c=c, hid=hid,
+                mask_desc=d["mask_desc"], taps=d["taps"], n_masks=q, idx_pitch=0, bits=ptr["bits"],
+                cnt=ptr["cnt"], idx=None, grp_ticket=plan.ticket.data_ptr(), grp_nu=ptr["grp_nu"],
+                grp_ulist=ptr["grp_ulist"], grp_omask=ptr["grp_omask"], grp_row=d["grp_row"],
+                grp_off=d["grp_off"], grp_member=d["grp_member"], n_groups=plan.n_groups,
+                max_group=plan.max_group, pooled=ptr["pooled"], obj_start=d["obj_start"],
+                obj_len=d["obj_len"], slot_off=d["slot_off"], n_obj=plan.n_obj, max_len=plan.max_len,
+                k_keep=k_keep, m_pad=m_pad, merged=ptr["merged"], counts=ptr["counts"],
+                counts_host=plan.counts_dev_addr, ttm_ticket=plan.ticket.data_ptr() + 4 * max(plan.n_groups, 1),
+                epoch=0,
+                w1=linears[0].weight.data_ptr(), b1=linears[0].bias.data_ptr(),
+                w2=linears[1].weight.data_ptr(), b2=linears[1].bias.data_ptr(),
+                hidden=ptr["hidden"], tokens_out=None)
+            run["args"] = a
+            run["args_ref"] = ctypes.byref(a)
+        return run
 
     # -- the reference's forward -----------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, feats, masks, X_features, ann_indices, frame_nums):
         """Same contract as layer.py:63-128: returns (mask_feats [N_tok, hidden], region_token_nums
         list[int]).  ``X_features`` and ``frame_nums`` are accepted and ignored, as in the reference
-        (which reads only ``X_features.device`` in its fallbacks)."""
+        (which reads only ``X_features.device`` in its fallbacks).  Forward only: no autograd graph
+        is recorded (DESIGN.md, "next")."""
         tokens, counts, plan = self.encode_padded(feats, masks, ann_indices)
         # the one unavoidable D2H: the caller slices rows by these counts (videorefer_arch.py:307-311)
-        if plan.counts_event is not None and len(self._linears()) == 2:
-            plan.counts_event.synchronize()        # merge kernel done; the projector may still be running
-            region_token_nums = plan.counts_pinned.numpy()[:plan.n_obj].copy()
+        if plan.run.get("args") is not None and plan.n_obj > 0:
+            # the merge kernel stores the counts straight into pinned host memory and stamps the
+            # call's epoch behind them; the projector may still be running when this returns
+            region_token_nums = _await_counts(plan, tokens.device)
         else:
             region_token_nums = counts.cpu().numpy()
         if np.array_equal(region_token_nums, plan.slots):
             return tokens, list(plan.expect_counts)
         # ties at the merge threshold left some object with fewer than min(T, K) tokens:
         # drop the zero-filled slots (rare; exact ties only)
+        region_token_nums = region_token_nums.copy()
         starts = plan.host["slot_off"]
         row_map = np.concatenate([np.arange(s, s + n, dtype=np.int32)
                                   for s, n in zip(starts, region_token_nums)] or [np.zeros(0, np.int32)])

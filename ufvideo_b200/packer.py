@@ -10,6 +10,7 @@ patched).
 from __future__ import annotations
 
 import ctypes
+import marshal
 from collections import OrderedDict
 from dataclasses import dataclass, field
 
@@ -30,7 +31,7 @@ assert MASK_DESC.itemsize == 32
 # A pinned host mask tensor is not copied: kernel 1 reads it through its mapped device address and
 # touches only the rows its taps need (384x384 fp32: 83 KB of 590 KB).  Developer knobs below.
 READ_PINNED_MASKS_IN_PLACE = True
-FORCE_TAP_MODE = False
+READ_MODE = "auto"          # "auto": row mode for host-resident masks, tap mode in HBM; "rows" / "taps" force one
 
 _tap_cache: dict = {}
 _plan_cache: "OrderedDict[tuple, EncodePlan]" = OrderedDict()
@@ -67,9 +68,11 @@ class EncodePlan:
     sample_of: np.ndarray | None = None           # int32 [q] sample each object-frame came from
     plane_off: np.ndarray | None = None           # int64 [q] byte offset of its plane in that sample
     base_ptrs: tuple = ()                         # mask tensor base addresses baked into ``buffer``
-    args: object = None                           # cached ctypes EncodeArgs
+    run: dict | None = None                       # workspace + ctypes EncodeArgs of the last call (layer.py)
+    counts_np: np.ndarray | None = None           # numpy view of counts_pinned[:n_obj]
     counts_pinned: torch.Tensor | None = None     # pinned int32 [n_obj]: early read-back of the counts
-    counts_event: object = None                   # torch.cuda.Event recorded right after the merge kernel
+    counts_dev_addr: int = 0                      # device-visible address of counts_pinned
+    epoch: int = 0                                # stamp of the last call (kernel 3 writes it behind the counts)
     expect_counts: list = field(default_factory=list)
 
 
@@ -115,9 +118,12 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
     ptrs = tuple(_device_address(m) for m in masks)
     key = None
     if use_cache:
-        key = (tuple(tuple(tuple(o) for o in s) for s in ann_indices),
-               tuple((tuple(m.shape), m.stride(), m.dtype) for m in masks),
-               n_feat_rows, k_keep, bool(pad_square), n_out, str(device), FORCE_TAP_MODE)
+        try:                                     # lists of python ints: one C-speed serialisation
+            ann_key = marshal.dumps(ann_indices)
+        except ValueError:                       # numpy / tensor scalars inside
+            ann_key = tuple(tuple(tuple(int(r) for r in o) for o in s) for s in ann_indices)
+        key = (ann_key, tuple((m.shape, m.stride(), m.dtype, m.device.type) for m in masks),
+               n_feat_rows, k_keep, bool(pad_square), n_out, str(device), READ_MODE)
         plan = _plan_cache.get(key)
         if plan is not None:
             _plan_cache.move_to_end(key)
@@ -194,12 +200,15 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
     group_of = np.empty(q_total, dtype=np.int32)
     group_of[order] = np.repeat(np.arange(n_groups, dtype=np.int32), run_len)
 
+    plan_sample = cat(sample_of, np.int32)
     desc = np.zeros(q_total, dtype=MASK_DESC)
     desc["pitch"] = cat(pitch, np.int32)
     desc["dtype"] = cat(dtype_id, np.int32)
     desc["tap_off"] = cat(tap_off, np.int32)
     desc["group"] = group_of
-    desc["flags"] = 1 if FORCE_TAP_MODE else 0
+    on_host = np.asarray([m.device.type == "cpu" for m in masks], dtype=bool)
+    rows_mode = on_host[plan_sample] if READ_MODE == "auto" else np.full(q_total, READ_MODE == "rows")
+    desc["flags"] = rows_mode.astype(np.int32)
 
     obj_len_a = np.asarray(obj_len, dtype=np.int32)
     slots = np.minimum(obj_len_a, k_keep).astype(np.int32)
@@ -221,7 +230,8 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
                       m_pad=int(slots.sum()), slots=slots, host=host,
                       sample_of=cat(sample_of, np.int32), plane_off=cat(plane_off, np.int64),
                       expect_counts=[int(s) for s in slots])
-    plan.ticket = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)
+    # per-group arrival counters of kernel 1 + one completion counter of kernel 3 (all self-resetting)
+    plan.ticket = torch.zeros(max(n_groups, 1) + 1, dtype=torch.int32, device=device)
     _fill_addresses(plan, ptrs)
     _upload(plan, device)
     return plan
@@ -257,4 +267,4 @@ def _upload(plan: EncodePlan, device) -> None:
     plan.buffer = staging.to(device, non_blocking=True)
     p0 = plan.buffer.data_ptr()
     plan.dev = {name: p0 + off for name, off in offsets.items()}
-    plan.args = None
+    plan.run = None
