@@ -269,14 +269,25 @@ def test_linear_matches_torch(dev, dtype, m):
     assert (y.float() - ref_y).abs().max().item() <= TOL[dtype]
 
 
-def test_linear_large_m_all_tile_shapes(dev):
-    for m in (1024, 4096):                       # switches the N tile to 64 / 128
-        x = (torch.randn((m, 1152), device=dev) * 0.05).bfloat16()
-        w = (torch.randn((3584, 1152), device=dev) * 0.03).bfloat16()
-        b = (torch.randn((3584,), device=dev) * 0.03).bfloat16()
-        y = layer.linear(x, w, b)
-        ref = torch.nn.functional.linear(x.float(), w.float(), b.float())
-        assert (y.float() - ref).abs().max().item() <= 1e-2
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
+def test_linear_large_m_all_tile_shapes(dev, bn):
+    """Every N-tile instantiation of the persistent tcgen05 kernel (0 = the cost model's choice),
+    with several tiles per CTA, a ragged M edge and a ragged N edge (n % 32 != 0)."""
+    if bn:
+        os.environ["UFV_GEMM_BN"] = str(bn)
+    try:
+        for m, n, k in ((1024, 3584, 1152), (4096 + 77, 3584, 1152), (333, 3584, 3584), (2500, 424, 1152)):
+            x = (torch.randn((m, k), device=dev) * 0.05).bfloat16()
+            w = (torch.randn((n, k), device=dev) * 0.03).bfloat16()
+            b = (torch.randn((n,), device=dev) * 0.03).bfloat16()
+            for gelu in (False, True):
+                y = layer.linear(x, w, b, gelu=gelu)
+                ref = torch.nn.functional.linear(x.float(), w.float(), b.float())
+                if gelu:
+                    ref = torch.nn.functional.gelu(ref.bfloat16().float())
+                assert (y.float() - ref).abs().max().item() <= 1e-2, (bn, m, n, k, gelu)
+    finally:
+        os.environ.pop("UFV_GEMM_BN", None)
 
 
 # ---------------------------------------------------------------------------------------------

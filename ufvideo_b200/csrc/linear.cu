@@ -6,14 +6,16 @@
 // is D[tmem] = A[smem] . B[smem]^T with A = 128 rows of x, B = BN rows of w.  Warp roles:
 //   warp 0   TMA producer: 128B-swizzled 2-D tensor-map loads of the A / B k-blocks into a
 //            ring of shared-memory stages (mbarrier full / empty pairs)
-//   warp 1   allocates TMEM; one elected lane issues tcgen05.mma (UMMA 128 x BN x 16, fp32
-//            accumulate in TMEM) and commits stage release / accumulator-ready barriers
-//   warps 2-5  epilogue: tcgen05.ld the accumulator (thread = row), + bias, round to the model
-//            dtype, GELU(erf), round, 16-byte stores
+//   warp 1   allocates TMEM (two accumulators); one elected lane issues tcgen05.mma (UMMA
+//            128 x BN x 16, fp32 accumulate in TMEM) and commits stage release / accumulator-ready
+//   warps 2-9  epilogue: tcgen05.ld the accumulator (thread = row), + bias, round to the model
+//            dtype, GELU(erf), round, 16-byte stores; runs under the next tile's main loop
+// The kernel is persistent (one CTA per SM walks the tile list).
 // fp32: CUDA-core tiled GEMM (the 1e-5 fp32 tolerance rules out bf16/tf32 tensor-core inputs).
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 
 namespace ufv {
 
@@ -24,19 +26,41 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
 
+// Exact-erf GELU for the tensor-core epilogue, whose result is rounded to bf16 / fp16 anyway:
+// Phi(v) = 0.5 * erfc(-v / sqrt(2)) with erfc(z) = P(t) * exp(-z^2), t = 1 / (1 + p z) (Abramowitz &
+// Stegun 7.1.26, |error| <= 1.5e-7 -- far below half a 16-bit ulp).  Evaluated on |v| and mirrored,
+// so the negative tail has no 1 + erf cancellation.  14 FP32 instructions + 2 MUFU per element,
+// against ~35 for erff(): with K = 1152 the epilogue would otherwise outlast the main loop.
+__device__ __forceinline__ float gelu_erf_16bit(float v) {
+  const float av = fabsf(v);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(av, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * (v * -0.72134752044448170368f)));   // exp(-v^2 / 2)
+  float p = 0.5f * 1.061405429f;
+  p = fmaf(p, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float q = p * t * e;                      // Phi(-|v|)
+  return v * (v > 0.0f ? 1.0f - q : q);
+}
+
 // ================================= tcgen05 path ===================================================
 constexpr int kBM = 128;
 constexpr int kBK = 64;             // 64 x 2 B = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;        // two per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
+constexpr int kTileBudget = 224 * 1024;   // shared memory for the stage ring (227 KB per CTA on sm_100)
 
 template <int BN> struct GemmCfg {
-  static constexpr int kStages = BN <= 64 ? 8 : 6;
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kTileBudget / kStageBytes < 8 ? kTileBudget / kStageBytes : 8;
   static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
+                                   : 2 * BN <= 256 ? 256 : 512;   // two accumulators
 };
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 format, version 1):
@@ -65,40 +89,65 @@ template <> struct Pack8<__nv_bfloat16> {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+  __device__ static float2 unpack(uint32_t r) {
+    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+  }
 };
 template <> struct Pack8<__half> {
   __device__ static uint32_t two(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+  __device__ static float2 unpack(uint32_t r) { return __half22float2(*reinterpret_cast<const __half2*>(&r)); }
 };
 
+// Tile order: m-tiles are taken in groups of kGroupM; inside a group the m-tile index runs fastest,
+// then the n-tile.  CTAs running side by side therefore share weight tiles through L2, and the
+// 2048 token rows of a group (<= 15 MB) stay L2-resident while every n-tile passes over them --
+// without the grouping, M = 16384 re-reads the 117 MB activation matrix from HBM once per n-tile.
+constexpr int kGroupM = 16;
+__device__ __forceinline__ void tile_origin(int tile, int tiles_m, int tiles_n, int bn, int& m0, int& n0) {
+  const int per_group = kGroupM * tiles_n;
+  const int g = tile / per_group;
+  const int r = tile - g * per_group;
+  const int gm = min(kGroupM, tiles_m - g * kGroupM);   // m-tiles in this (possibly last, short) group
+  const int nt = r / gm;
+  m0 = (g * kGroupM + (r - nt * gm)) * kBM;
+  n0 = nt * bn;
+}
+
+// Persistent: grid = min(tiles, SMs); CTA b takes tiles b, b + grid, ...  Three pipelines: the shared-memory stage
+// ring (TMA -> MMA), the two TMEM accumulators (MMA -> epilogue: the epilogue of tile i overlaps
+// the main loop of tile i + 1), and the tile loop itself.
 template <typename T, int BN, bool GELU>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                 const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k) {
+                 const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k, int tiles_m,
+                 int n_tiles) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t dyn_smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 1023) &
                                               ~uintptr_t(1023));   // SW128 atoms need 1024-B alignment
   __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
   __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
-  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_bias[BN];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBM;
   const int num_kb = (k + kBK - 1) / kBK;
+  const int tiles_n = n_tiles / tiles_m;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], kEpiWarps);
+    }
     mbar_fence_init();
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
@@ -107,91 +156,136 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tmem_alloc(&s_tmem_base, Cfg::kTmemCols);
     tmem_relinquish();
   }
-  pdl_wait();                  // x (and, transitively, the parameters) come from earlier kernels
-  pdl_launch_dependents();
-  if (threadIdx.x >= 64) {
-    for (int i = threadIdx.x - 64; i < BN; i += kGemmThreads - 64)
-      s_bias[i] = (n0 + i) < n ? Elem<T>::to_f32(bias[n0 + i]) : 0.f;
-  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();                  // x (and, transitively, the parameters) come from earlier kernels
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------- TMA producer -----------------------------------------------
     if (elect_one()) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* a_dst = tiles + size_t(s) * Cfg::kStageBytes;
-        uint8_t* b_dst = a_dst + Cfg::kABytes;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        tma_load_2d(a_dst, &tmap_x, kb * kBK, m0, &full_bar[s]);
-        tma_load_2d(b_dst, &tmap_w, kb * kBK, n0, &full_bar[s]);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int m0, n0;
+        tile_origin(tile, tiles_m, tiles_n, BN, m0, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* a_dst = tiles + size_t(s) * Cfg::kStageBytes;
+          uint8_t* b_dst = a_dst + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(a_dst, &tmap_x, kb * kBK, m0, &full_bar[s]);
+          tma_load_2d(b_dst, &tmap_w, kb * kBK, n0, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(Elem<T>::kDtype == UFV_BF16 ? 1 : 0, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+        mbar_wait(&acc_empty[acc], aph ^ 1u);   // the epilogue has drained this accumulator
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(tiles + size_t(s) * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + Cfg::kABytes;
+        const uint32_t d_tmem = tmem_base + acc * uint32_t(BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(tiles + size_t(s) * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
-        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-          const uint64_t da = smem_desc_sw128(a_addr + kk * kUmmaK * 2);
-          const uint64_t db = smem_desc_sw128(b_addr + kk * kUmmaK * 2);
-          umma_f16(tmem_base, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+            const uint64_t da = smem_desc_sw128(a_addr + kk * kUmmaK * 2);
+            const uint64_t db = smem_desc_sw128(b_addr + kk * kUmmaK * 2);
+            umma_f16(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);   // stage reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);   // stage reusable once these MMAs have read it
+        umma_commit(&acc_full[acc]);    // accumulator complete
       }
-      umma_commit(&acc_bar);          // accumulator complete
     }
   } else {
     // ------------------------------- epilogue warps -------------------------------------------------
-    const int quarter = warp & 3;     // TMEM lanes a warp may read: 32 * (warp_id % 4) ..
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after_sync();
-    const int row = m0 + quarter * 32 + lane;
+    const int quarter = warp & 3;       // TMEM lanes a warp may read: 32 * (warp_id % 4) ..
+    const int half = (warp - 2) >> 2;   // which of the two warps of this quarter
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      int m0, n0;
+      tile_origin(tile, tiles_m, tiles_n, BN, m0, n0);
+      const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+      mbar_wait(&acc_full[acc], aph);
+      tc_fence_after_sync();
+      const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
-    for (int col0 = 0; col0 < BN; col0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(col0), v);
-      tmem_ld_wait();
-      if (row < m) {
-        uint32_t packed[16];
+      for (int col0 = half * 32; col0 < BN; col0 += 64) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * uint32_t(BN) + uint32_t(col0), v);
+        tmem_ld_wait();
+        const int gcol = n0 + col0;
+        if (row < m && gcol < n) {
+          uint32_t packed[16];
+          if (gcol + 32 <= n) {
+            const uint4* bsrc = reinterpret_cast<const uint4*>(bias + gcol);   // warp-uniform: broadcast
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a = __uint_as_float(v[i]) + s_bias[col0 + i];
-          float b = __uint_as_float(v[i + 1]) + s_bias[col0 + i + 1];
-          if (GELU) {   // the reference rounds to the model dtype before and after GELU
-            a = gelu_erf(Elem<T>::to_f32(Elem<T>::from_f32(a)));
-            b = gelu_erf(Elem<T>::to_f32(Elem<T>::from_f32(b)));
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint4 bq = __ldg(bsrc + q4);
+              const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 bf = Pack8<T>::unpack(bw[j]);
+                const int i = q4 * 8 + j * 2;
+                float a = __uint_as_float(v[i]) + bf.x;
+                float b = __uint_as_float(v[i + 1]) + bf.y;
+                if (GELU) {   // the reference rounds to the model dtype before and after GELU
+                  a = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(a)));
+                  b = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(b)));
+                }
+                packed[i >> 1] = Pack8<T>::two(a, b);
+              }
+            }
+            T* dst = y + size_t(row) * n + gcol;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<uint4*>(dst)[i] =
+                  make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          } else {                       // ragged right edge (n % 32 != 0)
+            T* dst = y + size_t(row) * n + gcol;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (gcol + i < n) {
+                float a = __uint_as_float(v[i]) + Elem<T>::to_f32(bias[gcol + i]);
+                if (GELU) a = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(a)));
+                dst[i] = Elem<T>::from_f32(a);
+              }
+            }
           }
-          packed[i >> 1] = Pack8<T>::two(a, b);
-        }
-        T* dst = y + size_t(row) * n + n0 + col0;
-        if (n0 + col0 + 32 <= n) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<uint4*>(dst)[i] =
-                make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-        } else {
-          for (int i = 0; i < 32 && n0 + col0 + i < n; ++i)
-            dst[i] = reinterpret_cast<const T*>(packed)[i];
         }
       }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);   // this warp's share of the accumulator is in registers / stored
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+static int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      v = 148;
+    cudaGetLastError();
+    return v;
+  }();
+  return n;
 }
 
 template <typename T, int BN>
@@ -203,42 +297,53 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
   if (rc != 0) return rc;
   rc = make_tensor_map_2d(&tw, w, Elem<T>::kDtype, uint64_t(n), uint64_t(k), BN, kBK, 1);
   if (rc != 0) return rc;
-  const dim3 grid((n + BN - 1) / BN, (m + kBM - 1) / kBM);
-  if (gelu) {
-    auto kernel = linear_tc_kernel<T, BN, true>;
+  const int tiles_m = (m + kBM - 1) / kBM;
+  const int n_tiles = tiles_m * ((n + BN - 1) / BN);
+  const dim3 grid(n_tiles < sm_count() ? n_tiles : sm_count());
+  auto kernel = gelu ? linear_tc_kernel<T, BN, true> : linear_tc_kernel<T, BN, false>;
+  static bool configured[2] = {false, false};   // idempotent attribute; a benign race sets it twice
+  if (!configured[gelu ? 1 : 0]) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    return check_launch("ufv_linear (tcgen05)",
-                        launch_kernel(kernel, grid, dim3(kGemmThreads), Cfg::kSmem, stream, tx, tw,
-                                      static_cast<const T*>(bias), static_cast<T*>(y), m, n, k));
-  } else {
-    auto kernel = linear_tc_kernel<T, BN, false>;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    return check_launch("ufv_linear (tcgen05)",
-                        launch_kernel(kernel, grid, dim3(kGemmThreads), Cfg::kSmem, stream, tx, tw,
-                                      static_cast<const T*>(bias), static_cast<T*>(y), m, n, k));
+    configured[gelu ? 1 : 0] = true;
   }
+  return check_launch("ufv_linear (tcgen05)",
+                      launch_kernel(kernel, grid, dim3(kGemmThreads), Cfg::kSmem, stream, tx, tw,
+                                    static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles));
 }
 
-template <typename T>
-static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                       int gelu, cudaStream_t stream) {
-  // N-tile choice.  At small token counts a CTA's time is what it must pull through its SM's
-  // L2->shared-memory path, (128 + BN) * K * 2 bytes, times the number of waves over the 148 SMs
-  // (one CTA per SM: the stage ring fills shared memory).  Pick the BN with the smallest product.
+// N-tile choice.  Per 64-deep k-block a CTA spends max(2 * BN tensor-core clocks, the time to pull
+// (128 + BN) * 128 bytes through its SM's L2 port); a launch costs that times the number of waves
+// over the SMs.  Small token counts therefore take narrow tiles (more CTAs share the weight
+// stream), large ones wide tiles (fewer bytes per flop).  UFV_GEMM_BN overrides (developer sweeps).
+static int choose_bn(int m, int n) {
+  const char* env = getenv("UFV_GEMM_BN");
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
   const int m_tiles = (m + kBM - 1) / kBM;
   int best_bn = 32;
-  long best_cost = -1;
-  for (int bn : {32, 64, 128}) {
+  double best_cost = -1.0;
+  for (int bn : {32, 64, 128, 256}) {
     const long ctas = long(m_tiles) * ((n + bn - 1) / bn);
-    const long cost = ((ctas + 147) / 148) * (kBM + bn);
+    const long waves = (ctas + sm_count() - 1) / sm_count();
+    const double per_kb = (128.0 + bn) > 2.0 * bn ? (128.0 + bn) : 2.0 * bn;
+    const double cost = double(waves) * (per_kb + 24.0);   // + per-tile epilogue / refill share
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best_bn = bn;
     }
   }
-  if (best_bn == 128) return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, stream);
-  if (best_bn == 64) return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, stream);
-  return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, stream);
+  return best_bn;
+}
+
+template <typename T>
+static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+                       int gelu, cudaStream_t stream) {
+  switch (choose_bn(m, n)) {
+    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, stream);
+    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, stream);
+    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, stream);
+    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, stream);
+  }
 }
 
 // ================================= fp32 CUDA-core path ============================================

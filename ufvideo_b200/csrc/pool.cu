@@ -99,17 +99,22 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   __syncthreads();
   pdl_wait();                  // the union plan and counts come from kernel 1
   pdl_launch_dependents();
+  // every plan word this CTA needs is requested at once: one L2 round trip, not a dependent chain
+  const uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
+  int my_patch = 0, row = 0;
+  if (warp == kPoolConsumers) {
+    if (lane < R) my_patch = int(ulist[lane]);             // plan tail is zero-padded: always in bounds
+    row = grp_row[g];
+  }
   const int n_u = grp_nu[g];
   const int n_chunks = (n_u + R - 1) / R;
   const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == kPoolConsumers) {
     // ---------------- producer warp: plan -> TMA engine -> shared-memory ring ------------------
-    const uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
     const uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
-    const int64_t row_base = int64_t(grp_row[g]) * n_patch;
+    const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    int my_patch = (lane < R) ? int(ulist[lane]) : 0;      // plan tail is zero-padded: always in bounds
     for (int it = 0; it < n_chunks; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
@@ -141,6 +146,16 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     for (int o = 0; o < OT; ++o) acc[o] = make_float2(0.f, 0.f);
     const int my_ch = warp * (kPoolCh / kPoolConsumers) + lane * 2;      // within the slice
     const bool live = my_ch < slice_ch;
+    // output rows and denominators: requested now, needed only after the last stage
+    const int m0 = grp_off[g];
+    const int n_mem = grp_off[g + 1] - m0;
+    int out_row[OT];
+    float denorm[OT];
+#pragma unroll
+    for (int o = 0; o < OT; ++o) {
+      out_row[o] = o < n_mem ? grp_member[m0 + o] : -1;
+      denorm[o] = out_row[o] >= 0 ? __fadd_rn(float(cnt[out_row[o]]), 1e-8f) : 1.0f;   // layer.py:145
+    }
     for (int it = 0; it < n_chunks; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
@@ -163,18 +178,14 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
           if (m & (1u << o)) add2(acc[o], f);
       }
     }
-    const int m0 = grp_off[g];
-    const int n_mem = grp_off[g + 1] - m0;
     if (live) {
 #pragma unroll
       for (int o = 0; o < OT; ++o) {
-        if (o < n_mem) {
-          const int j = grp_member[m0 + o];
-          const float denorm = __fadd_rn(float(cnt[j]), 1e-8f);   // layer.py:145
+        if (out_row[o] >= 0) {
           float2 out;
-          out.x = __fdiv_rn(acc[o].x, denorm);
-          out.y = __fdiv_rn(acc[o].y, denorm);
-          *reinterpret_cast<float2*>(pooled + size_t(j) * c + ch0 + my_ch) = out;
+          out.x = __fdiv_rn(acc[o].x, denorm[o]);
+          out.y = __fdiv_rn(acc[o].y, denorm[o]);
+          *reinterpret_cast<float2*>(pooled + size_t(out_row[o]) * c + ch0 + my_ch) = out;
         }
       }
     }
@@ -199,9 +210,24 @@ void* tensor_map_encoder() {
   return fn;
 }
 
-// 2-D row-major [rows, cols] tensor map with a [box_rows, box_cols] box.
+// 2-D row-major [rows, cols] tensor map with a [box_rows, box_cols] box.  Encoding costs about a
+// microsecond of host time and the same few maps (features, tokens, weights) come back call after
+// call, so the last few are kept in a small per-thread table keyed by every encode parameter.
 int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint64_t cols,
                        uint32_t box_rows, uint32_t box_cols, int swizzle128) {
+  struct Entry {
+    const void* base; uint64_t rows, cols; uint32_t box_rows, box_cols; int dtype, swizzle; bool valid;
+    CUtensorMap map;
+  };
+  constexpr int kEntries = 16;
+  static thread_local Entry cache[kEntries] = {};
+  const size_t slot = ((reinterpret_cast<uintptr_t>(base) >> 8) ^ (box_rows * 7u) ^ cols) % kEntries;
+  Entry& e = cache[slot];
+  if (e.valid && e.base == base && e.rows == rows && e.cols == cols && e.box_rows == box_rows &&
+      e.box_cols == box_cols && e.dtype == dtype && e.swizzle == swizzle128) {
+    *map = e.map;
+    return 0;
+  }
   auto encode = reinterpret_cast<EncodeTiledFn>(tensor_map_encoder());
   if (encode == nullptr) return fail(UFV_E_DRIVER, "cuTensorMapEncodeTiled entry point not found");
   const CUtensorMapDataType dt = dtype == UFV_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -216,6 +242,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t r
                             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(UFV_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  e = Entry{base, rows, cols, box_rows, box_cols, dtype, swizzle128, true, *map};
   return 0;
 }
 

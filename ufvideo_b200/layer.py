@@ -343,7 +343,7 @@ class MaskExtractor(nn.Module):
             region_token_nums = _await_counts(plan, tokens.device)
         else:
             region_token_nums = counts.cpu().numpy()
-        if np.array_equal(region_token_nums, plan.slots):
+        if region_token_nums.tobytes() == plan.slots_bytes:   # no ties: every object kept min(T, K) tokens
             return tokens, list(plan.expect_counts)
         # ties at the merge threshold left some object with fewer than min(T, K) tokens:
         # drop the zero-filled slots (rare; exact ties only)

@@ -74,6 +74,7 @@ class EncodePlan:
     counts_dev_addr: int = 0                      # device-visible address of counts_pinned
     epoch: int = 0                                # stamp of the last call (kernel 3 writes it behind the counts)
     expect_counts: list = field(default_factory=list)
+    slots_bytes: bytes = b""                      # ``slots`` as bytes: the no-ties fast comparison
 
 
 def _as_mask_list(masks, device):
@@ -84,16 +85,18 @@ def _as_mask_list(masks, device):
         m = masks[i]
         if not torch.is_tensor(m):
             m = torch.as_tensor(m)
-        if m.dim() != 3:
-            raise ValueError(f"masks[{i}] must be [q, H, W], got {tuple(m.shape)}")
-        if m.shape[0] == 0:                      # layer.py:73-75: substitute one all-zero mask
+        shape = m.shape
+        if len(shape) != 3:
+            raise ValueError(f"masks[{i}] must be [q, H, W], got {tuple(shape)}")
+        if shape[0] == 0:                        # layer.py:73-75: substitute one all-zero mask
             m = torch.zeros((1, 336, 336), dtype=torch.uint8, device=device)
         if m.dtype not in _MASK_DTYPES:          # exotic dtypes: binarise once on the device
             m = (m.to(device) > 0).to(torch.uint8)
-        in_place = m.device == device or (READ_PINNED_MASKS_IN_PLACE and device.type == "cuda"
-                                          and m.device.type == "cpu" and m.is_pinned())
-        if not in_place:                         # pageable host memory / another device: copy
-            m = m.to(device, non_blocking=True)
+        if m.device != device:
+            in_place = (READ_PINNED_MASKS_IN_PLACE and device.type == "cuda"
+                        and m.device.type == "cpu" and m.is_pinned())
+            if not in_place:                     # pageable host memory / another device: copy
+                m = m.to(device, non_blocking=True)
         if m.stride(-1) != 1:
             m = m.contiguous()
         out.append(m)
@@ -229,7 +232,7 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
                       n_obj=len(obj_len), max_len=int(obj_len_a.max()) if len(obj_len) else 1,
                       m_pad=int(slots.sum()), slots=slots, host=host,
                       sample_of=cat(sample_of, np.int32), plane_off=cat(plane_off, np.int64),
-                      expect_counts=[int(s) for s in slots])
+                      expect_counts=[int(s) for s in slots], slots_bytes=slots.tobytes())
     # per-group arrival counters of kernel 1 + one completion counter of kernel 3 (all self-resetting)
     plan.ticket = torch.zeros(max(n_groups, 1) + 1, dtype=torch.int32, device=device)
     _fill_addresses(plan, ptrs)
