@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UFV_ABI_VERSION 3
+#define UFV_ABI_VERSION 5
 
 /* element types */
 enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3 };
@@ -91,6 +91,8 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  * The 16-byte chunks read in row mode are aligned down/up around the tap span, so a mask plane
  * must not begin or end closer than 16 bytes to an unmapped page (true for any allocator).
  *   desc[n_masks]        one ufv_mask_desc per object-frame
+ *   any_row_mode         non-zero iff some descriptor sets flags bit 0 (selects the kernel variant
+ *                        that carries the row-mode flag table; 0 = lean tap-mode kernel)
  *   taps                 concatenated tap tables (ufv_tap_table) the descriptors point into
  *   bits_out[n_masks*UFV_BITS_WORDS]  bit p%32 of word p/32 = patch p (row-major h,w) is on
  *   cnt_out[n_masks]     number of on patches
@@ -103,7 +105,7 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  *   must be zero on entry and is zero again on completion.
  * -------------------------------------------------------------------------------------------*/
 int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
-                        uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
+                        int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
                         const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
                         int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, void* stream);
 
@@ -133,17 +135,20 @@ int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, int n_patch
  *   it; rows past counts_out[o] are zero-filled.
  *   tokens_out [m_pad, c] of out_dtype; tokens_f32_out (optional) the same rows before the
  *   downcast; cuts_out (optional) [n_obj * cut_pitch_words] uint32, bit i set = run boundary
- *   after token i; sims_out (optional) [n_obj * sims_pitch] fp32 adjacent cosine similarities.
+ *   after token i; sims_out [n_obj * sims_pitch] fp32 adjacent cosine similarities: scratch the two
+ *   launches communicate through (sims_pitch >= max_len - 1), required when max_len > k_keep.
  *   Early read-back of the counts (optional, pass counts_host = null to skip): counts_host is the
- *   device-visible address (ufv_device_address) of a pinned int32[n_obj + 1]; every object's
- *   count is also stored there and the last CTA then writes `epoch` into element n_obj, which the
- *   host can poll.  done_ticket is one zeroed uint32 in device memory (zero again on completion).
+ *   device-visible address (ufv_device_address) of a pinned int32[n_obj]; object o's count is also
+ *   stored there as ONE word, (epoch << 16) | count, epoch in [1, 32767].  The host polls until all
+ *   n_obj words carry the call's epoch -- no fence, copy, event or stream synchronisation needed.
+ *   Objects of up to 64 frames are merged by one fused launch (a CTA per object), longer ones by
+ *   a similarity launch (a warp per adjacent pair) plus a merge launch (a CTA per output token).
  * -------------------------------------------------------------------------------------------*/
 int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
             const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
             int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
             int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
-            uint32_t* done_ticket, int32_t epoch, void* stream);
+            int32_t epoch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 4: one Linear (+ optional exact-erf GELU) of the object projector,
@@ -164,6 +169,7 @@ typedef struct ufv_encode_args {
   const void* feats; int32_t feat_dtype; int32_t n_patch_side; int64_t n_rows; int32_t c; int32_t hid;
   /* masks -> patches */
   const ufv_mask_desc* mask_desc; const int32_t* taps; int32_t n_masks; int32_t idx_pitch;
+  int32_t any_row_mode; int32_t reserved1;
   uint32_t* bits; int32_t* cnt; uint16_t* idx;            /* idx optional */
   uint32_t* grp_ticket; int32_t* grp_nu; uint16_t* grp_ulist; uint8_t* grp_omask;
   /* pool */
@@ -174,10 +180,11 @@ typedef struct ufv_encode_args {
   const int32_t* obj_start; const int32_t* obj_len; const int32_t* slot_off;
   int32_t n_obj; int32_t max_len; int32_t k_keep; int32_t m_pad;
   void* merged; int32_t* counts;
+  float* sims; int32_t sims_pitch; int32_t reserved0;      /* fp32 [n_obj * sims_pitch] scratch of the merge */
   /* optional early read-back of the token counts (see ufv_ttm): the merge kernel stores them into
-   * the pinned buffer behind counts_host and stamps `epoch` after them, so the caller can build the
+   * the pinned buffer behind counts_host tagged with `epoch`, so the caller can build the
    * reference's list[int] while the projector is still running */
-  int32_t* counts_host; uint32_t* ttm_ticket; int32_t epoch; int32_t reserved;
+  int32_t* counts_host; int32_t epoch; int32_t reserved;
   /* projector: feat_linear.0 / feat_linear.2 (layer.py:55-59) */
   const void* w1; const void* b1; const void* w2; const void* b2;
   void* hidden; void* tokens_out;
@@ -185,9 +192,13 @@ typedef struct ufv_encode_args {
 
 int ufv_encode(const ufv_encode_args* args_host, void* stream);
 
-/* Gather rows: out[i, :] = in[row_map[i], :], `row_bytes` per row (multiple of 16).  Used to
- * compact the padded token tensor when ties at the merge threshold left an object with fewer
- * than min(T, K) tokens. */
+/* Compaction after merge ties: object o's first counts[o] rows (starting at row slot_off[o] of
+ * `in`) are packed back to back into `out` in object order; `row_bytes` per row (multiple of 16).
+ * out must hold sum(counts) rows.  Replaces the variable-length torch.cat at layer.py:121. */
+int ufv_compact_rows(const void* in, const int32_t* slot_off, const int32_t* counts, int n_obj,
+                     void* out, int row_bytes, void* stream);
+
+/* Gather rows: out[i, :] = in[row_map[i], :], `row_bytes` per row (multiple of 16). */
 int ufv_gather_rows(const void* in, const int32_t* row_map, void* out, int n_out_rows,
                     int row_bytes, void* stream);
 

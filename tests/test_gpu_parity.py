@@ -351,6 +351,40 @@ def test_ties_compact_the_padded_rows(dev):
     assert counts == [1] and tokens.shape[0] == 1
 
 
+def test_ties_in_the_middle_keep_object_order(dev):
+    """Object 1 ties down to one token between two ordinary objects: compaction keeps row order."""
+    feats = synth.features(11, 8)
+    feats[3:6] = feats[3]                                   # frames 3..5 identical
+    masks = np.concatenate([synth.masks_blob(12, 1, 8, 60, 60), np.ones((3, 60, 60), np.uint8),
+                            synth.masks_blob(13, 1, 6, 60, 60)])
+    ann = [[list(range(8)), [3, 4, 5], [0, 1, 2, 5, 6, 7]]]
+    enc = make_encoder(dev, "f32", 2)
+    tokens, counts = enc(torch.from_numpy(feats).to(dev), [torch.from_numpy(masks).to(dev)], None, ann, None)
+    w = synth.make_weights(0)
+    o = R.encode(feats, [masks], ann, 2, "f32", w)
+    assert counts == o["counts"] == [2, 1, 2]
+    assert tuple(tokens.shape) == (5, 3584)
+    assert np.abs(tokens.cpu().numpy() - o["tokens"]).max() <= 1e-5
+
+
+def test_long_objects_spread_over_many_ctas(dev):
+    """T = 300 and T = 40 in one batch (K = 8): similarity and merge kernels index by (object, pair/slot)."""
+    g = synth.rng_for(77)
+    x = g.standard_normal((340, 1152), dtype=np.float32)
+    host = {"obj_start": np.array([0, 300], np.int32), "obj_len": np.array([300, 40], np.int32),
+            "slot_off": np.array([0, 8], np.int32)}
+    plan = packer.EncodePlan(n_masks=340, n_groups=0, max_group=1, n_obj=2, max_len=300, m_pad=16,
+                             slots=np.full(2, 8, np.int32), host=host)
+    packer._upload(plan, dev)
+    tok, counts, ex = layer.ttm(torch.from_numpy(x).to(dev), plan, 8, torch.float32, debug=True)
+    for o, (a, b) in enumerate(((0, 300), (300, 340))):
+        want, cut, sims = R.token_merge(x[a:b], 8)
+        n = int(counts[o])
+        assert n == want.shape[0]
+        assert np.array_equal(ex["sims"][o, : b - a - 1].cpu().numpy(), sims)
+        assert np.array_equal(ex["tokens_f32"][8 * o: 8 * o + n].cpu().numpy(), want)
+
+
 def test_c2_shape_properties_bf16(dev):
     """BASELINE configs[1] at full size (8 clips x 16 frames x 4 objects, bf16): size-independent
     properties instead of an oracle run."""

@@ -21,7 +21,7 @@ BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8
 PLAN_PITCH = 736
-ABI_VERSION = 3
+ABI_VERSION = 5
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -34,6 +34,7 @@ class EncodeArgs(C.Structure):
         ("feats", _p), ("feat_dtype", _i32), ("n_patch_side", _i32), ("n_rows", _i64),
         ("c", _i32), ("hid", _i32),
         ("mask_desc", _p), ("taps", _p), ("n_masks", _i32), ("idx_pitch", _i32),
+        ("any_row_mode", _i32), ("reserved1", _i32),
         ("bits", _p), ("cnt", _p), ("idx", _p),
         ("grp_ticket", _p), ("grp_nu", _p), ("grp_ulist", _p), ("grp_omask", _p),
         ("grp_row", _p), ("grp_off", _p), ("grp_member", _p), ("n_groups", _i32),
@@ -41,8 +42,8 @@ class EncodeArgs(C.Structure):
         ("pooled", _p),
         ("obj_start", _p), ("obj_len", _p), ("slot_off", _p),
         ("n_obj", _i32), ("max_len", _i32), ("k_keep", _i32), ("m_pad", _i32),
-        ("merged", _p), ("counts", _p), ("counts_host", _p), ("ttm_ticket", _p), ("epoch", _i32),
-        ("reserved", _i32),
+        ("merged", _p), ("counts", _p), ("sims", _p), ("sims_pitch", _i32), ("reserved0", _i32),
+        ("counts_host", _p), ("epoch", _i32), ("reserved", _i32),
         ("w1", _p), ("b1", _p), ("w2", _p), ("b2", _p),
         ("hidden", _p), ("tokens_out", _p),
     ]
@@ -53,14 +54,15 @@ _SIGNATURES = {
     "ufv_last_error": (C.c_char_p, []),
     "ufv_device_address": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "ufv_tap_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
-    "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p,
-                                      _p, _p]),
+    "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p,
+                                      _p, _p, _p]),
     "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_int,
                                 C.c_int, _p, _p]),
     "ufv_ttm": (C.c_int, [_p, C.c_int, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p,
-                          _p, C.c_int, _p, C.c_int, _p, _p, _i32, _p]),
+                          _p, C.c_int, _p, C.c_int, _p, _i32, _p]),
     "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "ufv_encode": (C.c_int, [C.POINTER(EncodeArgs), _p]),
+    "ufv_compact_rows": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int, _p]),
     "ufv_gather_rows": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p]),
 }
 EXPORTED = tuple(_SIGNATURES)

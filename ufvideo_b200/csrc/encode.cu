@@ -47,6 +47,29 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ in, const int32_t* 
   for (int i = threadIdx.x; i < vec_per_row; i += blockDim.x) dst[i] = src[i];
 }
 
+// Object o owns rows [slot_off[o], slot_off[o] + counts[o]) of `in`; they move to rows
+// [sum of counts before o, ...) of `out`.  One CTA per object; the offset is a block-wide sum.
+__global__ void compact_rows_kernel(const uint4* __restrict__ in, const int32_t* __restrict__ slot_off,
+                                    const int32_t* __restrict__ counts, uint4* __restrict__ out,
+                                    int vec_per_row) {
+  __shared__ int s_part[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int o = blockIdx.x;
+  int before = 0;
+  for (int i = threadIdx.x; i < o; i += blockDim.x) before += counts[i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = before;
+  __syncthreads();
+  before = 0;
+  for (int w = 0; w < int(blockDim.x >> 5); ++w) before += s_part[w];
+  const int n = counts[o] * vec_per_row;
+  const uint4* src = in + size_t(slot_off[o]) * vec_per_row;
+  uint4* dst = out + size_t(before) * vec_per_row;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace ufv
 
 extern "C" int ufv_abi_version(void) { return UFV_ABI_VERSION; }
@@ -80,11 +103,25 @@ extern "C" int ufv_gather_rows(const void* in, const int32_t* row_map, void* out
                                     static_cast<uint4*>(out), row_bytes / 16));
 }
 
+extern "C" int ufv_compact_rows(const void* in, const int32_t* slot_off, const int32_t* counts, int n_obj,
+                                void* out, int row_bytes, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(n_obj >= 0 && row_bytes > 0 && row_bytes % 16 == 0, UFV_E_SHAPE,
+              "ufv_compact_rows: n_obj=%d row_bytes=%d", n_obj, row_bytes);
+  if (n_obj == 0) return 0;
+  UFV_REQUIRE(in && slot_off && counts && out, UFV_E_NULL, "ufv_compact_rows: null pointer");
+  UFV_REQUIRE(aligned16(in) && aligned16(out), UFV_E_ALIGN, "ufv_compact_rows: unaligned buffer");
+  return check_launch("ufv_compact_rows",
+                      launch_kernel(compact_rows_kernel, dim3(n_obj), dim3(256), 0,
+                                    static_cast<cudaStream_t>(stream), static_cast<const uint4*>(in), slot_off,
+                                    counts, static_cast<uint4*>(out), row_bytes / 16));
+}
+
 extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
   using namespace ufv;
   UFV_REQUIRE(a != nullptr, UFV_E_NULL, "ufv_encode: args is null");
   const int side = a->n_patch_side;
-  int rc = ufv_mask_to_patches(a->mask_desc, a->taps, a->n_masks, side, a->bits, a->cnt, a->idx,
+  int rc = ufv_mask_to_patches(a->mask_desc, a->taps, a->n_masks, side, a->any_row_mode, a->bits, a->cnt, a->idx,
                                a->idx_pitch, a->grp_off, a->grp_member, a->grp_ticket, a->grp_nu,
                                a->grp_ulist, a->grp_omask, stream);
   if (rc != 0) return rc;
@@ -93,8 +130,8 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
                      a->pooled, stream);
   if (rc != 0) return rc;
   rc = ufv_ttm(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
-               a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, nullptr, 0, a->counts_host,
-               a->ttm_ticket, a->epoch, stream);
+               a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, a->sims, a->sims_pitch,
+               a->counts_host, a->epoch, stream);
   if (rc != 0) return rc;
   if (a->m_pad == 0) return 0;
   rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, stream);

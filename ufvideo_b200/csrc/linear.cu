@@ -311,25 +311,27 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
                                     static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles));
 }
 
-// N-tile choice.  Per 64-deep k-block a CTA spends max(2 * BN tensor-core clocks, the time to pull
-// (128 + BN) * 128 bytes through its SM's L2 port); a launch costs that times the number of waves
-// over the SMs.  Small token counts therefore take narrow tiles (more CTAs share the weight
-// stream), large ones wide tiles (fewer bytes per flop).  UFV_GEMM_BN overrides (developer sweeps).
+// N-tile choice.  A launch costs (waves over the SMs) x (time of one tile).  Tile times per 64-deep
+// k-block, in units fitted to B200 measurements (tools/gemm_sweep.py): narrow tiles are bound by the
+// bytes a CTA pulls through its SM, (128 + BN) x 128 B; 128 x 128 and 128 x 256 tiles by the tensor
+// pipe (a 256-wide tile takes 1.7x, not 2x, the time of a 128-wide one).  Small token counts thus
+// take narrow tiles (more CTAs share the weight stream), large ones wide tiles.
+// UFV_GEMM_BN overrides the choice (developer sweeps and tests).
 static int choose_bn(int m, int n) {
   const char* env = getenv("UFV_GEMM_BN");
   const int forced = env ? atoi(env) : 0;
   if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
   const int m_tiles = (m + kBM - 1) / kBM;
+  static const struct { int bn; double tile_cost; } kChoices[] = {{32, 184.0}, {64, 216.0}, {128, 300.0}, {256, 512.0}};
   int best_bn = 32;
   double best_cost = -1.0;
-  for (int bn : {32, 64, 128, 256}) {
-    const long ctas = long(m_tiles) * ((n + bn - 1) / bn);
+  for (const auto& c : kChoices) {
+    const long ctas = long(m_tiles) * ((n + c.bn - 1) / c.bn);
     const long waves = (ctas + sm_count() - 1) / sm_count();
-    const double per_kb = (128.0 + bn) > 2.0 * bn ? (128.0 + bn) : 2.0 * bn;
-    const double cost = double(waves) * (per_kb + 24.0);   // + per-tile epilogue / refill share
+    const double cost = double(waves) * c.tile_cost;
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
-      best_bn = bn;
+      best_bn = c.bn;
     }
   }
   return best_bn;

@@ -112,9 +112,19 @@ __device__ __forceinline__ void word_prefix(const uint32_t* s_words, int32_t* s_
   }
 }
 
-constexpr int kPatchThreads = 384;
 constexpr int kRowChunks = 256;                  // 16-byte chunks of one staged row span (4 KB)
 constexpr int kRowUnroll = 4;                    // chunk loads in flight per thread
+
+// Two instantiations: ROWS = true can read in either mode and carries the 27 KB flag table (4 CTAs
+// of 384 threads per SM); ROWS = false is the lean tap-mode kernel for batches whose masks all live
+// in HBM (256 threads, ~1 KB of shared memory, 8 CTAs per SM -- the kernel is a latency chain per
+// CTA, so resident CTAs are what hides it).
+template <bool ROWS> struct PatchCfg {
+  static constexpr int kThreads = ROWS ? 384 : 256;
+  static constexpr int kMinCtas = ROWS ? 4 : 8;
+  static constexpr int kFlagRows = ROWS ? 2 * UFV_MAX_PATCH_SIDE : 1;
+  static constexpr int kFlagCols = ROWS ? kRowChunks : 1;
+};
 
 // Two ways to read a mask, chosen per object-frame (desc.flags bit 0 asks for row mode):
 //   row mode  (column span of the taps <= ~4 KB per row): the CTA pulls the 2 * n_out source rows with
@@ -123,7 +133,8 @@ constexpr int kRowUnroll = 4;                    // chunk loads in flight per th
 //             efficient when the mask lives in pinned HOST memory and is read in place.
 //   tap mode  (default; also wide masks): every thread gathers the four taps of its patches directly --
 //             the lowest latency for masks in HBM (15.7 us vs 20.3 us in row mode at 512 masks of 384 x 384).
-__global__ void __launch_bounds__(kPatchThreads, 4)
+template <bool ROWS>
+__global__ void __launch_bounds__(PatchCfg<ROWS>::kThreads, PatchCfg<ROWS>::kMinCtas)
 mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __restrict__ taps, int n_out,
                        uint32_t* __restrict__ bits_out, int32_t* __restrict__ cnt_out,
                        uint16_t* __restrict__ idx_out, int idx_pitch,
@@ -134,7 +145,8 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   __shared__ uint32_t s_words[UFV_BITS_WORDS];
   __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
   __shared__ uint32_t s_member_bits[UFV_MAX_GROUP][UFV_BITS_WORDS];
-  __shared__ uint16_t s_flags[2 * UFV_MAX_PATCH_SIDE][kRowChunks];
+  constexpr int kPatchThreads = PatchCfg<ROWS>::kThreads;
+  __shared__ uint16_t s_flags[PatchCfg<ROWS>::kFlagRows][PatchCfg<ROWS>::kFlagCols];
   __shared__ int s_span[2];
   __shared__ int s_last;
 
@@ -170,11 +182,11 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   }
   __syncthreads();
   const int cmin = s_span[0], cmax = s_span[1];
-  const bool row_mode = (d.flags & 1) != 0 && cmax >= 0 && ((cmax - cmin + 1) * es + 30) >> 4 <= kRowChunks;
+  const bool row_mode = ROWS && (d.flags & 1) != 0 && cmax >= 0 && ((cmax - cmin + 1) * es + 30) >> 4 <= kRowChunks;
 
   constexpr int kIters = (UFV_BITS_WORDS * 32 + kPatchThreads - 1) / kPatchThreads;
   bool on[kIters];
-  if (row_mode) {
+  if (ROWS && row_mode) {
     const int span_bytes = (cmax - cmin + 1) * es;
     const int nch = (span_bytes + 30) >> 4;        // chunks per source row, whatever its misalignment
     const int total = 2 * n_out * nch;             // s_taps[0 .. 2 * n_out) = h0 then h1: one slot per source row
@@ -334,9 +346,10 @@ extern "C" int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* t
 }
 
 extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
-                                   uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
-                                   const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
-                                   int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, void* stream) {
+                                   int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out,
+                                   int idx_pitch, const int32_t* grp_off, const int32_t* grp_member,
+                                   uint32_t* grp_ticket, int32_t* grp_nu, uint16_t* grp_ulist,
+                                   uint8_t* grp_omask, void* stream) {
   UFV_REQUIRE(n_masks >= 0 && n_out >= 1 && n_out <= UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
               "ufv_mask_to_patches: n_masks=%d n_out=%d out of range", n_masks, n_out);
   if (n_masks == 0) return 0;
@@ -346,9 +359,11 @@ extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* tap
   if (grp_ticket != nullptr)
     UFV_REQUIRE(grp_off && grp_member && grp_nu && grp_ulist && grp_omask, UFV_E_NULL,
                 "ufv_mask_to_patches: group plan requested but a plan pointer is null");
+  auto kernel = any_row_mode ? ufv::mask_to_patches_kernel<true> : ufv::mask_to_patches_kernel<false>;
+  const int threads = any_row_mode ? ufv::PatchCfg<true>::kThreads : ufv::PatchCfg<false>::kThreads;
   return ufv::check_launch(
       "ufv_mask_to_patches",
-      ufv::launch_kernel(ufv::mask_to_patches_kernel, dim3(n_masks), dim3(ufv::kPatchThreads), 0,
-                         static_cast<cudaStream_t>(stream), desc, taps, n_out, bits_out, cnt_out, idx_out,
-                         idx_pitch, grp_off, grp_member, grp_ticket, grp_nu, grp_ulist, grp_omask));
+      ufv::launch_kernel(kernel, dim3(n_masks), dim3(threads), 0, static_cast<cudaStream_t>(stream), desc,
+                         taps, n_out, bits_out, cnt_out, idx_out, idx_pitch, grp_off, grp_member, grp_ticket,
+                         grp_nu, grp_ulist, grp_omask));
 }

@@ -1,26 +1,29 @@
-// Kernel 3: fused temporal token merge (TTM).
+// Kernel 3: temporal token merge (TTM).
 //
 // Replaces token_merge (reference ufvideo/model/layer.py:6-33), its per-object dispatch
 // (layer.py:110-119) and the downcast to the model dtype (layer.py:123).  On a GPU the reference
 // pays one device->host sync per frame per object (the python `if sim[0,i] < kth`) plus O(T)
-// tiny launches; here one CTA per object does everything on chip:
-//   1. norms       m_t = max(sqrt(sum x_t^2), 1e-12)                      (F.normalize, :13-14)
-//   2. sims        s_i = sum (x_i / m_i) * (x_{i+1} / m_{i+1})            (:15)
-//   3. threshold   kth = r-th largest s (duplicates counted), r = T - K   (torch.topk, :17-18)
-//   4. cuts        cut after token i  <=>  s_i < kth (strict)             (:24)
-//   5. merge       mean of every maximal run, in temporal order           (:26,31)
+// tiny launches.  Here two launches cover every object of the batch:
+//   3a  ttm_sims_kernel   one warp per (object, adjacent pair):
+//         m_t = max(sqrt(sum x_t^2), 1e-12)                              (F.normalize, :13-14)
+//         s_i = sum (x_i / m_i) * (x_{i+1} / m_{i+1})                    (:15)
+//   3b  ttm_merge_kernel  one CTA per (object, output slot): r-th largest s by rank counting
+//         (torch.topk, :17-18), strict-below cuts (:24), the slot's run bounds by popcount
+//         prefix, the run mean in ascending token order (:26,31), downcast, count.
+// Work is spread over (objects x pairs) and (objects x K) CTAs, so a single 512-frame object
+// fills the GPU instead of one SM (r01's one-CTA-per-object kernel: 185 us at T = 512).
 // Sums follow the canonical order documented in oracle/restatement.py (one accumulator per lane
 // over elements 128k + 4*lane + j, xor-butterfly across lanes, no FMA contraction; run sums in
 // ascending token order), so sims, cuts and merged tokens are bit-identical to the oracle.
 //
-// Roofline: HBM/L2 (reads T*C*4 bytes per object twice from L2, writes <= K*C tokens).
+// Roofline: L2 (pooled rows were just written by kernel 2); reads ~3 T C 4 bytes per object.
 #include "common.cuh"
 
 namespace ufv {
 
-constexpr int kTtmThreads = 512;
-constexpr int kTtmWarps = kTtmThreads / 32;
-constexpr int kTtmBatch = 5;   // float4 loads in flight per lane while a row is reduced
+constexpr int kSimWarps = 4;                 // adjacent pairs per CTA of the similarity kernel
+constexpr int kMergeThreads = 288;           // 1152 channels / 4 per thread
+constexpr int kTtmBatch = 5;                 // float4 loads in flight per lane per row
 
 __device__ __forceinline__ float butterfly_sum(float v) {
 #pragma unroll
@@ -33,31 +36,259 @@ __device__ __forceinline__ bool ranks_above(float a, float b) {
   return a > b || (a != a && b == b);
 }
 
-// Token count of object o: to the device array and, when the caller asked for it, straight into
-// pinned host memory.  The CTA that publishes last stamps `epoch` behind the counts, which is what
-// the host polls: the reference's list[int] is ready as soon as the merge decisions are, with no
-// copy, event or stream synchronisation in between.
-__device__ __forceinline__ void publish_count(int32_t* counts_out, int32_t* counts_host,
-                                              uint32_t* done_ticket, int32_t epoch, int o, int count) {
-  counts_out[o] = count;
-  if (counts_host == nullptr) return;
-  counts_host[o] = count;
-  __threadfence_system();
-  if (atomicAdd(done_ticket, 1u) == gridDim.x - 1) {
-    *done_ticket = 0u;                    // self-reset for the next call
-    __threadfence_system();
-    *reinterpret_cast<volatile int32_t*>(counts_host + gridDim.x) = epoch;
+// canonical 32-lane strided sum of squares of one row (oracle/restatement.py::_rowsum)
+__device__ __forceinline__ float row_norm(const float* __restrict__ row, int c, int lane) {
+  float acc = 0.f;
+  for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
+    float4 v[kTtmBatch];
+#pragma unroll
+    for (int u = 0; u < kTtmBatch; ++u)
+      if (e0 + u * 128 < c) v[u] = *reinterpret_cast<const float4*>(row + e0 + u * 128);
+#pragma unroll
+    for (int u = 0; u < kTtmBatch; ++u) {
+      if (e0 + u * 128 < c) {
+        acc = __fadd_rn(acc, __fmul_rn(v[u].x, v[u].x));
+        acc = __fadd_rn(acc, __fmul_rn(v[u].y, v[u].y));
+        acc = __fadd_rn(acc, __fmul_rn(v[u].z, v[u].z));
+        acc = __fadd_rn(acc, __fmul_rn(v[u].w, v[u].w));
+      }
+    }
   }
+  return fmaxf(__fsqrt_rn(butterfly_sum(acc)), 1e-12f);   // F.normalize: max(||x||, eps)
+}
+
+// ---- kernel 3a: adjacent cosine similarities, one warp per (object, pair) --------------------------
+// Every pair of every object runs in parallel (a 512-frame object is 511 warps, not one CTA); each
+// warp derives both norms itself, so there is no norm pass and no synchronisation.
+__global__ void __launch_bounds__(32 * kSimWarps)
+ttm_sims_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ obj_start,
+                const int32_t* __restrict__ obj_len, int k_keep, float* __restrict__ sims, int sims_pitch) {
+  pdl_wait();                  // pooled rows come from kernel 2
+  pdl_launch_dependents();
+  const int o = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kSimWarps + (threadIdx.x >> 5);
+  const int t_len = obj_len[o];
+  if (t_len <= k_keep || i >= t_len - 1) return;     // layer.py:115: nothing to merge / no such pair
+  const float* ra = pooled + (size_t(obj_start[o]) + i) * c;
+  const float* rb = ra + c;
+  const float ma = row_norm(ra, c, lane);
+  const float mb = row_norm(rb, c, lane);
+  float acc = 0.f;
+  for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
+    float4 a[kTtmBatch], b[kTtmBatch];
+#pragma unroll
+    for (int u = 0; u < kTtmBatch; ++u) {
+      if (e0 + u * 128 < c) {
+        a[u] = *reinterpret_cast<const float4*>(ra + e0 + u * 128);   // L1 hits: just read by row_norm
+        b[u] = *reinterpret_cast<const float4*>(rb + e0 + u * 128);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTtmBatch; ++u) {
+      if (e0 + u * 128 < c) {
+        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].x, ma), __fdiv_rn(b[u].x, mb)));
+        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].y, ma), __fdiv_rn(b[u].y, mb)));
+        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].z, ma), __fdiv_rn(b[u].z, mb)));
+        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].w, ma), __fdiv_rn(b[u].w, mb)));
+      }
+    }
+  }
+  acc = butterfly_sum(acc);
+  if (lane == 0) sims[size_t(o) * sims_pitch + i] = acc;
+}
+
+// Token count of object o: to the device array and, when the caller asked for it, straight into
+// pinned host memory as ONE self-describing word, (epoch << 16) | count.  The host polls until every
+// word of the call carries the call's epoch: no fence, ticket, copy, event or stream synchronisation
+// sits between the merge decisions and the reference's list[int].
+__device__ __forceinline__ void publish_count(int32_t* counts_out, int32_t* counts_host, int32_t epoch,
+                                              int o, int count) {
+  counts_out[o] = count;
+  if (counts_host != nullptr)
+    *reinterpret_cast<volatile int32_t*>(counts_host + o) = (epoch << 16) | (count & 0xffff);
 }
 
 template <typename T>
+__device__ __forceinline__ void store_token(T* tokens_out, float* tokens_f32_out, size_t dst, float4 v) {
+  if (tokens_f32_out != nullptr) *reinterpret_cast<float4*>(tokens_f32_out + dst) = v;
+  tokens_out[dst + 0] = Elem<T>::from_f32(v.x);
+  tokens_out[dst + 1] = Elem<T>::from_f32(v.y);
+  tokens_out[dst + 2] = Elem<T>::from_f32(v.z);
+  tokens_out[dst + 3] = Elem<T>::from_f32(v.w);
+}
+template <>
+__device__ __forceinline__ void store_token<float>(float* tokens_out, float* tokens_f32_out, size_t dst, float4 v) {
+  if (tokens_f32_out != nullptr) *reinterpret_cast<float4*>(tokens_f32_out + dst) = v;
+  *reinterpret_cast<float4*>(tokens_out + dst) = v;
+}
+template <>
+__device__ __forceinline__ void store_token<__nv_bfloat16>(__nv_bfloat16* tokens_out, float* tokens_f32_out,
+                                                           size_t dst, float4 v) {
+  if (tokens_f32_out != nullptr) *reinterpret_cast<float4*>(tokens_f32_out + dst) = v;
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(tokens_out + dst) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+template <>
+__device__ __forceinline__ void store_token<__half>(__half* tokens_out, float* tokens_f32_out, size_t dst,
+                                                    float4 v) {
+  if (tokens_f32_out != nullptr) *reinterpret_cast<float4*>(tokens_f32_out + dst) = v;
+  const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(tokens_out + dst) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
+// ---- kernel 3b: threshold, cuts and ONE merged token per CTA (object, slot) -------------------------
+//   threshold   kth = r-th largest s (duplicates counted), r = T - K   (torch.topk, :17-18)
+//   cuts        cut after token i  <=>  s_i < kth (strict)             (:24)
+//   merge       mean of the slot's run, ascending token order          (:26,31)
+// Every slot CTA of an object repeats the (cheap) selection; slot 0 also publishes the count.
+template <typename T>
+__global__ void __launch_bounds__(kMergeThreads)
+ttm_merge_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ obj_start,
+                 const int32_t* __restrict__ obj_len, const int32_t* __restrict__ slot_off, int k_keep,
+                 int max_len, const float* __restrict__ sims, int sims_pitch, T* __restrict__ tokens_out,
+                 float* __restrict__ tokens_f32_out, int32_t* __restrict__ counts_out,
+                 uint32_t* __restrict__ cuts_out, int cut_pitch_words, int32_t* __restrict__ counts_host,
+                 int32_t epoch) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const int len_words = (max_len + 31) / 32;
+  float* s_sim = reinterpret_cast<float*>(dyn_smem);                 // [max_len]
+  uint32_t* s_cutw = reinterpret_cast<uint32_t*>(s_sim + max_len);   // [len_words]
+  int32_t* s_wpre = reinterpret_cast<int32_t*>(s_cutw + len_words);  // [len_words + 1]
+  __shared__ float s_kth;
+  __shared__ int s_first, s_last;
+
+  const int o = blockIdx.y, g = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();                  // similarities come from kernel 3a, pooled rows from kernel 2
+  pdl_launch_dependents();
+  const int t_len = obj_len[o];
+  const int n_slots = min(t_len, k_keep);
+  if (g >= n_slots) {          // this object reserved fewer than K slots (T_o < K)
+    if (g == 0 && tid == 0) publish_count(counts_out, counts_host, epoch, o, 0);
+    return;
+  }
+  const float* x = pooled + size_t(obj_start[o]) * c;
+  const int c4 = c >> 2;
+  const size_t out_row = size_t(slot_off[o] + g) * c;
+
+  if (g == 0 && cuts_out != nullptr)
+    for (int w = tid; w < cut_pitch_words; w += kMergeThreads) cuts_out[size_t(o) * cut_pitch_words + w] = 0u;
+
+  if (t_len <= k_keep) {       // layer.py:115: nothing to merge, token g passes through
+    for (int q = tid; q < c4; q += kMergeThreads)
+      store_token<T>(tokens_out, tokens_f32_out, out_row + q * 4,
+                     *reinterpret_cast<const float4*>(x + size_t(g) * c + q * 4));
+    if (g == 0 && tid == 0) publish_count(counts_out, counts_host, epoch, o, t_len);
+    return;
+  }
+
+  // ---- r-th largest similarity by rank counting ------------------------------------------------------
+  const int n_sim = t_len - 1;
+  for (int i = tid; i < n_sim; i += kMergeThreads) s_sim[i] = sims[size_t(o) * sims_pitch + i];
+  __syncthreads();
+  const int r = t_len - k_keep;
+  for (int i = tid; i < n_sim; i += kMergeThreads) {
+    const float si = s_sim[i];
+    int above = 0, not_below = 0;
+    for (int j = 0; j < n_sim; ++j) {
+      const float sj = s_sim[j];          // broadcast read
+      above += ranks_above(sj, si);
+      not_below += !ranks_above(si, sj);
+    }
+    if (above < r && r <= not_below) s_kth = si;   // every writer holds an equal value
+  }
+  __syncthreads();
+
+  // ---- cuts -> bounds of run g ---------------------------------------------------------------------------
+  const float kth = s_kth;
+  for (int base = 0; base < len_words * 32; base += 32 * (kMergeThreads / 32)) {
+    const int i = base + tid;
+    const bool cut = i < n_sim && s_sim[i] < kth;
+    const uint32_t word = __ballot_sync(0xffffffffu, cut);
+    if (lane == 0 && (i >> 5) < len_words) s_cutw[i >> 5] = word;
+  }
+  __syncthreads();
+  if (warp == 0) {   // exclusive prefix over the cut words
+    int carry = 0;
+    for (int w0 = 0; w0 < len_words; w0 += 32) {
+      const int w = w0 + lane;
+      const int mine = w < len_words ? __popc(s_cutw[w]) : 0;
+      int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+      }
+      if (w < len_words) s_wpre[w] = carry + incl - mine;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_wpre[len_words] = carry;
+  }
+  if (tid == 0) {
+    s_first = 0;
+    s_last = t_len - 1;        // the last run always ends at the last token (:29-31)
+  }
+  __syncthreads();
+  const int n_cut = s_wpre[len_words];
+  const int count = n_cut + 1;            // <= k_keep because at least r sims are >= kth
+  for (int i = tid; i < n_sim; i += kMergeThreads) {   // cut number g - 1 opens run g, cut number g closes it
+    const uint32_t word = s_cutw[i >> 5];
+    const uint32_t bit = 1u << (i & 31);
+    if (word & bit) {
+      const int ord = s_wpre[i >> 5] + __popc(word & (bit - 1u));
+      if (ord == g - 1) s_first = i + 1;
+      if (ord == g) s_last = i;
+    }
+  }
+  if (g == 0) {
+    if (tid == 0) publish_count(counts_out, counts_host, epoch, o, count);
+    if (cuts_out != nullptr)
+      for (int w = tid; w < min(len_words, cut_pitch_words); w += kMergeThreads)
+        cuts_out[size_t(o) * cut_pitch_words + w] = s_cutw[w];
+  }
+  __syncthreads();
+
+  // ---- mean of run g, ascending token order; slots past the count are zero-filled -----------------------
+  const int first = s_first, last = s_last;
+  for (int q = tid; q < c4; q += kMergeThreads) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < count) {
+      const float* src = x + size_t(first) * c + q * 4;
+#pragma unroll 8
+      for (int t = first; t <= last; ++t, src += c) {
+        const float4 v = *reinterpret_cast<const float4*>(src);
+        acc.x = __fadd_rn(acc.x, v.x);
+        acc.y = __fadd_rn(acc.y, v.y);
+        acc.z = __fadd_rn(acc.z, v.z);
+        acc.w = __fadd_rn(acc.w, v.w);
+      }
+      const float n = float(last - first + 1);
+      acc.x = __fdiv_rn(acc.x, n);
+      acc.y = __fdiv_rn(acc.y, n);
+      acc.z = __fdiv_rn(acc.z, n);
+      acc.w = __fdiv_rn(acc.w, n);
+    }
+    store_token<T>(tokens_out, tokens_f32_out, out_row + q * 4, acc);
+  }
+}
+
+// ---- fused variant for short objects (max_len <= kFusedMaxLen): one CTA per object does 3a and 3b ------
+// With T = 16 the whole merge is a few microseconds of latency; one launch and one CTA per object
+// beat two launches (measured at 32 objects x 16 frames: 11.7 us against 8.2 + 15.7 us).
+constexpr int kTtmThreads = 512;
+constexpr int kTtmWarps = kTtmThreads / 32;
+constexpr int kFusedMaxLen = 64;
+
+template <typename T>
 __global__ void __launch_bounds__(kTtmThreads)
-ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ obj_start,
+ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ obj_start,
            const int32_t* __restrict__ obj_len, const int32_t* __restrict__ slot_off, int k_keep,
            int max_len, T* __restrict__ tokens_out, float* __restrict__ tokens_f32_out,
            int32_t* __restrict__ counts_out, uint32_t* __restrict__ cuts_out, int cut_pitch_words,
-           float* __restrict__ sims_out, int sims_pitch, int32_t* __restrict__ counts_host,
-           uint32_t* __restrict__ done_ticket, int32_t epoch) {
+           float* __restrict__ sims_out, int sims_pitch, int32_t* __restrict__ counts_host, int32_t epoch) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const int len_words = (max_len + 31) / 32;
   float* s_norm = reinterpret_cast<float*>(dyn_smem);          // [max_len]
@@ -91,7 +322,7 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
       tokens_out[dst + 2] = Elem<T>::from_f32(v.z);
       tokens_out[dst + 3] = Elem<T>::from_f32(v.w);
     }
-    if (tid == 0) publish_count(counts_out, counts_host, done_ticket, epoch, o, t_len);
+    if (tid == 0) publish_count(counts_out, counts_host, epoch, o, t_len);
     return;
   }
 
@@ -202,7 +433,7 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
   }
   if (tid == 0) {
     s_gend[n_cut] = t_len - 1;            // the last run always ends at the last token (:29-31)
-    publish_count(counts_out, counts_host, done_ticket, epoch, o, count);
+    publish_count(counts_out, counts_host, epoch, o, count);
   }
   if (cuts_out != nullptr)
     for (int w = tid; w < min(len_words, cut_pitch_words); w += kTtmThreads)
@@ -240,22 +471,41 @@ ttm_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ 
   }
 }
 
+
 template <typename T>
 static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
                       const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
                       float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
-                      int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
-                      uint32_t* done_ticket, int32_t epoch, cudaStream_t stream) {
+                      int cut_pitch_words, float* sims, int sims_pitch, int32_t* counts_host, int32_t epoch,
+                      cudaStream_t stream) {
   const int len_words = (max_len + 31) / 32;
-  const size_t smem = size_t(max_len) * 8 + size_t(len_words) * 4 + size_t(len_words + 1) * 4 +
-                      size_t(k_keep + 1) * 4;
-  auto kernel = ttm_kernel<T>;
+  if (max_len <= kFusedMaxLen) {
+    const size_t smem = size_t(max_len) * 8 + size_t(len_words) * 4 + size_t(len_words + 1) * 4 +
+                        size_t(k_keep + 1) * 4;
+    auto kernel = ttm_fused_kernel<T>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    return check_launch("ufv_ttm (fused)",
+                        launch_kernel(kernel, dim3(n_obj), dim3(kTtmThreads), smem, stream, pooled, c, obj_start,
+                                      obj_len, slot_off, k_keep, max_len, static_cast<T*>(tokens_out),
+                                      tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims, sims_pitch,
+                                      counts_host, epoch));
+  }
+  if (max_len > k_keep) {
+    const dim3 grid((max_len - 1 + kSimWarps - 1) / kSimWarps, n_obj);
+    const int rc = check_launch("ufv_ttm (similarities)",
+                                launch_kernel(ttm_sims_kernel, grid, dim3(32 * kSimWarps), 0, stream, pooled, c,
+                                              obj_start, obj_len, k_keep, sims, sims_pitch));
+    if (rc != 0) return rc;
+  }
+  const size_t smem = size_t(max_len) * 4 + size_t(len_words) * 4 + size_t(len_words + 1) * 4;
+  auto kernel = ttm_merge_kernel<T>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  return check_launch("ufv_ttm",
-                      launch_kernel(kernel, dim3(n_obj), dim3(kTtmThreads), smem, stream, pooled, c, obj_start,
-                                    obj_len, slot_off, k_keep, max_len, static_cast<T*>(tokens_out),
-                                    tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out,
-                                    sims_pitch, counts_host, done_ticket, epoch));
+  const dim3 grid(max_len < k_keep ? max_len : k_keep, n_obj);
+  return check_launch("ufv_ttm (merge)",
+                      launch_kernel(kernel, grid, dim3(kMergeThreads), smem, stream, pooled, c, obj_start,
+                                    obj_len, slot_off, k_keep, max_len, static_cast<const float*>(sims),
+                                    sims_pitch, static_cast<T*>(tokens_out), tokens_f32_out, counts_out,
+                                    cuts_out, cut_pitch_words, counts_host, epoch));
 }
 
 }  // namespace ufv
@@ -264,7 +514,7 @@ extern "C" int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, con
                        const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
                        int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
                        int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
-                       uint32_t* done_ticket, int32_t epoch, void* stream) {
+                       int32_t epoch, void* stream) {
   using namespace ufv;
   UFV_REQUIRE(n_obj >= 0, UFV_E_SHAPE, "ufv_ttm: n_obj=%d", n_obj);
   if (n_obj == 0) return 0;
@@ -277,21 +527,25 @@ extern "C" int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, con
               "ufv_ttm: buffers must be 16-byte aligned");
   UFV_REQUIRE(cuts_out == nullptr || cut_pitch_words >= (max_len + 31) / 32, UFV_E_SHAPE,
               "ufv_ttm: cut_pitch_words too small");
+  UFV_REQUIRE(max_len <= k_keep || sims_out != nullptr, UFV_E_NULL,
+              "ufv_ttm: sims_out (fp32 [n_obj * sims_pitch] scratch) is required when an object has more "
+              "than k_keep frames");
   UFV_REQUIRE(sims_out == nullptr || sims_pitch >= max_len - 1, UFV_E_SHAPE, "ufv_ttm: sims_pitch too small");
-  UFV_REQUIRE(counts_host == nullptr || done_ticket != nullptr, UFV_E_NULL,
-              "ufv_ttm: counts_host needs done_ticket");
+  UFV_REQUIRE(counts_host == nullptr || (epoch > 0 && epoch < 32768), UFV_E_SHAPE,
+              "ufv_ttm: epoch %d must be in [1, 32767] when counts_host is given", epoch);
+  UFV_REQUIRE(counts_host == nullptr || k_keep < 65536, UFV_E_SHAPE, "ufv_ttm: k_keep too large for the host word");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (out_dtype) {
     case UFV_F32:
       return launch_ttm<float>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep, tokens_out,
-                               tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, done_ticket, epoch, st);
+                               tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, epoch, st);
     case UFV_BF16:
       return launch_ttm<__nv_bfloat16>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep,
                                        tokens_out, tokens_f32_out, counts_out, cuts_out, cut_pitch_words,
-                                       sims_out, sims_pitch, counts_host, done_ticket, epoch, st);
+                                       sims_out, sims_pitch, counts_host, epoch, st);
     case UFV_F16:
       return launch_ttm<__half>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep, tokens_out,
-                                tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, done_ticket, epoch, st);
+                                tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, epoch, st);
     default:
       return fail(UFV_E_DTYPE, "ufv_ttm: unsupported output dtype %d", out_dtype);
   }

@@ -62,7 +62,7 @@ def mask_to_patches(plan: packer.EncodePlan, device, n_out: int = 27, want_idx: 
     nu, ulist, omask = _plan_buffers(plan, device)
     d = plan.dev
     _cabi.check(_cabi.lib().ufv_mask_to_patches(
-        d["mask_desc"], d["taps"], q, n_out, bits.data_ptr(), cnt.data_ptr(),
+        d["mask_desc"], d["taps"], q, n_out, plan.any_row_mode, bits.data_ptr(), cnt.data_ptr(),
         idx.data_ptr() if want_idx else None, 736, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
         nu.data_ptr(), ulist.data_ptr(), omask.data_ptr(), _stream_ptr(device)))
     return {"bits": bits, "cnt": cnt, "idx": idx, "grp_nu": nu, "grp_ulist": ulist, "grp_omask": omask}
@@ -90,19 +90,18 @@ def ttm(pooled: torch.Tensor, plan: packer.EncodePlan, k_keep: int, out_dtype: t
     tokens = torch.empty((plan.m_pad, c), dtype=out_dtype, device=device)
     counts = torch.empty((plan.n_obj,), dtype=torch.int32, device=device)
     extras = {}
-    f32 = cuts = sims = None
+    f32 = cuts = None
     words = (plan.max_len + 31) // 32
+    sims = extras["sims"] = torch.zeros((plan.n_obj, max(plan.max_len, 1)), dtype=torch.float32, device=device)
     if debug:
         f32 = extras["tokens_f32"] = torch.empty((plan.m_pad, c), dtype=torch.float32, device=device)
         cuts = extras["cuts"] = torch.zeros((plan.n_obj, words), dtype=torch.int32, device=device)
-        sims = extras["sims"] = torch.zeros((plan.n_obj, max(plan.max_len, 1)), dtype=torch.float32,
-                                            device=device)
     d = plan.dev
     _cabi.check(_cabi.lib().ufv_ttm(
         pooled.data_ptr(), c, d["obj_start"], d["obj_len"], d["slot_off"], plan.n_obj, plan.max_len,
         k_keep, tokens.data_ptr(), packer.FEAT_DTYPES[out_dtype],
         f32.data_ptr() if debug else None, counts.data_ptr(), cuts.data_ptr() if debug else None,
-        words, sims.data_ptr() if debug else None, max(plan.max_len, 1), None, None, 0,
+        words, sims.data_ptr(), max(plan.max_len, 1), None, 0,
         _stream_ptr(device)))
     return tokens, counts, extras
 
@@ -130,17 +129,22 @@ def gather_rows(x: torch.Tensor, row_map: torch.Tensor):
 
 
 def _await_counts(plan: packer.EncodePlan, device) -> np.ndarray:
-    """Poll the epoch stamp kernel 3 writes behind the counts in pinned host memory."""
-    flag, n, epoch = plan.counts_np, plan.n_obj, plan.epoch
+    """Poll the pinned words kernel 3 writes, (epoch << 16) | count per object, until all of them
+    carry this call's epoch; returns the int32 counts."""
+    words, epoch = plan.counts_np[:plan.n_obj], plan.epoch
     spins = 0
-    while flag[n] != epoch:
+    while True:
+        snap = words.copy()
+        if ((snap >> 16) == epoch).all():
+            return snap & 0xffff
         spins += 1
-        if spins & 0xffff == 0:                  # every ~10 ms: surface a failed launch instead of hanging
-            stream = torch.cuda.current_stream(device)
-            if stream.query() and flag[n] != epoch:
+        if spins & 0x3fff == 0:                  # every few ms: surface a failed launch instead of hanging
+            if torch.cuda.current_stream(device).query():
+                snap = words.copy()
+                if ((snap >> 16) == epoch).all():
+                    return snap & 0xffff
                 torch.cuda.synchronize(device)
                 raise RuntimeError("ufvideo_b200: the merge kernel finished without publishing its counts")
-    return flag[:n]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -257,10 +261,11 @@ class MaskExtractor(nn.Module):
         if two:                                   # the reference's depth=2 projector: one chained call
             a = run["args"]
             a.tokens_out = tokens.data_ptr()
-            a.epoch = plan.epoch = (plan.epoch + 1) & 0x3fffffff
+            a.epoch = plan.epoch = plan.epoch % 32767 + 1          # 1 .. 32767, the tag of this call's counts
             _cabi.check(lib.ufv_encode(run["args_ref"], stream))
         else:                                     # other depths: the same kernels, staged
-            _cabi.check(lib.ufv_mask_to_patches(d["mask_desc"], d["taps"], q, side, ptr["bits"], ptr["cnt"],
+            _cabi.check(lib.ufv_mask_to_patches(d["mask_desc"], d["taps"], q, side, plan.any_row_mode,
+                                                ptr["bits"], ptr["cnt"],
                                                 None, 0, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
                                                 ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], stream))
             _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, n_patch, c, ptr["cnt"], d["grp_row"],
@@ -268,7 +273,7 @@ class MaskExtractor(nn.Module):
                                           ptr["grp_omask"], plan.n_groups, plan.max_group, ptr["pooled"], stream))
             _cabi.check(lib.ufv_ttm(ptr["pooled"], c, d["obj_start"], d["obj_len"], d["slot_off"],
                                     plan.n_obj, plan.max_len, k_keep, ptr["merged"], dt, None,
-                                    ptr["counts"], None, 0, None, 0, None, None, 0, stream))
+                                    ptr["counts"], None, 0, ptr["sims"], max(plan.max_len, 1), None, 0, stream))
             x = run["view"]("merged", feats.dtype, (m_pad, c))
             for i, lin in enumerate(linears):
                 x = linear(x, lin.weight, lin.bias, gelu=i < len(linears) - 1)
@@ -290,6 +295,7 @@ class MaskExtractor(nn.Module):
         # one workspace allocation, carved into 256-byte aligned pieces
         sizes = (("bits", q * _cabi.BITS_WORDS * 4), ("cnt", q * 4), ("pooled", q * c * 4),
                  ("merged", m_pad * c * es), ("hidden", m_pad * hid * es), ("counts", plan.n_obj * 4),
+                 ("sims", plan.n_obj * max(plan.max_len, 1) * 4),
                  ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.PLAN_PITCH))
         off, total = {}, 0
         for name, nbytes in sizes:
@@ -307,21 +313,22 @@ class MaskExtractor(nn.Module):
                "counts": view("counts", torch.int32, (plan.n_obj,))}
         if two:
             d = plan.dev
-            if plan.counts_pinned is None:        # pinned int32 [n_obj + 1]: counts, then the epoch stamp
-                plan.counts_pinned = torch.zeros((plan.n_obj + 1,), dtype=torch.int32).pin_memory()
+            if plan.counts_pinned is None:        # pinned int32 [n_obj]: (epoch << 16) | count per object
+                plan.counts_pinned = torch.zeros((max(plan.n_obj, 1),), dtype=torch.int32).pin_memory()
                 plan.counts_np = plan.counts_pinned.numpy()
                 plan.counts_dev_addr = packer._device_address(plan.counts_pinned)
             a = _cabi.EncodeArgs(
                 feats=feats.data_ptr(), feat_dtype=dt, n_patch_side=side, n_rows=f, c=c, hid=hid,
-                mask_desc=d["mask_desc"], taps=d["taps"], n_masks=q, idx_pitch=0, bits=ptr["bits"],
+                mask_desc=d["mask_desc"], taps=d["taps"], n_masks=q, idx_pitch=0,
+                any_row_mode=plan.any_row_mode, bits=ptr["bits"],
                 cnt=ptr["cnt"], idx=None, grp_ticket=plan.ticket.data_ptr(), grp_nu=ptr["grp_nu"],
                 grp_ulist=ptr["grp_ulist"], grp_omask=ptr["grp_omask"], grp_row=d["grp_row"],
                 grp_off=d["grp_off"], grp_member=d["grp_member"], n_groups=plan.n_groups,
                 max_group=plan.max_group, pooled=ptr["pooled"], obj_start=d["obj_start"],
                 obj_len=d["obj_len"], slot_off=d["slot_off"], n_obj=plan.n_obj, max_len=plan.max_len,
                 k_keep=k_keep, m_pad=m_pad, merged=ptr["merged"], counts=ptr["counts"],
-                counts_host=plan.counts_dev_addr, ttm_ticket=plan.ticket.data_ptr() + 4 * max(plan.n_groups, 1),
-                epoch=0,
+                sims=ptr["sims"], sims_pitch=max(plan.max_len, 1),
+                counts_host=plan.counts_dev_addr, epoch=0,
                 w1=linears[0].weight.data_ptr(), b1=linears[0].bias.data_ptr(),
                 w2=linears[1].weight.data_ptr(), b2=linears[1].bias.data_ptr(),
                 hidden=ptr["hidden"], tokens_out=None)
@@ -347,12 +354,12 @@ class MaskExtractor(nn.Module):
             return tokens, list(plan.expect_counts)
         # ties at the merge threshold left some object with fewer than min(T, K) tokens:
         # drop the zero-filled slots (rare; exact ties only)
-        region_token_nums = region_token_nums.copy()
-        starts = plan.host["slot_off"]
-        row_map = np.concatenate([np.arange(s, s + n, dtype=np.int32)
-                                  for s, n in zip(starts, region_token_nums)] or [np.zeros(0, np.int32)])
-        tokens = gather_rows(tokens, torch.from_numpy(row_map).to(tokens.device))
-        return tokens, [int(n) for n in region_token_nums]
+        nums = region_token_nums.tolist()
+        packed = torch.empty((sum(nums), tokens.shape[1]), dtype=tokens.dtype, device=tokens.device)
+        _cabi.check(_cabi.lib().ufv_compact_rows(
+            tokens.data_ptr(), plan.dev["slot_off"], counts.data_ptr(), plan.n_obj, packed.data_ptr(),
+            tokens.shape[1] * tokens.element_size(), _stream_ptr(tokens.device)))
+        return packed, nums
 
 
 def build_region_encoder(config, image_aspect_ratio):
