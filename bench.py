@@ -19,6 +19,7 @@ cpu_baseline  the oracle's torch-CPU port of the reference on a bounded sample (
 from __future__ import annotations
 
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -207,20 +208,83 @@ def run_ours(a):
     enc = enc.to(dev).bfloat16()
     pad_rows, pad_objs = n_obj * k, n_obj
 
-    def collect(tokens, counts):
-        if world > 1:   # the one collective: NCCL all-gather of the per-rank object tokens
-            return sharding.all_gather_tokens(tokens, torch.tensor(counts, dtype=torch.int32, device=dev),
-                                              pad_rows, pad_objs)
-        return tokens
+    # N > 1: the projector and the merge kernel write straight into the all-gather payload
+    # (sharding.new_payload); the ONE collective per step is an asynchronous NCCL all-gather of
+    # that payload, overlapped with the next step's kernels and drained before the clock stops.
+    slots = packer.build_plan(masks_dev, ann, feats_dev.shape[0], k, dev).slots
+    pending = collections.deque()
+    pg, gather_kind = None, "none (1 GPU)"
+    if world > 1:
+        # Preferred: the all-gather fused into the last Linear (ufv_linear_gather): its epilogue stores
+        # every tile into all ranks' gathered buffers over NVLink.  UFV_BENCH_GATHER=nccl (or a failed
+        # symmetric-memory rendezvous) falls back to one asynchronous NCCL all-gather of the payload.
+        if os.environ.get("UFV_BENCH_GATHER", "fused") != "nccl":
+            try:
+                pg = sharding.PeerGather(pad_rows, pad_objs, 3584, torch.bfloat16, dev)
+                gather_kind = ("fused into the last Linear: tcgen05 epilogue stores tiles to every rank over NVLink ("
+                               + ("multimem.st via NVSwitch multicast" if pg.multimem else "one st per peer")
+                               + "), arrival flags, no NCCL on the data path")
+            except Exception as exc:   # noqa: BLE001 -- report and fall back
+                print(f"[bench] symmetric-memory gather unavailable ({exc!r}); using NCCL", file=sys.stderr)
+        if pg is None:
+            gather_kind = ("one asynchronous NCCL all-gather per step of the payload the kernels wrote "
+                           "(padded tokens + counts), overlapped with the next step")
+
+    def gather_step(feats, masks):
+        if pg is not None:
+            peer, tok_view, cnt_view, step = pg.begin(slots)
+            enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
+            pending.append(step)
+            while len(pending) > 1:
+                pending.popleft()
+            return step
+        payload, tok_view, cnt_view = sharding.new_payload(slots, pad_rows, pad_objs, 3584, torch.bfloat16, dev)
+        enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view)   # counts also reach the host
+        gathered, work = sharding.all_gather_payload(payload, async_op=True)
+        pending.append((work, gathered, payload))
+        while len(pending) > 2:
+            pending.popleft()[0].wait()
+        return gathered, work
+
+    def drain():
+        """Stream-ordered: every outstanding step's gathered result is complete on this rank."""
+        while pending:
+            item = pending.popleft()
+            if pg is not None:
+                pg.wait(item)
+            else:
+                item[0].wait()
 
     def step_resident():
-        tokens, counts = enc(feats_dev, masks_dev, None, ann, None)
-        return collect(tokens, counts)
+        if world > 1:
+            return gather_step(feats_dev, masks_dev)
+        return enc(feats_dev, masks_dev, None, ann, None)[0]
 
     def step_e2e():
-        tokens, counts = enc(feats_host, masks_host, None, ann, None)       # H2D inside forward
-        out = collect(tokens, counts)
-        return out.cpu()                                                     # D2H of the result
+        if world > 1:
+            res = gather_step(feats_host, masks_host)                           # H2D inside forward_padded
+            if pg is not None:
+                pg.wait(res)
+                return pg.gathered(res).cpu()                                    # D2H of the gathered result
+            res[1].wait()
+            return res[0].cpu()
+        tokens, counts = enc(feats_host, masks_host, None, ann, None)           # H2D inside forward
+        return tokens.cpu()                                                      # D2H of the result
+
+    if pg is not None:
+        # self-check before timing: the fused gather equals an NCCL all-gather of the same payload
+        step = gather_step(feats_dev, masks_dev)
+        drain()
+        torch.cuda.synchronize()
+        got_t, got_c = sharding.unpack_padded(pg.gathered(step), pad_rows, pad_objs)
+        payload, tok_view, cnt_view = sharding.new_payload(slots, pad_rows, pad_objs, 3584, torch.bfloat16, dev)
+        enc.forward_padded(feats_dev, masks_dev, ann, out=tok_view, counts_out=cnt_view)
+        ref, _ = sharding.all_gather_payload(payload)
+        torch.cuda.synchronize()
+        ref_t, ref_c = sharding.unpack_padded(ref, pad_rows, pad_objs)
+        if got_c != ref_c or not torch.equal(got_t, ref_t):
+            sys.exit("bench.py: fused all-gather disagrees with the NCCL all-gather")
+        pg.check()
 
     def barrier():
         if world > 1:
@@ -230,11 +294,13 @@ def run_ours(a):
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
+        drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        drain()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -265,6 +331,8 @@ def run_ours(a):
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
 
+    if pg is not None:
+        pg.check()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -287,7 +355,11 @@ def run_ours(a):
         span = (int(cols.max()) - int(cols.min()) + 1) * 4
         mask_bytes_read += m.shape[0] * rows * ((span + 15) // 16 * 16)
     h2d = feats_host.numel() * 2 + mask_bytes_read + int(plan.buffer.numel())
-    d2h = n_obj * k * 3584 * 2 * (world if world > 1 else 1) + n_obj * 4
+    if world > 1:
+        tail_rows = sharding._padded_tail_rows(pad_objs, 3584 * 2)
+        d2h = world * (pad_rows + tail_rows) * 3584 * 2 + n_obj * 4
+    else:
+        d2h = n_obj * k * 3584 * 2 + n_obj * 4
     line = {
         "metric": METRIC, "value": total_q / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -298,10 +370,10 @@ def run_ours(a):
                                   f"{mask_bytes_full / 1e6:.0f} MB read in place over PCIe by kernel 1, "
                                   f"{mask_bytes_read / 1e6:.0f} MB touched"),
                    "l2": f"inputs larger than L2: {feats_dev.numel() * 2 / 1e6:.0f} MB of features per step vs 126 MB",
-                   "collective": "one NCCL all-gather of object tokens per step" if world > 1 else "none (1 GPU)"},
+                   "collective": gather_kind},
         "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-        "gpu_launches": 5 * a.steps,
+        "gpu_launches": (6 if pg is not None else 5) * a.steps,   # kernels 1, 2, 3, 4a, 4b (+ flag wait)
         "roofline": {"kernel": "mask_pool_kernel<bf16>", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": pool_bytes, "us_per_launch": ms_pool * 1e3,

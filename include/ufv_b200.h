@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UFV_ABI_VERSION 5
+#define UFV_ABI_VERSION 6
 
 /* element types */
 enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3 };
@@ -161,6 +161,45 @@ int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, i
                int dtype, int gelu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Kernel 4 fused with the result-collection all-gather (multi-GPU, clips sharded over ranks).
+ * The reference collects per-rank results through files (eval/inference_PixRQA.py:214); here the
+ * epilogue of the last Linear stores every output tile straight into the gathered buffer of
+ * EVERY rank over NVLink -- one multimem.st per 16 bytes through the NVSwitch multicast address,
+ * or one st per peer -- so the transfer rides under the GEMM instead of following it.
+ *   dst[i]       address of element (0, 0) of THIS rank's token rows inside destination copy i
+ *                (the multicast alias of the symmetric gathered buffer when multimem != 0, else
+ *                one entry per rank, this rank included)
+ *   tail_src     int32 [tail_words] in local memory (reserved rows per object + token counts,
+ *                written earlier in the stream), copied to tail_dst[i] by the last CTA
+ *   flag[i]      address of this rank's int32 arrival flag in destination i; written with
+ *                release.sys semantics = flag_value after every store of the call is fenced
+ *   ticket       one zeroed uint32 in local device memory (zero again on completion)
+ * Receivers wait with ufv_wait_flags.
+ * -------------------------------------------------------------------------------------------*/
+#define UFV_MAX_PEER_DST 8
+typedef struct ufv_peer_args {
+  uint64_t dst[UFV_MAX_PEER_DST];
+  uint64_t tail_dst[UFV_MAX_PEER_DST];
+  uint64_t flag[UFV_MAX_PEER_DST];
+  const int32_t* tail_src;
+  uint32_t* ticket;
+  int32_t tail_words;
+  int32_t n_dst;
+  int32_t multimem;
+  int32_t flag_value;
+} ufv_peer_args;
+
+/* y[m, n] = x . w^T + bias (bf16 / fp16, no activation), written to every peer->dst instead of a
+ * local y. */
+int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
+                      const ufv_peer_args* peer_host, void* stream);
+
+/* Block the stream until flags[0 .. n) (int32, local memory) all equal `value` (acquire.sys loads).
+ * Gives up after ~timeout_ms (0 = 2000) and stores 1 to *timed_out (device int32, optional). */
+int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The whole path in one call (kernels 1-4 chained on `stream`).  Replaces
  * MaskExtractor.forward (layer.py:63-128) minus the host read-back of counts.
  * -------------------------------------------------------------------------------------------*/
@@ -188,6 +227,9 @@ typedef struct ufv_encode_args {
   /* projector: feat_linear.0 / feat_linear.2 (layer.py:55-59) */
   const void* w1; const void* b1; const void* w2; const void* b2;
   void* hidden; void* tokens_out;
+  /* optional: fuse the result-collection all-gather into the last Linear (ufv_linear_gather);
+   * tokens_out is then unused */
+  const ufv_peer_args* peer;
 } ufv_encode_args;
 
 int ufv_encode(const ufv_encode_args* args_host, void* stream);

@@ -367,6 +367,68 @@ def test_ties_in_the_middle_keep_object_order(dev):
     assert np.abs(tokens.cpu().numpy() - o["tokens"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("m", [0, 40, 256, 700])
+def test_linear_gather_stores_tiles_tail_and_flags_to_every_destination(dev, m):
+    """ufv_linear_gather on one GPU with two local "ranks" as destinations (one st per peer): both
+    copies equal ufv_linear's output, the tail is forwarded, flags carry the step value, the ticket
+    resets.  (The multimem.st path needs NVSwitch multicast: covered by bench.py's self-check at N > 1.)"""
+    import ctypes
+    from ufvideo_b200 import _cabi
+    n, k, tail_words = 3584, 3584, 37
+    x = (torch.randn((max(m, 1), k), device=dev) * 0.05).bfloat16()[:m]
+    w = (torch.randn((n, k), device=dev) * 0.03).bfloat16()
+    b = (torch.randn((n,), device=dev) * 0.03).bfloat16()
+    copies = [torch.zeros((m + 8, n), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    tails = [torch.zeros(tail_words, dtype=torch.int32, device=dev) for _ in range(2)]
+    flags = torch.zeros(2, dtype=torch.int32, device=dev)
+    tail_src = torch.arange(1, tail_words + 1, dtype=torch.int32, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    a = _cabi.PeerArgs()
+    for i in range(2):
+        a.dst[i], a.tail_dst[i], a.flag[i] = copies[i].data_ptr(), tails[i].data_ptr(), flags.data_ptr() + 4 * i
+    a.tail_src, a.ticket, a.tail_words, a.n_dst, a.multimem, a.flag_value = (
+        tail_src.data_ptr(), ticket.data_ptr(), tail_words, 2, 0, 7)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    lib = _cabi.lib()
+    for rep in range(2):                                     # twice: the ticket must have reset itself
+        a.flag_value = 7 + rep
+        _cabi.check(lib.ufv_linear_gather(x.data_ptr(), w.data_ptr(), b.data_ptr(), m, n, k, _cabi.UFV_BF16,
+                                          ctypes.byref(a), stream))
+        _cabi.check(lib.ufv_wait_flags(flags.data_ptr(), 2, 7 + rep, 500, timed_out.data_ptr(), stream))
+        torch.cuda.synchronize()
+        assert int(timed_out.item()) == 0 and flags.tolist() == [7 + rep] * 2 and int(ticket.item()) == 0
+        want = layer.linear(x, w, b) if m else x.new_zeros((0, n))
+        for c, tl in zip(copies, tails):
+            assert torch.equal(c[:m], want) and not c[m:].any()
+            assert torch.equal(tl, tail_src)
+    _cabi.check(lib.ufv_wait_flags(flags.data_ptr(), 2, 99, 50, timed_out.data_ptr(), stream))   # never arrives
+    torch.cuda.synchronize()
+    assert int(timed_out.item()) == 1
+
+
+def test_kernels_write_straight_into_the_gather_payload(dev):
+    """forward_padded(out=, counts_out=) + sharding.unpack_padded == forward(), including an object
+    that ties down to fewer tokens than its reserved slots."""
+    from ufvideo_b200 import sharding
+    feats = synth.features(21, 8)
+    feats[3:6] = feats[3]
+    masks = np.concatenate([synth.masks_blob(22, 1, 8, 60, 60), np.ones((3, 60, 60), np.uint8),
+                            synth.masks_blob(23, 1, 6, 60, 60)])
+    ann = [[list(range(8)), [3, 4, 5], [0, 1, 2, 5, 6, 7]]]
+    enc = make_encoder(dev, "bf16", 2)
+    ft = torch.from_numpy(feats).to(dev).bfloat16()
+    md = [torch.from_numpy(masks).to(dev)]
+    want_tokens, want_counts = enc(ft, md, None, ann, None)
+    slots = enc.last_plan.slots
+    payload, tok_view, cnt_view = sharding.new_payload(slots, 16, 5, 3584, torch.bfloat16, dev)
+    tokens, counts, plan = enc.forward_padded(ft, md, ann, out=tok_view, counts_out=cnt_view)
+    assert tokens.data_ptr() == payload.data_ptr() and counts.tolist() == want_counts == [2, 1, 2]
+    torch.cuda.synchronize()
+    got_tokens, got_counts = sharding.unpack_padded(payload[None], 16, 5)
+    assert got_counts == want_counts and torch.equal(got_tokens, want_tokens)
+
+
 def test_long_objects_spread_over_many_ctas(dev):
     """T = 300 and T = 40 in one batch (K = 8): similarity and merge kernels index by (object, pair/slot)."""
     g = synth.rng_for(77)

@@ -48,6 +48,19 @@ def _worker(rank, world, port, n_clips, result_dir):
         gathered = sharding.all_gather_tokens(tokens, torch.tensor(counts, dtype=torch.int32),
                                               pad_rows=pad_clips * objs * k, pad_objs=pad_clips * objs)
         all_tokens, all_counts = sharding.unpack_payloads(gathered, pad_clips * objs * k)
+        # the zero-copy variant: "kernels" write padded rows and counts straight into the payload
+        slots = np.full(len(counts), k, np.int32)
+        payload, tok_view, cnt_view = sharding.new_payload(slots, pad_clips * objs * k, pad_clips * objs, hid,
+                                                           torch.float32, torch.device("cpu"))
+        tok_view.zero_()
+        off = 0
+        for row, n in zip(rows, counts):
+            tok_view[off:off + n] = row
+            off += k
+        cnt_view.copy_(torch.tensor(counts, dtype=torch.int32))
+        g2, _ = sharding.all_gather_payload(payload)
+        padded_tokens, padded_counts = sharding.unpack_padded(g2, pad_clips * objs * k, pad_clips * objs)
+        assert padded_counts == all_counts and torch.equal(padded_tokens, all_tokens)
         torch.save((all_tokens, all_counts), os.path.join(result_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()

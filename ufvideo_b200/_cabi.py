@@ -21,11 +21,23 @@ BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8
 PLAN_PITCH = 736
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _p = C.c_void_p
 _i32 = C.c_int32
 _i64 = C.c_int64
+
+
+MAX_PEER_DST = 8
+
+
+class PeerArgs(C.Structure):
+    """Mirror of ``struct ufv_peer_args`` (include/ufv_b200.h)."""
+    _fields_ = [
+        ("dst", C.c_uint64 * MAX_PEER_DST), ("tail_dst", C.c_uint64 * MAX_PEER_DST),
+        ("flag", C.c_uint64 * MAX_PEER_DST), ("tail_src", _p), ("ticket", _p),
+        ("tail_words", _i32), ("n_dst", _i32), ("multimem", _i32), ("flag_value", _i32),
+    ]
 
 
 class EncodeArgs(C.Structure):
@@ -45,7 +57,7 @@ class EncodeArgs(C.Structure):
         ("merged", _p), ("counts", _p), ("sims", _p), ("sims_pitch", _i32), ("reserved0", _i32),
         ("counts_host", _p), ("epoch", _i32), ("reserved", _i32),
         ("w1", _p), ("b1", _p), ("w2", _p), ("b2", _p),
-        ("hidden", _p), ("tokens_out", _p),
+        ("hidden", _p), ("tokens_out", _p), ("peer", C.POINTER(PeerArgs)),
     ]
 
 
@@ -61,6 +73,8 @@ _SIGNATURES = {
     "ufv_ttm": (C.c_int, [_p, C.c_int, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p,
                           _p, C.c_int, _p, C.c_int, _p, _i32, _p]),
     "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "ufv_linear_gather": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PeerArgs), _p]),
+    "ufv_wait_flags": (C.c_int, [_p, C.c_int, _i32, C.c_int, _p, _p]),
     "ufv_encode": (C.c_int, [C.POINTER(EncodeArgs), _p]),
     "ufv_compact_rows": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int, _p]),
     "ufv_gather_rows": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p]),

@@ -133,9 +133,14 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
                a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, a->sims, a->sims_pitch,
                a->counts_host, a->epoch, stream);
   if (rc != 0) return rc;
-  if (a->m_pad == 0) return 0;
+  if (a->m_pad == 0)
+    return a->peer != nullptr
+               ? ufv_linear_gather(nullptr, nullptr, nullptr, 0, a->hid, a->hid, a->feat_dtype, a->peer, stream)
+               : 0;
   rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, stream);
   if (rc != 0) return rc;
+  if (a->peer != nullptr)   // last Linear fused with the all-gather: tiles go straight to every rank
+    return ufv_linear_gather(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, stream);
   return ufv_linear(a->hidden, a->w2, a->b2, a->tokens_out, a->m_pad, a->hid, a->hid, a->feat_dtype, 0,
                     stream);
 }

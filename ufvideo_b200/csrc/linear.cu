@@ -119,11 +119,36 @@ __device__ __forceinline__ void tile_origin(int tile, int tiles_m, int tiles_n, 
 // Persistent: grid = min(tiles, SMs); CTA b takes tiles b, b + grid, ...  Three pipelines: the shared-memory stage
 // ring (TMA -> MMA), the two TMEM accumulators (MMA -> epilogue: the epilogue of tile i overlaps
 // the main loop of tile i + 1), and the tile loop itself.
-template <typename T, int BN, bool GELU>
+// ---- stores of the fused all-gather variant ----------------------------------------------------------
+__device__ __forceinline__ void st_multimem_v4(uint64_t addr, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr),
+               "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+               "f"(__uint_as_float(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void st_multimem_u32(uint64_t addr, uint32_t v) {
+  asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(uint64_t addr, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_multimem_release_u32(uint64_t addr, uint32_t v) {
+  asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+// 16 bytes at byte offset `off` of this rank's rows in every destination copy
+__device__ __forceinline__ void peer_store16(const ufv_peer_args& peer, size_t off, uint4 v) {
+  if (peer.multimem) {
+    st_multimem_v4(peer.dst[0] + off, v);
+  } else {
+    for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint4*>(peer.dst[d] + off) = v;
+  }
+}
+
+template <typename T, int BN, bool GELU, bool PEER>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k, int tiles_m,
-                 int n_tiles) {
+                 int n_tiles, const __grid_constant__ ufv_peer_args peer) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t dyn_smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 1023) &
@@ -249,12 +274,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 packed[i >> 1] = Pack8<T>::two(a, b);
               }
             }
-            T* dst = y + size_t(row) * n + gcol;
+            if (PEER) {                  // fused all-gather: the tile goes to every rank's gathered buffer
+              const size_t off = (size_t(row) * n + gcol) * sizeof(T);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<uint4*>(dst)[i] =
-                  make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-          } else {                       // ragged right edge (n % 32 != 0)
+              for (int i = 0; i < 4; ++i)
+                peer_store16(peer, off + 16 * i,
+                             make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]));
+            } else {
+              T* dst = y + size_t(row) * n + gcol;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<uint4*>(dst)[i] =
+                    make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            }
+          } else if (!PEER) {            // ragged right edge (n % 32 != 0); the gather variant requires n % 32 == 0
             T* dst = y + size_t(row) * n + gcol;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -272,9 +305,84 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) mbar_arrive(&acc_empty[acc]);   // this warp's share of the accumulator is in registers / stored
     }
   }
+  if (PEER) __threadfence_system();        // this thread's remote stores are ordered before the ticket below
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (PEER) {
+    // The CTA that finishes last forwards the tail (reserved rows + token counts) and then raises this
+    // rank's arrival flag in every destination: flag == flag_value  =>  every byte of the call landed.
+    __shared__ int s_is_last;
+    if (threadIdx.x == 0) s_is_last = (atomicAdd(peer.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_is_last) {
+      __threadfence();
+      for (int wi = threadIdx.x; wi < peer.tail_words; wi += kGemmThreads) {
+        const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(peer.tail_src) + wi);
+        if (peer.multimem) {
+          st_multimem_u32(peer.tail_dst[0] + 4ull * wi, v);
+        } else {
+          for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint32_t*>(peer.tail_dst[d] + 4ull * wi) = v;
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (peer.multimem) {
+          st_multimem_release_u32(peer.flag[0], uint32_t(peer.flag_value));
+        } else {
+          for (int d = 0; d < peer.n_dst; ++d) st_release_sys_u32(peer.flag[d], uint32_t(peer.flag_value));
+        }
+        *peer.ticket = 0u;                 // self-reset for the next call
+      }
+    }
+  }
+}
+
+// an empty shard (no token rows) still has to forward its tail and raise its flag
+__global__ void peer_tail_only_kernel(const __grid_constant__ ufv_peer_args peer) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int wi = threadIdx.x; wi < peer.tail_words; wi += blockDim.x) {
+    const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(peer.tail_src) + wi);
+    if (peer.multimem) {
+      st_multimem_u32(peer.tail_dst[0] + 4ull * wi, v);
+    } else {
+      for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint32_t*>(peer.tail_dst[d] + 4ull * wi) = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (peer.multimem) {
+      st_multimem_release_u32(peer.flag[0], uint32_t(peer.flag_value));
+    } else {
+      for (int d = 0; d < peer.n_dst; ++d) st_release_sys_u32(peer.flag[d], uint32_t(peer.flag_value));
+    }
+  }
+}
+
+// ---- receiver side of the fused all-gather: spin until every rank's flag carries `value` ------------
+__global__ void wait_flags_kernel(const int32_t* __restrict__ flags, int n, int32_t value, long long timeout_ns,
+                                  int32_t* __restrict__ timed_out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    int32_t v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+    if (v == value) return;
+    __nanosleep(200);
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) {
+      if (timed_out != nullptr) *timed_out = 1;
+      return;
+    }
+  }
 }
 
 static int sm_count() {
@@ -290,7 +398,7 @@ static int sm_count() {
 
 template <typename T, int BN>
 static int launch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                     int gelu, cudaStream_t stream) {
+                     int gelu, const ufv_peer_args* peer, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tx, tw;
   int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
@@ -300,15 +408,20 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
   const int tiles_m = (m + kBM - 1) / kBM;
   const int n_tiles = tiles_m * ((n + BN - 1) / BN);
   const dim3 grid(n_tiles < sm_count() ? n_tiles : sm_count());
-  auto kernel = gelu ? linear_tc_kernel<T, BN, true> : linear_tc_kernel<T, BN, false>;
-  static bool configured[2] = {false, false};   // idempotent attribute; a benign race sets it twice
-  if (!configured[gelu ? 1 : 0]) {
+  const int variant = peer != nullptr ? 2 : gelu ? 1 : 0;
+  auto kernel = variant == 2   ? linear_tc_kernel<T, BN, false, true>
+                : variant == 1 ? linear_tc_kernel<T, BN, true, false>
+                               : linear_tc_kernel<T, BN, false, false>;
+  static bool configured[3] = {false, false, false};   // idempotent attribute; a benign race sets it twice
+  if (!configured[variant]) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    configured[gelu ? 1 : 0] = true;
+    configured[variant] = true;
   }
+  static const ufv_peer_args no_peer = {};
   return check_launch("ufv_linear (tcgen05)",
                       launch_kernel(kernel, grid, dim3(kGemmThreads), Cfg::kSmem, stream, tx, tw,
-                                    static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles));
+                                    static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles,
+                                    peer != nullptr ? *peer : no_peer));
 }
 
 // N-tile choice.  A launch costs (waves over the SMs) x (time of one tile).  Tile times per 64-deep
@@ -339,12 +452,12 @@ static int choose_bn(int m, int n) {
 
 template <typename T>
 static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                       int gelu, cudaStream_t stream) {
+                       int gelu, const ufv_peer_args* peer, cudaStream_t stream) {
   switch (choose_bn(m, n)) {
-    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, stream);
-    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, stream);
-    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, stream);
-    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, stream);
+    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, stream);
+    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, stream);
+    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, peer, stream);
+    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, peer, stream);
   }
 }
 
@@ -423,6 +536,43 @@ extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* 
   }
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "ufv_linear: unsupported dtype %d", dtype);
   UFV_REQUIRE(k % 8 == 0 && n % 8 == 0, UFV_E_SHAPE, "ufv_linear: k=%d and n=%d must be multiples of 8", k, n);
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, st);
-  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, st);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, nullptr, st);
+  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, nullptr, st);
+}
+
+extern "C" int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int n, int k,
+                                 int dtype, const ufv_peer_args* peer, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(m >= 0 && n >= 1 && k >= 1, UFV_E_SHAPE, "ufv_linear_gather: m=%d n=%d k=%d", m, n, k);
+  UFV_REQUIRE(peer && (m == 0 || (x && w && bias)), UFV_E_NULL, "ufv_linear_gather: null pointer");
+  UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE,
+              "ufv_linear_gather: dtype %d (bf16 / fp16 only)", dtype);
+  UFV_REQUIRE(k % 8 == 0 && n % 32 == 0, UFV_E_SHAPE, "ufv_linear_gather: k=%d %% 8, n=%d %% 32 must be 0", k, n);
+  UFV_REQUIRE(peer->n_dst >= 1 && peer->n_dst <= UFV_MAX_PEER_DST && (!peer->multimem || peer->n_dst == 1),
+              UFV_E_SHAPE, "ufv_linear_gather: n_dst=%d multimem=%d", peer->n_dst, peer->multimem);
+  UFV_REQUIRE(peer->ticket != nullptr && (peer->tail_words == 0 || peer->tail_src != nullptr), UFV_E_NULL,
+              "ufv_linear_gather: ticket / tail_src is null");
+  for (int d = 0; d < peer->n_dst; ++d)
+    UFV_REQUIRE(peer->dst[d] != 0 && (peer->dst[d] & 15u) == 0 && peer->flag[d] != 0 &&
+                    (peer->tail_words == 0 || peer->tail_dst[d] != 0),
+                UFV_E_ALIGN, "ufv_linear_gather: destination %d is null or not 16-byte aligned", d);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (m == 0)
+    return check_launch("ufv_linear_gather (empty shard)",
+                        launch_kernel(peer_tail_only_kernel, dim3(1), dim3(256), 0, st, *peer));
+  UFV_REQUIRE(aligned16(x) && aligned16(w), UFV_E_ALIGN, "ufv_linear_gather: x / w must be 16-byte aligned");
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, st);
+  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, st);
+}
+
+extern "C" int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,
+                              void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(n >= 0 && n <= 1024, UFV_E_SHAPE, "ufv_wait_flags: n=%d", n);
+  if (n == 0) return 0;
+  UFV_REQUIRE(flags != nullptr, UFV_E_NULL, "ufv_wait_flags: flags is null");
+  const long long ns = (timeout_ms > 0 ? (long long)timeout_ms : 2000LL) * 1000000LL;
+  return check_launch("ufv_wait_flags",
+                      launch_kernel(wait_flags_kernel, dim3(1), dim3((n + 31) / 32 * 32), 0,
+                                    static_cast<cudaStream_t>(stream), flags, n, value, ns, timed_out));
 }

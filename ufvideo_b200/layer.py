@@ -214,9 +214,14 @@ class MaskExtractor(nn.Module):
     def _linears(self):
         return [m for m in self.feat_linear if isinstance(m, nn.Linear)]
 
-    def encode_padded(self, feats, masks, ann_indices):
+    def encode_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None):
         """Kernels 1-4 without the host read-back: returns (tokens [m_pad, hid], counts int32
         [n_obj] on the device, plan).  Row r of an object is valid iff r < counts[object].
+        ``out`` / ``counts_out`` let the projector and the merge kernel write straight into caller
+        memory (e.g. the all-gather payload of ``sharding.new_payload``): contiguous [m_pad, hid]
+        of the model dtype and int32 [n_obj] on the module's device.  ``peer`` (a ``_cabi.PeerArgs``
+        from ``sharding.PeerGather.begin``) fuses the result-collection all-gather into the last
+        Linear: its tiles are stored into every rank's gathered buffer and ``out`` is not written.
 
         Host work per call is kept to the plan lookup and ONE C call: the workspace, the argument
         struct and the pinned counts buffer live in the cached plan and are reused as long as the
@@ -254,13 +259,35 @@ class MaskExtractor(nn.Module):
         run = plan.run
         if run is None or run["sig"] != sig:
             run = plan.run = self._prepare_run(plan, sig, feats, linears, side, k_keep, device)
-        tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
+        if peer is not None and not two:
+            raise ValueError("peer gather needs the depth-2 projector path")
+        if out is None:
+            tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
+        else:
+            if (tuple(out.shape) != (m_pad, hid) or out.dtype != feats.dtype or out.device != device
+                    or not out.is_contiguous() or out.data_ptr() % 16):
+                raise ValueError(f"out must be a contiguous, 16-byte aligned [{m_pad}, {hid}] {feats.dtype} tensor on {device}")
+            tokens = out
+        if counts_out is not None:
+            if (counts_out.numel() != plan.n_obj or counts_out.dtype != torch.int32 or counts_out.device != device
+                    or not counts_out.is_contiguous()):
+                raise ValueError(f"counts_out must be a contiguous int32 [{plan.n_obj}] tensor on {device}")
+            if not two:
+                raise ValueError("counts_out needs the depth-2 projector path")
         lib = _cabi.lib()
         ptr = run["ptr"]
         d = plan.dev
         if two:                                   # the reference's depth=2 projector: one chained call
             a = run["args"]
             a.tokens_out = tokens.data_ptr()
+            a.counts = ptr["counts"] if counts_out is None else counts_out.data_ptr()
+            if peer is None:
+                a.peer = None
+            else:
+                ref = getattr(peer, "_as_pointer", None)
+                if ref is None:
+                    ref = peer._as_pointer = ctypes.pointer(peer)
+                a.peer = ref
             a.epoch = plan.epoch = plan.epoch % 32767 + 1          # 1 .. 32767, the tag of this call's counts
             _cabi.check(lib.ufv_encode(run["args_ref"], stream))
         else:                                     # other depths: the same kernels, staged
@@ -278,7 +305,7 @@ class MaskExtractor(nn.Module):
             for i, lin in enumerate(linears):
                 x = linear(x, lin.weight, lin.bias, gelu=i < len(linears) - 1)
             tokens = x
-        counts = run["counts"]
+        counts = run["counts"] if counts_out is None else counts_out
         if self.keep_debug:
             view = run["view"]
             self._debug = {"bits": view("bits", torch.int32, (q, _cabi.BITS_WORDS)),
@@ -335,6 +362,15 @@ class MaskExtractor(nn.Module):
             run["args"] = a
             run["args_ref"] = ctypes.byref(a)
         return run
+
+    def forward_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None):
+        """forward() without the compaction: (tokens [m_pad, hidden] with object o's rows at
+        plan.host['slot_off'][o], region_token_nums as an int32 numpy array read back from the merge
+        kernel, plan).  What the clip-sharded driver gathers (sharding.all_gather_payload)."""
+        tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, out, counts_out, peer)
+        if plan.run.get("args") is not None and plan.n_obj > 0:
+            return tokens, _await_counts(plan, tokens.device), plan
+        return tokens, counts.cpu().numpy(), plan
 
     # -- the reference's forward -----------------------------------------------------------------
     def forward(self, feats, masks, X_features, ann_indices, frame_nums):

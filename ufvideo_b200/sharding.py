@@ -8,9 +8,13 @@ tensor, with the int32 token counts riding in the tail rows of the same buffer.
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import _cabi
 
 
 def clip_block(n_clips: int, rank: int, world: int) -> range:
@@ -64,3 +68,189 @@ def all_gather_tokens(tokens: torch.Tensor, counts: torch.Tensor, pad_rows: int,
     out = torch.empty((world * rows, hid), dtype=payload.dtype, device=payload.device)
     dist.all_gather_into_tensor(out, payload, group=group)     # concatenated along dim 0
     return out.view(world, rows, hid)
+
+
+# ------------------------------------------------------------------------------------------------
+# zero-copy variant: the kernels write straight into the payload
+# ------------------------------------------------------------------------------------------------
+# Payload of one rank, [pad_rows + tail, hid] of the model dtype:
+#   rows [0, m_pad)        padded object tokens, object o at slot_off[o] (written by the projector)
+#   tail, viewed as int32  [m_pad, n_obj, slots[pad_objs], counts[pad_objs]]
+#                          slots = min(T_o, K) rows reserved per object (static per batch structure),
+#                          counts = tokens actually produced (written by the merge kernel)
+# Nothing is packed or copied on the way: the all-gather sends what the kernels produced.
+_static_tail_cache: dict = {}
+
+
+def _padded_tail_rows(pad_objs: int, row_bytes: int) -> int:
+    return -(-(4 * (2 + 2 * pad_objs)) // row_bytes)
+
+
+def new_payload(slots, pad_rows: int, pad_objs: int, hid: int, dtype, device):
+    """Allocate one payload.  ``slots`` = plan.slots (int32 numpy, rows reserved per object).
+    Returns (payload, tokens_view [m_pad, hid], counts_view int32 [n_obj])."""
+    n_obj = int(len(slots))
+    m_pad = int(slots.sum()) if n_obj else 0
+    if m_pad > pad_rows or n_obj > pad_objs:
+        raise ValueError(f"payload overflow: {m_pad} rows / {n_obj} objects > pad {pad_rows} / {pad_objs}")
+    es = torch.empty((), dtype=dtype).element_size()
+    tail = _padded_tail_rows(pad_objs, hid * es)
+    payload = torch.empty((pad_rows + tail, hid), dtype=dtype, device=device)
+    meta = payload[pad_rows:].view(torch.int32).reshape(-1)
+    key = (slots.tobytes(), pad_objs, str(device))
+    static = _static_tail_cache.get(key)
+    if static is None:
+        host = np.zeros(2 + pad_objs, dtype=np.int32)
+        host[0], host[1] = m_pad, n_obj
+        host[2:2 + n_obj] = slots
+        static = torch.from_numpy(host).to(device)
+        if len(_static_tail_cache) > 64:
+            _static_tail_cache.clear()
+        _static_tail_cache[key] = static
+    meta[:2 + pad_objs].copy_(static, non_blocking=True)
+    return payload, payload[:m_pad], meta[2 + pad_objs:2 + pad_objs + n_obj]
+
+
+def all_gather_payload(payload: torch.Tensor, group=None, async_op: bool = False):
+    """THE collective: one all-gather of every rank's payload.  Returns (gathered [world, rows, hid],
+    work handle or None)."""
+    world = dist.get_world_size(group)
+    rows, hid = payload.shape
+    out = torch.empty((world * rows, hid), dtype=payload.dtype, device=payload.device)
+    work = dist.all_gather_into_tensor(out, payload, group=group, async_op=async_op)
+    return out.view(world, rows, hid), work
+
+
+def unpack_padded(gathered: torch.Tensor, pad_rows: int, pad_objs: int):
+    """gathered [world, pad_rows + tail, hid] -> (tokens [sum counts, hid] in global clip order,
+    counts list[int]).  Host-side; drops the zero-filled slots that merge ties left."""
+    world = gathered.shape[0]
+    meta = gathered[:, pad_rows:].reshape(world, -1).view(torch.int32).cpu().numpy()
+    rows, counts = [], []
+    for r in range(world):
+        n_obj = int(meta[r, 1])
+        slots = meta[r, 2:2 + n_obj]
+        cnt = meta[r, 2 + pad_objs:2 + pad_objs + n_obj]
+        off = 0
+        for s, c in zip(slots, cnt):
+            rows.append(gathered[r, off:off + int(c)])
+            off += int(s)
+        counts.extend(int(c) for c in cnt)
+    tokens = torch.cat(rows, dim=0) if rows else gathered.new_zeros((0, gathered.shape[2]))
+    return tokens, counts
+
+
+# ------------------------------------------------------------------------------------------------
+# the all-gather fused into the last Linear: tiles are stored into every rank's buffer over NVLink
+# ------------------------------------------------------------------------------------------------
+class PeerGather:
+    """Symmetric gathered buffers for ``ufv_linear_gather`` (include/ufv_b200.h).
+
+    Every rank owns ``ring`` copies of the gathered result, [world, pad_rows + tail, hid] each (same
+    payload layout as ``new_payload``), allocated as torch symmetric memory so that all ranks can
+    address them -- through the NVSwitch multicast alias when the fabric has one (one
+    ``multimem.st`` reaches every rank), otherwise through one mapped pointer per peer.  A step:
+
+        peer, tokens_view, counts_view, step = pg.begin(plan.slots)
+        enc.forward_padded(feats, masks, ann, out=tokens_view, counts_out=counts_view, peer=peer)
+        ...                       # next steps may be issued; nothing here blocks the host
+        pg.wait(step)             # stream-ordered: all ranks' rows of `step` have landed
+        gathered = pg.gathered(step)
+
+    Flow control: ``begin(s)`` makes the stream wait for every rank's arrival flag of step
+    ``s - ring + 2``; a rank therefore never overwrites a copy that some rank may still read, as
+    long as ``gathered(t)`` is consumed (in stream order) before that rank's ``begin(t + 2)``.
+    torch.distributed is used for the rendezvous only; no collective runs on the data path.
+    """
+
+    def __init__(self, pad_rows: int, pad_objs: int, hid: int, dtype, device, group=None, ring: int = 4,
+                 use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm
+
+        if ring < 3:
+            raise ValueError("ring must be >= 3")
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _cabi.MAX_PEER_DST:
+            raise ValueError(f"at most {_cabi.MAX_PEER_DST} ranks")
+        self.pad_rows, self.pad_objs, self.hid, self.ring, self.device = pad_rows, pad_objs, hid, ring, device
+        self.es = torch.empty((), dtype=dtype).element_size()
+        self.rows = pad_rows + _padded_tail_rows(pad_objs, hid * self.es)
+        self.tail_words = 2 + 2 * pad_objs
+        self.buf = symm.empty((ring, self.world, self.rows, hid), dtype=dtype, device=device)
+        self.flags = symm.empty((ring, self.world), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        torch.cuda.synchronize(device)
+        self.buf_h = symm.rendezvous(self.buf, group)
+        self.flag_h = symm.rendezvous(self.flags, group)
+        self.flag_h.barrier()
+        self.multimem = bool(use_multicast and self.buf_h.has_multicast_support
+                             and self.flag_h.has_multicast_support and self.buf_h.multicast_ptr
+                             and self.flag_h.multicast_ptr)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
+        self.step = 0
+        self._wait_fn = _cabi.lib().ufv_wait_flags
+        self._flags_ptr, self._timed_out_ptr = self.flags.data_ptr(), self.timed_out.data_ptr()
+        self._static = {}                         # slot -> (slots bytes, tokens view, counts view)
+        self._args = [self._make_args(s) for s in range(ring)]
+
+    def _row_bytes(self):
+        return self.hid * self.es
+
+    def _make_args(self, slot: int) -> _cabi.PeerArgs:
+        a = _cabi.PeerArgs()
+        off = (slot * self.world + self.rank) * self.rows * self._row_bytes()
+        tail_off = off + self.pad_rows * self._row_bytes()
+        flag_off = (slot * self.world + self.rank) * 4
+        if self.multimem:
+            bases, flag_bases = [self.buf_h.multicast_ptr], [self.flag_h.multicast_ptr]
+        else:
+            bases, flag_bases = list(self.buf_h.buffer_ptrs), list(self.flag_h.buffer_ptrs)
+        for i, (b, f) in enumerate(zip(bases, flag_bases)):
+            a.dst[i], a.tail_dst[i], a.flag[i] = b + off, b + tail_off, f + flag_off
+        a.n_dst, a.multimem = len(bases), int(self.multimem)
+        a.tail_src = self.buf.data_ptr() + tail_off
+        a.ticket = self.ticket.data_ptr()
+        a.tail_words = self.tail_words
+        return a
+
+    def begin(self, slots: np.ndarray):
+        """Start a step.  Returns (peer args, local tokens view [m_pad, hid], counts view int32 [n_obj], step)."""
+        step, slot = self.step, self.step % self.ring
+        self.step += 1
+        if step >= self.ring - 2:
+            self.wait(step - (self.ring - 2))
+        key = slots.tobytes()
+        cached = self._static.get(slot)
+        if cached is None or cached[0] != key:   # views + the static tail part: once per (slot, batch structure)
+            n_obj = int(len(slots))
+            m_pad = int(slots.sum()) if n_obj else 0
+            if m_pad > self.pad_rows or n_obj > self.pad_objs:
+                raise ValueError(f"payload overflow: {m_pad} rows / {n_obj} objects > pad {self.pad_rows} / {self.pad_objs}")
+            mine = self.buf[slot, self.rank]
+            meta = mine[self.pad_rows:].view(torch.int32).reshape(-1)
+            host = np.zeros(2 + self.pad_objs, dtype=np.int32)
+            host[0], host[1] = m_pad, n_obj
+            host[2:2 + n_obj] = slots            # reserved rows per object: static per batch structure
+            meta[:2 + self.pad_objs].copy_(torch.from_numpy(host).to(self.device), non_blocking=True)
+            cached = self._static[slot] = (key, mine[:m_pad], meta[2 + self.pad_objs:2 + self.pad_objs + n_obj])
+        a = self._args[slot]
+        a.flag_value = step + 1
+        return a, cached[1], cached[2], step
+
+    def wait(self, step: int) -> None:
+        """Make the current stream wait until every rank's rows of ``step`` are in this rank's copy."""
+        slot = step % self.ring
+        rc = self._wait_fn(self._flags_ptr + slot * self.world * 4, self.world, step + 1, 0, self._timed_out_ptr,
+                           torch._C._cuda_getCurrentRawStream(self.device.index))
+        if rc:
+            _cabi.check(rc)
+
+    def gathered(self, step: int) -> torch.Tensor:
+        """This rank's copy of the gathered result of ``step``: [world, pad_rows + tail, hid]."""
+        return self.buf[step % self.ring]
+
+    def check(self) -> None:
+        if int(self.timed_out.item()):
+            raise RuntimeError("PeerGather: timed out waiting for a peer's arrival flag")
