@@ -157,18 +157,21 @@ class PeerGather:
         pg.wait(step)             # stream-ordered: all ranks' rows of `step` have landed
         gathered = pg.gathered(step)
 
-    Flow control: ``begin(s)`` makes the stream wait for every rank's arrival flag of step
-    ``s - ring + 2``; a rank therefore never overwrites a copy that some rank may still read, as
-    long as ``gathered(t)`` is consumed (in stream order) before that rank's ``begin(t + 2)``.
+    Flow control: step t may overwrite its ring slot once every rank has raised the flag of step
+    ``t - ring + 2`` (whoever raised it has, in stream order, finished reading ``gathered`` of
+    anything older than that).  ``begin(s)`` issues the stream-side wait only every ``ring / 2`` steps,
+    on the flags of step ``s - 2``, which covers the following ``ring / 2`` steps.  Contract for the
+    caller: consume ``gathered(t)`` (in stream order) before this rank's ``begin(t + 2)``.
     torch.distributed is used for the rendezvous only; no collective runs on the data path.
     """
 
-    def __init__(self, pad_rows: int, pad_objs: int, hid: int, dtype, device, group=None, ring: int = 4,
+    def __init__(self, pad_rows: int, pad_objs: int, hid: int, dtype, device, group=None, ring: int = 8,
                  use_multicast: bool = True):
         import torch.distributed._symmetric_memory as symm
 
-        if ring < 3:
-            raise ValueError("ring must be >= 3")
+        if ring < 4 or ring % 2:
+            raise ValueError("ring must be even and >= 4")
+        self.check_every = ring // 2              # flow-control waits are issued every ring / 2 steps
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > _cabi.MAX_PEER_DST:
@@ -219,8 +222,8 @@ class PeerGather:
         """Start a step.  Returns (peer args, local tokens view [m_pad, hid], counts view int32 [n_obj], step)."""
         step, slot = self.step, self.step % self.ring
         self.step += 1
-        if step >= self.ring - 2:
-            self.wait(step - (self.ring - 2))
+        if step >= 2 and step % self.check_every == 0:
+            self.wait(step - 2)
         key = slots.tobytes()
         cached = self._static.get(slot)
         if cached is None or cached[0] != key:   # views + the static tail part: once per (slot, batch structure)
