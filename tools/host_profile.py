@@ -45,5 +45,54 @@ def main():
     st.sort_stats("cumulative").print_stats(25)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("UFV_FINE"):
     main()
+
+
+def fine_grained():
+    """perf_counter around the pieces of one forward() (no profiler overhead)."""
+    import ctypes
+    from ufvideo_b200 import _cabi, packer, layer
+    dev = torch.device("cuda:0")
+    feats, masks, ann = synth.make_batch(8, 16, 4, "dense")
+    ft = torch.from_numpy(feats).to(dev).bfloat16()
+    md = [torch.from_numpy(m).to(dev).float() for m in masks]
+    enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
+    enc.region_token_num = 8
+    enc = enc.to(dev).bfloat16()
+    for _ in range(10):
+        enc(ft, md, None, ann, None)
+    torch.cuda.synchronize()
+    n = 300
+    acc = {"build_plan": 0.0, "ufv_encode (C)": 0.0, "encode_padded total": 0.0, "await counts": 0.0, "forward total": 0.0}
+    lib = _cabi.lib()
+    for _ in range(n):
+        t0 = time.perf_counter()
+        plan = packer.build_plan(md, ann, ft.shape[0], 8, dev)
+        t1 = time.perf_counter()
+        acc["build_plan"] += t1 - t0
+        torch.cuda.synchronize()
+        run = plan.run
+        t0 = time.perf_counter()
+        _cabi.check(lib.ufv_encode(run["args_ref"], torch._C._cuda_getCurrentRawStream(0)))
+        t1 = time.perf_counter()
+        acc["ufv_encode (C)"] += t1 - t0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tokens, counts, plan = enc.encode_padded(ft, md, ann)
+        t1 = time.perf_counter()
+        layer._await_counts(plan, dev)
+        t2 = time.perf_counter()
+        acc["encode_padded total"] += t1 - t0
+        acc["await counts"] += t2 - t1
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        enc(ft, md, None, ann, None)
+        acc["forward total"] += time.perf_counter() - t0
+        torch.cuda.synchronize()
+    for k, v in acc.items():
+        print(f"{k:24s} {v / n * 1e6:8.1f} us")
+
+
+if __name__ == "__main__" and os.environ.get("UFV_FINE"):
+    fine_grained()

@@ -20,6 +20,7 @@ from ufvideo_b200 import build_region_encoder, layer, packer, synth  # noqa: E40
 
 CONFIGS = {
     # name: (clips, frames, objects, family, ragged, note)
+    "c1": (1, 16, 1, "dense", False, "configs[0]: 1 clip x 16 frames x 1 object, fp32 (the reference's CPU-runnable case)"),
     "c2": (8, 16, 4, "dense", False, "configs[1]: 8 clips x 16 frames x 4 objects"),
     "c2-blob": (8, 16, 4, "blob", False, "configs[1] shape, blob masks"),
     "c3": (8, 32, 8, "sparse", False, "configs[2] per-GPU share: 8 of 64 clips x 32 frames x 8 objects, sparse masks"),
@@ -45,21 +46,73 @@ def timed(fn, iters=20, warm=3):
     return t[len(t) // 2] * 1e3   # median, us
 
 
-def run(name, k=8):
+def baselines(name, feats, masks, ann, k, dt, enc, dev):
+    """The reference's own op sequence (oracle/reference_port.py, validated bit-identical to the real
+    module): on the host CPU (all cores, fp32, a bounded sample of the clips) and as CUDA eager on this GPU."""
+    import os
+    import time
+    from oracle import reference_port
+    out = {}
+    weights = [p.detach() for p in (enc.feat_linear[0].weight, enc.feat_linear[0].bias,
+                                    enc.feat_linear[2].weight, enc.feat_linear[2].bias)]
+    # CUDA eager, model dtype, full config (skipped when the three dense fp32 temporaries would not fit)
+    q = sum(m.shape[0] for m in masks)
+    q_max = max(m.shape[0] for m in masks)
+    if q_max * 729 * 1152 * 4 * 4 < 120e9:
+        ft = torch.from_numpy(feats).to(dev).to(dt)
+        mt = [torch.from_numpy(m).to(dev).float() for m in masks]
+        with torch.no_grad():
+            for _ in range(2):
+                reference_port.encode(ft, mt, ann, k, *weights)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n = 3
+            for _ in range(n):
+                reference_port.encode(ft, mt, ann, k, *weights)
+            torch.cuda.synchronize()
+            out["eager_cuda_obj_frames_per_s"] = q * n / (time.perf_counter() - t0)
+        del ft, mt
+        torch.cuda.empty_cache()
+    # host CPU, fp32, first clip(s) only
+    n_clips = 1 if q / len(masks) >= 256 else min(2, len(masks))
+    frames_per_clip = feats.shape[0] // len(masks)
+    cf = torch.from_numpy(feats[: n_clips * frames_per_clip])
+    cm = [torch.from_numpy(m).float() for m in masks[:n_clips]]
+    ca = ann[:n_clips]
+    cw = [w.float().cpu() for w in weights]
+    torch.set_num_threads(os.cpu_count() or 1)
+    qs = sum(m.shape[0] for m in cm)
+    if qs * 729 * 1152 * 4 * 4 < 60e9:
+        with torch.no_grad():
+            reference_port.encode(cf, cm, ca, k, *cw)
+            t0 = time.perf_counter()
+            n = 0
+            while n < 2 or time.perf_counter() - t0 < 3.0:
+                reference_port.encode(cf, cm, ca, k, *cw)
+                n += 1
+            out["cpu_obj_frames_per_s"] = qs * n / (time.perf_counter() - t0)
+            out["cpu_cores"] = os.cpu_count()
+            out["cpu_sample"] = f"{n_clips} clip(s), {qs} object-frames, fp32"
+    return out
+
+
+def run(name, k=8, with_baselines=False):
     clips, frames, objects, family, ragged, note = CONFIGS[name]
     dev = torch.device("cuda:0")
+    dt = torch.float32 if name == "c1" else torch.bfloat16
     feats, masks, ann = synth.make_batch(clips, frames, objects, family, ragged=ragged)
-    ft = torch.from_numpy(feats).to(dev).bfloat16()
-    del feats
+    ft = torch.from_numpy(feats).to(dev).to(dt)
     md = [torch.from_numpy(m).to(dev) for m in masks]          # uint8
     enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
     enc.region_token_num = k
-    enc = enc.to(dev).bfloat16()
+    enc = enc.to(dev).to(dt)
+    base = baselines(name, feats, masks, ann, k, dt, enc, dev) if with_baselines else {}
+    del feats
     plan = packer.build_plan(md, ann, ft.shape[0], k, dev)
     q = plan.n_masks
     patches = layer.mask_to_patches(plan, dev)
     pooled = layer.mask_pool(ft, plan, patches)
-    merged, counts, _ = layer.ttm(pooled, plan, k, torch.bfloat16)
+    merged, counts, _ = layer.ttm(pooled, plan, k, dt)
     l0, l2 = enc.feat_linear[0], enc.feat_linear[2]
     hid = layer.linear(merged, l0.weight, l0.bias, True)
     bits = patches["bits"].cpu().numpy().view(np.uint32)
@@ -68,14 +121,14 @@ def run(name, k=8):
     for g in range(plan.n_groups):
         u = np.bitwise_or.reduce(bits[gm[go[g]:go[g + 1]]], axis=0)
         union += int(np.unpackbits(u.view(np.uint8)).sum())
-    pool_bytes = union * 1152 * 2 + q * 1152 * 4
+    pool_bytes = union * 1152 * ft.element_size() + q * 1152 * 4
     res = {
         "config": name, "note": note, "object_frames": q, "frames": int(ft.shape[0]), "objects": plan.n_obj,
         "tokens": plan.m_pad, "groups": plan.n_groups, "max_len": plan.max_len,
         "union_patch_frac": union / (plan.n_groups * 729.0),
         "k1_us": timed(lambda: layer.mask_to_patches(plan, dev)),
         "k2_us": timed(lambda: layer.mask_pool(ft, plan, patches)),
-        "k3_us": timed(lambda: layer.ttm(pooled, plan, k, torch.bfloat16)),
+        "k3_us": timed(lambda: layer.ttm(pooled, plan, k, dt)),
         "k4a_us": timed(lambda: layer.linear(merged, l0.weight, l0.bias, True)),
         "k4b_us": timed(lambda: layer.linear(hid, l2.weight, l2.bias, False)),
         "forward_us": timed(lambda: enc(ft, md, None, ann, None)),
@@ -84,14 +137,17 @@ def run(name, k=8):
     res["pool_bytes"] = pool_bytes
     res["proj_tflops"] = 33947648.0 * plan.m_pad / (res["k4a_us"] + res["k4b_us"]) / 1e6
     res["object_frames_per_s"] = q / res["forward_us"] * 1e6
+    res.update(base)
     return res
 
 
 def main():
-    names = sys.argv[1:] or list(CONFIGS)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    with_baselines = "--baselines" in sys.argv
+    names = args or list(CONFIGS)
     out = []
     for n in names:
-        r = run(n)
+        r = run(n, with_baselines=with_baselines)
         out.append(r)
         print(json.dumps(r), flush=True)
         torch.cuda.empty_cache()
@@ -101,7 +157,9 @@ def main():
     for r in out:
         print(f"{r['config']:10s} {r['object_frames']:7d} {r['tokens']:6d} {r['k1_us']:7.1f} {r['k2_us']:8.1f} "
               f"{r['k3_us']:7.1f} {r['k4a_us']:6.1f} {r['k4b_us']:6.1f} {r['forward_us']:8.1f} "
-              f"{r['object_frames_per_s']:10.0f} {r['pool_gbs']:9.0f} {r['proj_tflops']:7.1f}")
+              f"{r['object_frames_per_s']:10.0f} {r['pool_gbs']:9.0f} {r['proj_tflops']:7.1f}"
+              + (f"   eager-CUDA {r['eager_cuda_obj_frames_per_s']:9.0f}/s" if "eager_cuda_obj_frames_per_s" in r else "")
+              + (f"   CPU({r.get('cpu_cores')}c) {r['cpu_obj_frames_per_s']:7.0f}/s" if "cpu_obj_frames_per_s" in r else ""))
 
 
 if __name__ == "__main__":
