@@ -240,6 +240,19 @@ int ufv_encode(const ufv_encode_args* args_host, void* stream);
 int ufv_compact_rows(const void* in, const int32_t* slot_off, const int32_t* counts, int n_obj,
                      void* out, int row_bytes, void* stream);
 
+/* <region> splice, the consumer of the path (videorefer_arch.py:300-311), on the device.
+ *   text [n_text, row]    embeddings of the flattened token sequence, one placeholder row per object
+ *   region_pos[n_obj]     row of object o's placeholder in `text`, strictly ascending
+ *   tokens [m_pad, row]   padded object tokens (object o at slot_off[o]), counts[n_obj] on the device
+ *   out                   the sequence with placeholder o replaced by object o's counts[o] rows; must
+ *                         hold n_text - n_obj + m_pad rows; *out_len (optional) = rows actually written
+ *   row_src (optional)    int32 per output row: text row index, or -(token row + 1)
+ * Driven by the device-side counts, so inputs_embeds can be built without the host copy of
+ * region_token_nums. */
+int ufv_splice_rows(const void* text, int n_text, const int32_t* region_pos, const void* tokens,
+                    const int32_t* slot_off, const int32_t* counts, int n_obj, int m_pad, void* out,
+                    int32_t* out_len, int32_t* row_src, int row_bytes, void* stream);
+
 /* Gather rows: out[i, :] = in[row_map[i], :], `row_bytes` per row (multiple of 16). */
 int ufv_gather_rows(const void* in, const int32_t* row_map, void* out, int n_out_rows,
                     int row_bytes, void* stream);

@@ -429,6 +429,40 @@ def test_kernels_write_straight_into_the_gather_payload(dev):
     assert got_counts == want_counts and torch.equal(got_tokens, want_tokens)
 
 
+def test_region_splice_matches_the_reference_consumer_loop(dev):
+    """splice_regions == the python loop of videorefer_arch.py:300-311 (text pieces and object tokens
+    concatenated at the <region> placeholders), with one object tied down to fewer tokens."""
+    feats = synth.features(31, 8)
+    feats[3:6] = feats[3]
+    masks = np.concatenate([synth.masks_blob(32, 1, 8, 60, 60), np.ones((3, 60, 60), np.uint8),
+                            synth.masks_blob(33, 1, 6, 60, 60)])
+    ann = [[list(range(8)), [3, 4, 5], [0, 1, 2, 5, 6, 7]]]
+    enc = make_encoder(dev, "bf16", 2)
+    ft = torch.from_numpy(feats).to(dev).bfloat16()
+    md = [torch.from_numpy(masks).to(dev)]
+    flat_tokens, nums = enc(ft, md, None, ann, None)                       # the reference contract
+    assert nums == [2, 1, 2]
+    tokens, counts, plan = enc.encode_padded(ft, md, ann)                   # padded rows + device counts
+    n_text = 23
+    text = torch.randn((n_text, 3584), device=dev).bfloat16()
+    pos = [2, 3, 20]                                                        # adjacent placeholders, one near the end
+    out, out_len, row_src = layer.splice_regions(text, torch.tensor(pos, dtype=torch.int32, device=dev),
+                                                 tokens, counts, plan, want_row_src=True)
+    pieces, cur, prev = [], 0, 0
+    for p_, n_ in zip(pos, nums):                                           # videorefer_arch.py:300-311
+        pieces.append(text[prev:p_])
+        pieces.append(flat_tokens[cur:cur + n_])
+        cur += n_
+        prev = p_ + 1
+    pieces.append(text[prev:])
+    want = torch.cat(pieces)
+    n = int(out_len.item())
+    assert n == want.shape[0] == n_text - 3 + sum(nums)
+    assert torch.equal(out[:n], want)
+    src = row_src[:n].cpu().numpy()
+    assert (src[:2] == [0, 1]).all() and src[2] == -1 and src[-1] == n_text - 1
+
+
 def test_long_objects_spread_over_many_ctas(dev):
     """T = 300 and T = 40 in one batch (K = 8): similarity and merge kernels index by (object, pair/slot)."""
     g = synth.rng_for(77)

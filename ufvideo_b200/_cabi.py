@@ -77,6 +77,7 @@ _SIGNATURES = {
     "ufv_wait_flags": (C.c_int, [_p, C.c_int, _i32, C.c_int, _p, _p]),
     "ufv_encode": (C.c_int, [C.POINTER(EncodeArgs), _p]),
     "ufv_compact_rows": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int, _p]),
+    "ufv_splice_rows": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p]),
     "ufv_gather_rows": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p]),
 }
 EXPORTED = tuple(_SIGNATURES)

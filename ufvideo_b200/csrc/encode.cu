@@ -70,6 +70,75 @@ __global__ void compact_rows_kernel(const uint4* __restrict__ in, const int32_t*
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+// ---- <region> splice (the consumer of the path, videorefer_arch.py:300-311) ----------------------------
+// The flattened token sequence has one placeholder row per object (region_pos ascending); the output is
+// that sequence with placeholder o replaced by object o's counts[o] token rows.  One CTA per work item:
+// items [0, n_text) are text rows, items [n_text, n_text + m_pad) are padded token rows.  Where a row
+// lands depends on the counts of the objects before it, which live on the device -- so the caller never
+// needs the host copy of region_token_nums to build inputs_embeds.
+__device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int v) {   // first index with a[i] >= v
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void splice_rows_kernel(const uint4* __restrict__ text, int n_text, const int32_t* __restrict__ region_pos,
+                                   const uint4* __restrict__ tokens, const int32_t* __restrict__ slot_off,
+                                   const int32_t* __restrict__ counts, int n_obj, int m_pad, uint4* __restrict__ out,
+                                   int32_t* __restrict__ out_len, int32_t* __restrict__ row_src, int vec_per_row) {
+  __shared__ int s_part[32];
+  __shared__ int s_dst;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int item = blockIdx.x;
+  const uint4* src;
+  int n_before;          // objects whose placeholder precedes this row
+  int extra = 0;         // offset inside the object's own tokens
+  int tag;
+  bool live = true;
+  if (item < n_text) {
+    n_before = lower_bound_i32(region_pos, n_obj, item);
+    live = !(n_before < n_obj && region_pos[n_before] == item);   // placeholders themselves disappear
+    src = text + size_t(item) * vec_per_row;
+    tag = item;
+  } else {
+    const int r = item - n_text;
+    int o = lower_bound_i32(slot_off, n_obj, r + 1) - 1;           // last object with slot_off[o] <= r
+    live = o >= 0 && r - slot_off[o] < counts[o];
+    n_before = max(o, 0);
+    extra = o >= 0 ? r - slot_off[o] : 0;
+    src = tokens + size_t(r) * vec_per_row;
+    tag = -(r + 1);
+  }
+  // rows before this one: its own text position (or its placeholder's) + sum over earlier objects of (count - 1)
+  int shift = 0;
+  for (int i = threadIdx.x; i < n_before; i += blockDim.x) shift += counts[i] - 1;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) shift += __shfl_xor_sync(0xffffffffu, shift, off);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = shift;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) total += s_part[w];
+    const int base = item < n_text ? item : region_pos[n_before];
+    s_dst = base + total + extra;
+    if (item == 0 && out_len != nullptr) {     // total length: every placeholder turns into counts[o] rows
+      int len = n_text;
+      for (int i = 0; i < n_obj; ++i) len += counts[i] - 1;
+      *out_len = len;
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  const int dst = s_dst;
+  uint4* d = out + size_t(dst) * vec_per_row;
+  for (int i = threadIdx.x; i < vec_per_row; i += blockDim.x) d[i] = src[i];
+  if (threadIdx.x == 0 && row_src != nullptr) row_src[dst] = tag;
+}
+
 }  // namespace ufv
 
 extern "C" int ufv_abi_version(void) { return UFV_ABI_VERSION; }
@@ -115,6 +184,24 @@ extern "C" int ufv_compact_rows(const void* in, const int32_t* slot_off, const i
                       launch_kernel(compact_rows_kernel, dim3(n_obj), dim3(256), 0,
                                     static_cast<cudaStream_t>(stream), static_cast<const uint4*>(in), slot_off,
                                     counts, static_cast<uint4*>(out), row_bytes / 16));
+}
+
+extern "C" int ufv_splice_rows(const void* text, int n_text, const int32_t* region_pos, const void* tokens,
+                               const int32_t* slot_off, const int32_t* counts, int n_obj, int m_pad, void* out,
+                               int32_t* out_len, int32_t* row_src, int row_bytes, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(n_text >= 0 && n_obj >= 0 && m_pad >= 0 && row_bytes > 0 && row_bytes % 16 == 0, UFV_E_SHAPE,
+              "ufv_splice_rows: n_text=%d n_obj=%d m_pad=%d row_bytes=%d", n_text, n_obj, m_pad, row_bytes);
+  UFV_REQUIRE(n_obj <= n_text, UFV_E_SHAPE, "ufv_splice_rows: more placeholders (%d) than rows (%d)", n_obj, n_text);
+  if (n_text + m_pad == 0) return 0;
+  UFV_REQUIRE(out && (n_text == 0 || text) && (n_obj == 0 || (region_pos && slot_off && counts)) &&
+                  (m_pad == 0 || tokens), UFV_E_NULL, "ufv_splice_rows: null pointer");
+  UFV_REQUIRE(aligned16(text) && aligned16(tokens) && aligned16(out), UFV_E_ALIGN, "ufv_splice_rows: unaligned buffer");
+  return check_launch("ufv_splice_rows",
+                      launch_kernel(splice_rows_kernel, dim3(n_text + m_pad), dim3(128), 0,
+                                    static_cast<cudaStream_t>(stream), static_cast<const uint4*>(text), n_text,
+                                    region_pos, static_cast<const uint4*>(tokens), slot_off, counts, n_obj, m_pad,
+                                    static_cast<uint4*>(out), out_len, row_src, row_bytes / 16));
 }
 
 extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {

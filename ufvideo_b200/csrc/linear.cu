@@ -515,6 +515,58 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
 }
 
+// Few tokens (m <= 16): the Linear is a stream over the weights.  One warp per two output columns reads
+// their weight rows once with coalesced float4 loads and keeps all m x 2 dot products in registers; the
+// m token rows (<= 229 KB) come through L1/L2.  224 CTAs of 8 warps for n = 3584.
+constexpr int kSkinnyM = 16, kSkinnyCols = 2, kSkinnyWarps = 8;
+
+template <bool GELU>
+__global__ void __launch_bounds__(32 * kSkinnyWarps)
+linear_f32_skinny_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                         const float* __restrict__ bias, float* __restrict__ y, int m, int n, int k) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int col0 = (blockIdx.x * kSkinnyWarps + (threadIdx.x >> 5)) * kSkinnyCols;
+  if (col0 >= n) return;
+  float acc[kSkinnyM][kSkinnyCols];
+#pragma unroll
+  for (int r = 0; r < kSkinnyM; ++r)
+#pragma unroll
+    for (int c = 0; c < kSkinnyCols; ++c) acc[r][c] = 0.f;
+  const bool has2 = col0 + 1 < n;
+  const float* w0 = w + size_t(col0) * k;
+  const float* w1 = w + size_t(has2 ? col0 + 1 : col0) * k;
+  for (int k0 = lane * 4; k0 < k; k0 += 128) {       // k % 4 == 0 is checked by the caller
+    const float4 a = *reinterpret_cast<const float4*>(w0 + k0);
+    const float4 b = *reinterpret_cast<const float4*>(w1 + k0);
+#pragma unroll
+    for (int r = 0; r < kSkinnyM; ++r) {
+      if (r < m) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + size_t(r) * k + k0));
+        acc[r][0] = fmaf(v.x, a.x, fmaf(v.y, a.y, fmaf(v.z, a.z, fmaf(v.w, a.w, acc[r][0]))));
+        acc[r][1] = fmaf(v.x, b.x, fmaf(v.y, b.y, fmaf(v.z, b.z, fmaf(v.w, b.w, acc[r][1]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kSkinnyM; ++r) {
+    if (r < m) {
+#pragma unroll
+      for (int c = 0; c < kSkinnyCols; ++c) {
+        float v = acc[r][c];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0 && (c == 0 || has2)) {
+          v += bias[col0 + c];
+          if (GELU) v = gelu_erf(v);
+          y[size_t(r) * n + col0 + c] = v;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ufv
 
 extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
@@ -526,6 +578,14 @@ extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* 
   UFV_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), UFV_E_ALIGN,
               "ufv_linear: x / w / y must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == UFV_F32 && m <= kSkinnyM && k % 4 == 0) {
+    const int cols_per_cta = kSkinnyWarps * kSkinnyCols;
+    auto kernel = gelu ? linear_f32_skinny_kernel<true> : linear_f32_skinny_kernel<false>;
+    return check_launch("ufv_linear (fp32, skinny)",
+                        launch_kernel(kernel, dim3((n + cols_per_cta - 1) / cols_per_cta), dim3(32 * kSkinnyWarps), 0,
+                                      st, static_cast<const float*>(x), static_cast<const float*>(w),
+                                      static_cast<const float*>(bias), static_cast<float*>(y), m, n, k));
+  }
   if (dtype == UFV_F32) {
     const dim3 grid((n + kSBN - 1) / kSBN, (m + kSBM - 1) / kSBM);
     auto kernel = gelu ? linear_f32_kernel<true> : linear_f32_kernel<false>;

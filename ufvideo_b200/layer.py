@@ -147,6 +147,32 @@ def _await_counts(plan: packer.EncodePlan, device) -> np.ndarray:
                 raise RuntimeError("ufvideo_b200: the merge kernel finished without publishing its counts")
 
 
+def splice_regions(text_embeds: torch.Tensor, region_pos: torch.Tensor, tokens: torch.Tensor,
+                   counts: torch.Tensor, plan: packer.EncodePlan, want_row_src: bool = False):
+    """Device-side <region> splice (the consumer loop of videorefer_arch.py:300-311, flattened over
+    the batch): ``text_embeds`` [n_text, hid] holds one placeholder row per object at ``region_pos``
+    (int32, ascending, on the device); each is replaced by that object's tokens.  ``tokens`` /
+    ``counts`` / ``plan`` are what ``encode_padded`` returned, so nothing here waits for the host copy
+    of region_token_nums.  Returns (out [n_text - n_obj + m_pad, hid], out_len int32 device scalar,
+    row_src or None); rows past out_len are unspecified."""
+    _require_cuda(text_embeds, "text_embeds")
+    n_text, hid = text_embeds.shape
+    if tokens.shape[1] != hid or tokens.dtype != text_embeds.dtype:
+        raise ValueError("tokens and text_embeds must share width and dtype")
+    if region_pos.numel() != plan.n_obj or region_pos.dtype != torch.int32:
+        raise ValueError(f"region_pos must be int32 [{plan.n_obj}]")
+    text_embeds, tokens = text_embeds.contiguous(), tokens.contiguous()
+    dev = text_embeds.device
+    out = torch.empty((n_text - plan.n_obj + plan.m_pad, hid), dtype=text_embeds.dtype, device=dev)
+    out_len = torch.empty((1,), dtype=torch.int32, device=dev)
+    row_src = torch.full((out.shape[0],), 2 ** 31 - 1, dtype=torch.int32, device=dev) if want_row_src else None
+    _cabi.check(_cabi.lib().ufv_splice_rows(
+        text_embeds.data_ptr(), n_text, region_pos.data_ptr(), tokens.data_ptr(), plan.dev["slot_off"],
+        counts.data_ptr(), plan.n_obj, plan.m_pad, out.data_ptr(), out_len.data_ptr(),
+        row_src.data_ptr() if want_row_src else None, hid * text_embeds.element_size(), _stream_ptr(dev)))
+    return out, out_len, row_src
+
+
 # ------------------------------------------------------------------------------------------------
 # reference-named API
 # ------------------------------------------------------------------------------------------------
