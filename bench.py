@@ -76,12 +76,15 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index = index
+        self.enabled = enabled          # only rank 0 samples: one nvidia-smi poller per box is enough
         self.proc = None
         self.file = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
@@ -308,7 +311,7 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=rank == 0) as clocks:
         ms_step = timed(step_resident, a.steps, max(a.warmup, 3))
         ms_e2e = timed(step_e2e, a.steps, max(a.warmup, 3))
     clock_summary = clocks.summary()

@@ -52,12 +52,14 @@ constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;        // two per TMEM lane quarter, each takes every other 32-column chunk
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr int kTileBudget = 224 * 1024;   // shared memory for the stage ring (227 KB per CTA on sm_100)
+constexpr int kPeerStageBytes = 20 * 1024;   // epilogue staging of the fused all-gather variant (static)
 
-template <int BN> struct GemmCfg {
+template <int BN, bool PEER = false> struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kTileBudget / kStageBytes < 8 ? kTileBudget / kStageBytes : 8;
+  static constexpr int kBudget = kTileBudget - (PEER ? kPeerStageBytes : 0);
+  static constexpr int kStages = kBudget / kStageBytes < 8 ? kBudget / kStageBytes : 8;
   static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
                                    : 2 * BN <= 256 ? 256 : 512;   // two accumulators
@@ -149,7 +151,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k, int tiles_m,
                  int n_tiles, const __grid_constant__ ufv_peer_args peer) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PEER>;
+  // fused all-gather: a warp's 32 x 32 sub-tile is turned around in shared memory so that its remote
+  // stores are contiguous 64-byte row segments (4 lanes x 16 B) instead of 32 scattered 16-byte
+  // pieces -- 16-byte NVLink writes ran at ~170 GB/s, and the packet rate, not the bandwidth, was the limit
+  __shared__ uint4 s_stage[PEER ? kEpiWarps : 1][PEER ? 32 : 1][5];   // 80-byte rows: conflict-free both ways
   extern __shared__ uint8_t dyn_smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 1023) &
                                               ~uintptr_t(1023));   // SW128 atoms need 1024-B alignment
@@ -253,7 +259,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * uint32_t(BN) + uint32_t(col0), v);
         tmem_ld_wait();
         const int gcol = n0 + col0;
-        if (row < m && gcol < n) {
+        if ((PEER || row < m) && gcol < n) {
           uint32_t packed[16];
           if (gcol + 32 <= n) {
             const uint4* bsrc = reinterpret_cast<const uint4*>(bias + gcol);   // warp-uniform: broadcast
@@ -275,11 +281,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               }
             }
             if (PEER) {                  // fused all-gather: the tile goes to every rank's gathered buffer
-              const size_t off = (size_t(row) * n + gcol) * sizeof(T);
+              uint4(*stage)[5] = s_stage[warp - 2];
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                peer_store16(peer, off + 16 * i,
-                             make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]));
+                stage[lane][i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+              __syncwarp();
+              const int row_base = m0 + quarter * 32;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {       // 8 rows per instruction, 4 lanes x 16 B per row
+                const int r = i * 8 + (lane >> 2), c = lane & 3;
+                if (row_base + r < m)
+                  peer_store16(peer, (size_t(row_base + r) * n + gcol) * sizeof(T) + 16 * c, stage[r][c]);
+              }
+              __syncwarp();
             } else {
               T* dst = y + size_t(row) * n + gcol;
 #pragma unroll
@@ -399,7 +413,7 @@ static int sm_count() {
 template <typename T, int BN>
 static int launch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
                      int gelu, const ufv_peer_args* peer, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  const int smem_bytes = peer != nullptr ? GemmCfg<BN, true>::kSmem : GemmCfg<BN, false>::kSmem;
   CUtensorMap tx, tw;
   int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
   if (rc != 0) return rc;
@@ -414,12 +428,12 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
                                : linear_tc_kernel<T, BN, false, false>;
   static bool configured[3] = {false, false, false};   // idempotent attribute; a benign race sets it twice
   if (!configured[variant]) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     configured[variant] = true;
   }
   static const ufv_peer_args no_peer = {};
   return check_launch("ufv_linear (tcgen05)",
-                      launch_kernel(kernel, grid, dim3(kGemmThreads), Cfg::kSmem, stream, tx, tw,
+                      launch_kernel(kernel, grid, dim3(kGemmThreads), smem_bytes, stream, tx, tw,
                                     static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles,
                                     peer != nullptr ? *peer : no_peer));
 }
