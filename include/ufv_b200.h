@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UFV_ABI_VERSION 6
+#define UFV_ABI_VERSION 7
 
 /* element types */
 enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3 };
@@ -199,6 +199,16 @@ int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int
 int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,
                    void* stream);
 
+/* Per-call values of a replayed launch sequence (see ufv_encode_graph_create): 256 bytes. */
+typedef struct ufv_dyn_args {
+  uint64_t tokens_out;     /* output of the last Linear for this call                              */
+  uint64_t counts_out;     /* int32 [n_obj] device array for the counts, 0 = args->counts           */
+  int32_t epoch;           /* tag of this call's counts words (ufv_ttm)                             */
+  int32_t reserved;
+  ufv_peer_args peer;      /* fused all-gather destinations of this call (when args->peer != null)   */
+  uint64_t pad;
+} ufv_dyn_args;
+
 /* ---------------------------------------------------------------------------------------------
  * The whole path in one call (kernels 1-4 chained on `stream`).  Replaces
  * MaskExtractor.forward (layer.py:63-128) minus the host read-back of counts.
@@ -230,9 +240,26 @@ typedef struct ufv_encode_args {
   /* optional: fuse the result-collection all-gather into the last Linear (ufv_linear_gather);
    * tokens_out is then unused */
   const ufv_peer_args* peer;
+  /* optional: per-call values through a device block instead of kernel parameters (graph replay) */
+  const ufv_dyn_args* dyn_src;   /* device-visible address of the caller's pinned block */
+  ufv_dyn_args* dyn_dev;         /* 256 bytes of device scratch */
 } ufv_encode_args;
 
 int ufv_encode(const ufv_encode_args* args_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Replaying the chained path as a CUDA graph.  A repeated call differs from the previous one only
+ * in a few values (the output tensor, the tag of the counts words, the all-gather slot); those are
+ * kept OUT of the kernel parameters: the caller writes them into a pinned ufv_dyn_args block,
+ * kernel 1 copies the block to device memory (dyn_dev) and the later kernels read it there.  With
+ * args->dyn_src / dyn_dev set, the whole launch sequence is therefore constant and can be captured
+ * once (ufv_encode_graph_create) and relaunched with one driver call (ufv_encode_graph_launch).
+ * The block must stay unchanged until kernel 1 of that launch has run (callers that wait for the
+ * counts before their next call satisfy this).
+ * -------------------------------------------------------------------------------------------*/
+int ufv_encode_graph_create(const ufv_encode_args* args_host, void** graph_out_host);
+int ufv_encode_graph_launch(void* graph, void* stream);
+int ufv_encode_graph_destroy(void* graph);
 
 /* Compaction after merge ties: object o's first counts[o] rows (starting at row slot_off[o] of
  * `in`) are packed back to back into `out` in object order; `row_bytes` per row (multiple of 16).

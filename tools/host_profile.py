@@ -92,6 +92,31 @@ def fine_grained():
         torch.cuda.synchronize()
     for k, v in acc.items():
         print(f"{k:24s} {v / n * 1e6:8.1f} us")
+    # cold path: a batch structure never seen before on every call (what a real eval loop does)
+    import cProfile, pstats
+    n = 40
+    variants = []
+    for i in range(n):
+        a2 = [[[r for r in obj[: 16 - (i % 7)]] for obj in clip] for clip in ann]
+        a2[0][0] = a2[0][0][: 3 + i % 5]
+        variants.append(a2)
+    md2 = []
+    for i in range(n):
+        md2.append([m[: sum(len(o) for o in variants[i][c])] for c, m in enumerate(md)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        enc(ft, md2[i], None, variants[i], None)
+    torch.cuda.synchronize()
+    print(f"cold forward (new structure every call): {(time.perf_counter() - t0) / n * 1e6:.1f} us/call")
+    variants = [[[list(o)[::-1][: len(o)] for o in clip] for clip in v] for v in variants]
+    pr = cProfile.Profile()
+    pr.enable()
+    for i in range(n):
+        enc(ft, md2[i], None, variants[i], None)
+    pr.disable()
+    torch.cuda.synchronize()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(14)
 
 
 if __name__ == "__main__" and os.environ.get("UFV_FINE"):

@@ -21,7 +21,7 @@ BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8
 PLAN_PITCH = 736
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -58,7 +58,17 @@ class EncodeArgs(C.Structure):
         ("counts_host", _p), ("epoch", _i32), ("reserved", _i32),
         ("w1", _p), ("b1", _p), ("w2", _p), ("b2", _p),
         ("hidden", _p), ("tokens_out", _p), ("peer", C.POINTER(PeerArgs)),
+        ("dyn_src", _p), ("dyn_dev", _p),
     ]
+
+
+class DynArgs(C.Structure):
+    """Mirror of ``struct ufv_dyn_args`` (include/ufv_b200.h): the per-call block of a replayed graph."""
+    _fields_ = [("tokens_out", C.c_uint64), ("counts_out", C.c_uint64), ("epoch", _i32), ("reserved", _i32),
+                ("peer", PeerArgs), ("pad", C.c_uint64)]
+
+
+assert C.sizeof(DynArgs) == 256
 
 
 _SIGNATURES = {
@@ -75,6 +85,9 @@ _SIGNATURES = {
     "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "ufv_linear_gather": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PeerArgs), _p]),
     "ufv_wait_flags": (C.c_int, [_p, C.c_int, _i32, C.c_int, _p, _p]),
+    "ufv_encode_graph_create": (C.c_int, [C.POINTER(EncodeArgs), C.POINTER(_p)]),
+    "ufv_encode_graph_launch": (C.c_int, [_p, _p]),
+    "ufv_encode_graph_destroy": (C.c_int, [_p]),
     "ufv_encode": (C.c_int, [C.POINTER(EncodeArgs), _p]),
     "ufv_compact_rows": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int, _p]),
     "ufv_splice_rows": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p]),

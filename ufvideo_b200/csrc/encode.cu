@@ -7,6 +7,21 @@
 
 namespace ufv {
 
+int launch_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out, int any_row_mode,
+                           uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
+                           const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
+                           int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, const ufv_dyn_args* dyn_src,
+                           ufv_dyn_args* dyn_dev, void* stream);
+int ttm_dispatch(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
+                 const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
+                 int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
+                 int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
+                 int32_t epoch, const ufv_dyn_args* dyn, void* stream);
+int last_linear_dyn(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
+                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* stream);
+
+static_assert(sizeof(ufv_dyn_args) == 256, "ufv_dyn_args must stay 256 bytes (kernel 1 copies 64 words)");
+
 static thread_local char g_error[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -208,17 +223,23 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
   using namespace ufv;
   UFV_REQUIRE(a != nullptr, UFV_E_NULL, "ufv_encode: args is null");
   const int side = a->n_patch_side;
-  int rc = ufv_mask_to_patches(a->mask_desc, a->taps, a->n_masks, side, a->any_row_mode, a->bits, a->cnt, a->idx,
-                               a->idx_pitch, a->grp_off, a->grp_member, a->grp_ticket, a->grp_nu,
-                               a->grp_ulist, a->grp_omask, stream);
+  const bool dyn_mode = a->dyn_src != nullptr && a->dyn_dev != nullptr;
+  const ufv_dyn_args* dyn = dyn_mode ? a->dyn_dev : nullptr;
+  if (dyn_mode)
+    UFV_REQUIRE(a->n_masks > 0 && a->n_obj > 0 && a->m_pad > 0, UFV_E_SHAPE,
+                "ufv_encode: graph-replay mode needs a non-empty batch");
+  int rc = launch_mask_to_patches(a->mask_desc, a->taps, a->n_masks, side, a->any_row_mode, a->bits, a->cnt, a->idx,
+                                  a->idx_pitch, a->grp_off, a->grp_member, a->grp_ticket, a->grp_nu, a->grp_ulist,
+                                  a->grp_omask, dyn_mode ? a->dyn_src : nullptr, dyn_mode ? a->dyn_dev : nullptr,
+                                  stream);
   if (rc != 0) return rc;
   rc = ufv_mask_pool(a->feats, a->feat_dtype, a->n_rows, side * side, a->c, a->cnt, a->grp_row, a->grp_off,
                      a->grp_member, a->grp_nu, a->grp_ulist, a->grp_omask, a->n_groups, a->max_group,
                      a->pooled, stream);
   if (rc != 0) return rc;
-  rc = ufv_ttm(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
-               a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, a->sims, a->sims_pitch,
-               a->counts_host, a->epoch, stream);
+  rc = ttm_dispatch(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
+                    a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, a->sims, a->sims_pitch,
+                    a->counts_host, a->epoch, dyn, stream);
   if (rc != 0) return rc;
   if (a->m_pad == 0)
     return a->peer != nullptr
@@ -226,8 +247,64 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
                : 0;
   rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, stream);
   if (rc != 0) return rc;
+  if (dyn_mode)             // output pointer / all-gather destinations are read from the device block
+    return last_linear_dyn(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, dyn, stream);
   if (a->peer != nullptr)   // last Linear fused with the all-gather: tiles go straight to every rank
     return ufv_linear_gather(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, stream);
   return ufv_linear(a->hidden, a->w2, a->b2, a->tokens_out, a->m_pad, a->hid, a->hid, a->feat_dtype, 0,
                     stream);
+}
+
+// ---- graph replay ---------------------------------------------------------------------------------------
+extern "C" int ufv_encode_graph_create(const ufv_encode_args* a, void** graph_out) {
+  using namespace ufv;
+  UFV_REQUIRE(a != nullptr && graph_out != nullptr, UFV_E_NULL, "ufv_encode_graph_create: null pointer");
+  UFV_REQUIRE(a->dyn_src != nullptr && a->dyn_dev != nullptr, UFV_E_NULL,
+              "ufv_encode_graph_create: args->dyn_src / dyn_dev must be set");
+  *graph_out = nullptr;
+  cudaStream_t cap = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return fail(int(e), "ufv_encode_graph_create: stream: %s", cudaGetErrorString(e));
+  e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(cap);
+    return fail(int(e), "ufv_encode_graph_create: begin capture: %s", cudaGetErrorString(e));
+  }
+  const int rc = ufv_encode(a, cap);
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(cap, &graph);
+  cudaStreamDestroy(cap);
+  if (rc != 0) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess || graph == nullptr) {
+    cudaGetLastError();
+    return fail(int(e), "ufv_encode_graph_create: end capture: %s", cudaGetErrorString(e));
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(int(e), "ufv_encode_graph_create: instantiate: %s", cudaGetErrorString(e));
+  }
+  *graph_out = exec;
+  return 0;
+}
+
+extern "C" int ufv_encode_graph_launch(void* graph, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(graph != nullptr, UFV_E_NULL, "ufv_encode_graph_launch: graph is null");
+  const cudaError_t e = cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(int(e), "ufv_encode_graph_launch: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+extern "C" int ufv_encode_graph_destroy(void* graph) {
+  if (graph != nullptr) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph));
+  return 0;
 }

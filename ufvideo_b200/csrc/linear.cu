@@ -137,10 +137,12 @@ __device__ __forceinline__ void st_release_sys_u32(uint64_t addr, uint32_t v) {
 __device__ __forceinline__ void st_multimem_release_u32(uint64_t addr, uint32_t v) {
   asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
-// 16 bytes at byte offset `off` of this rank's rows in every destination copy
-__device__ __forceinline__ void peer_store16(const ufv_peer_args& peer, size_t off, uint4 v) {
-  if (peer.multimem) {
-    st_multimem_v4(peer.dst[0] + off, v);
+// 16 bytes at byte offset `off` of this rank's rows in every destination copy (multimem / dst0 are the
+// caller's register copies of peer.multimem / peer.dst[0]: the struct may live in global memory)
+__device__ __forceinline__ void peer_store16(const ufv_peer_args& peer, bool multimem, uint64_t dst0, size_t off,
+                                             uint4 v) {
+  if (multimem) {
+    st_multimem_v4(dst0 + off, v);
   } else {
     for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint4*>(peer.dst[d] + off) = v;
   }
@@ -150,7 +152,8 @@ template <typename T, int BN, bool GELU, bool PEER>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k, int tiles_m,
-                 int n_tiles, const __grid_constant__ ufv_peer_args peer) {
+                 int n_tiles, const __grid_constant__ ufv_peer_args peer_param,
+                 const ufv_dyn_args* __restrict__ dyn) {
   using Cfg = GemmCfg<BN, PEER>;
   // fused all-gather: a warp's 32 x 32 sub-tile is turned around in shared memory so that its remote
   // stores are contiguous 64-byte row segments (4 lanes x 16 B) instead of 32 scattered 16-byte
@@ -193,6 +196,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const uint32_t tmem_base = s_tmem_base;
   pdl_wait();                  // x (and, transitively, the parameters) come from earlier kernels
   pdl_launch_dependents();
+  // graph replay: the output pointer / all-gather destinations of this call come through the device block
+  if (dyn != nullptr) y = reinterpret_cast<T*>(dyn->tokens_out);
+  const ufv_peer_args& peer = (PEER && dyn != nullptr) ? dyn->peer : peer_param;
+  const bool peer_mm = PEER && peer.multimem != 0;
+  const uint64_t peer_dst0 = PEER ? peer.dst[0] : 0;
 
   if (warp == 0) {
     // ------------------------------- TMA producer -----------------------------------------------
@@ -291,7 +299,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               for (int i = 0; i < 4; ++i) {       // 8 rows per instruction, 4 lanes x 16 B per row
                 const int r = i * 8 + (lane >> 2), c = lane & 3;
                 if (row_base + r < m)
-                  peer_store16(peer, (size_t(row_base + r) * n + gcol) * sizeof(T) + 16 * c, stage[r][c]);
+                  peer_store16(peer, peer_mm, peer_dst0, (size_t(row_base + r) * n + gcol) * sizeof(T) + 16 * c,
+                               stage[r][c]);
               }
               __syncwarp();
             } else {
@@ -412,7 +421,7 @@ static int sm_count() {
 
 template <typename T, int BN>
 static int launch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                     int gelu, const ufv_peer_args* peer, cudaStream_t stream) {
+                     int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, cudaStream_t stream) {
   const int smem_bytes = peer != nullptr ? GemmCfg<BN, true>::kSmem : GemmCfg<BN, false>::kSmem;
   CUtensorMap tx, tw;
   int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
@@ -435,7 +444,7 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
   return check_launch("ufv_linear (tcgen05)",
                       launch_kernel(kernel, grid, dim3(kGemmThreads), smem_bytes, stream, tx, tw,
                                     static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles,
-                                    peer != nullptr ? *peer : no_peer));
+                                    peer != nullptr ? *peer : no_peer, dyn));
 }
 
 // N-tile choice.  A launch costs (waves over the SMs) x (time of one tile).  Tile times per 64-deep
@@ -466,12 +475,12 @@ static int choose_bn(int m, int n) {
 
 template <typename T>
 static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                       int gelu, const ufv_peer_args* peer, cudaStream_t stream) {
+                       int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, cudaStream_t stream) {
   switch (choose_bn(m, n)) {
-    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, stream);
-    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, stream);
-    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, peer, stream);
-    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, peer, stream);
+    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
+    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
+    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
+    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
   }
 }
 
@@ -610,9 +619,23 @@ extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* 
   }
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "ufv_linear: unsupported dtype %d", dtype);
   UFV_REQUIRE(k % 8 == 0 && n % 8 == 0, UFV_E_SHAPE, "ufv_linear: k=%d and n=%d must be multiples of 8", k, n);
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, nullptr, st);
-  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, nullptr, st);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, st);
+  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, st);
 }
+
+namespace ufv {
+// last Linear of the chained path in graph-replay mode (tensor-core dtypes only): the output pointer and,
+// with `peer`, the all-gather destinations are read from the device block `dyn` at run time
+int last_linear_dyn(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
+                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* stream) {
+  UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "graph replay: bf16 / fp16 only (dtype %d)", dtype);
+  UFV_REQUIRE(m >= 1 && k % 8 == 0 && n % 32 == 0, UFV_E_SHAPE, "graph replay: m=%d n=%d k=%d", m, n, k);
+  UFV_REQUIRE(x && w && bias && dyn && aligned16(x) && aligned16(w), UFV_E_NULL, "graph replay: bad pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, st);
+  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, st);
+}
+}  // namespace ufv
 
 extern "C" int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int n, int k,
                                  int dtype, const ufv_peer_args* peer, void* stream) {
@@ -635,8 +658,8 @@ extern "C" int ufv_linear_gather(const void* x, const void* w, const void* bias,
     return check_launch("ufv_linear_gather (empty shard)",
                         launch_kernel(peer_tail_only_kernel, dim3(1), dim3(256), 0, st, *peer));
   UFV_REQUIRE(aligned16(x) && aligned16(w), UFV_E_ALIGN, "ufv_linear_gather: x / w must be 16-byte aligned");
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, st);
-  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, st);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, st);
+  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, st);
 }
 
 extern "C" int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,

@@ -140,7 +140,8 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
                        uint16_t* __restrict__ idx_out, int idx_pitch,
                        const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member,
                        uint32_t* __restrict__ grp_ticket, int32_t* __restrict__ grp_nu,
-                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask) {
+                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask,
+                       const uint32_t* __restrict__ dyn_src, uint32_t* __restrict__ dyn_dev) {
   __shared__ int32_t s_taps[4 * UFV_MAX_PATCH_SIDE];
   __shared__ uint32_t s_words[UFV_BITS_WORDS];
   __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
@@ -155,6 +156,11 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   const int lane = tid & 31, warp = tid >> 5;
   pdl_wait();                  // masks / descriptors may come from the previous kernel in the stream
   pdl_launch_dependents();     // the pool kernel may get resident and set up while this one runs
+  // graph replay: CTA 0 forwards the caller's per-call block (pinned host memory) to device memory for
+  // the later kernels; the PCIe read is requested here and only consumed by the store at the very end
+  uint32_t dyn_word = 0;
+  const bool dyn_copy = dyn_src != nullptr && j == 0 && tid < int(sizeof(ufv_dyn_args) / 4);
+  if (dyn_copy) dyn_word = *reinterpret_cast<const volatile uint32_t*>(dyn_src + tid);
   const ufv_mask_desc d = desc[j];
   if (tid < 4 * n_out) s_taps[tid] = taps[d.tap_off + tid];
   __syncthreads();
@@ -271,6 +277,7 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
             static_cast<uint16_t>(p);
     }
   }
+  if (dyn_copy) dyn_dev[tid] = dyn_word;
   if (grp_ticket == nullptr) return;
 
   // ---- group plan, built by whichever member CTA arrives last ---------------------------------------
@@ -345,11 +352,12 @@ extern "C" int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* t
   return 0;
 }
 
-extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
-                                   int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out,
-                                   int idx_pitch, const int32_t* grp_off, const int32_t* grp_member,
-                                   uint32_t* grp_ticket, int32_t* grp_nu, uint16_t* grp_ulist,
-                                   uint8_t* grp_omask, void* stream) {
+namespace ufv {
+int launch_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out, int any_row_mode,
+                           uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
+                           const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
+                           int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, const ufv_dyn_args* dyn_src,
+                           ufv_dyn_args* dyn_dev, void* stream) {
   UFV_REQUIRE(n_masks >= 0 && n_out >= 1 && n_out <= UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
               "ufv_mask_to_patches: n_masks=%d n_out=%d out of range", n_masks, n_out);
   if (n_masks == 0) return 0;
@@ -365,5 +373,17 @@ extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* tap
       "ufv_mask_to_patches",
       ufv::launch_kernel(kernel, dim3(n_masks), dim3(threads), 0, static_cast<cudaStream_t>(stream), desc,
                          taps, n_out, bits_out, cnt_out, idx_out, idx_pitch, grp_off, grp_member, grp_ticket,
-                         grp_nu, grp_ulist, grp_omask));
+                         grp_nu, grp_ulist, grp_omask, reinterpret_cast<const uint32_t*>(dyn_src),
+                         reinterpret_cast<uint32_t*>(dyn_dev)));
+}
+}  // namespace ufv
+
+extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
+                                   int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out,
+                                   int idx_pitch, const int32_t* grp_off, const int32_t* grp_member,
+                                   uint32_t* grp_ticket, int32_t* grp_nu, uint16_t* grp_ulist,
+                                   uint8_t* grp_omask, void* stream) {
+  return ufv::launch_mask_to_patches(desc, taps, n_masks, n_out, any_row_mode, bits_out, cnt_out, idx_out, idx_pitch,
+                                     grp_off, grp_member, grp_ticket, grp_nu, grp_ulist, grp_omask, nullptr, nullptr,
+                                     stream);
 }

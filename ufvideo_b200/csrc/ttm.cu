@@ -151,7 +151,7 @@ ttm_merge_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
                  int max_len, const float* __restrict__ sims, int sims_pitch, T* __restrict__ tokens_out,
                  float* __restrict__ tokens_f32_out, int32_t* __restrict__ counts_out,
                  uint32_t* __restrict__ cuts_out, int cut_pitch_words, int32_t* __restrict__ counts_host,
-                 int32_t epoch) {
+                 int32_t epoch, const ufv_dyn_args* __restrict__ dyn) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const int len_words = (max_len + 31) / 32;
   float* s_sim = reinterpret_cast<float*>(dyn_smem);                 // [max_len]
@@ -164,6 +164,10 @@ ttm_merge_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();                  // similarities come from kernel 3a, pooled rows from kernel 2
   pdl_launch_dependents();
+  if (dyn != nullptr) {        // graph replay: per-call values come through the device block
+    epoch = dyn->epoch;
+    if (dyn->counts_out != 0) counts_out = reinterpret_cast<int32_t*>(dyn->counts_out);
+  }
   const int t_len = obj_len[o];
   const int n_slots = min(t_len, k_keep);
   if (g >= n_slots) {          // this object reserved fewer than K slots (T_o < K)
@@ -288,7 +292,8 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
            const int32_t* __restrict__ obj_len, const int32_t* __restrict__ slot_off, int k_keep,
            int max_len, T* __restrict__ tokens_out, float* __restrict__ tokens_f32_out,
            int32_t* __restrict__ counts_out, uint32_t* __restrict__ cuts_out, int cut_pitch_words,
-           float* __restrict__ sims_out, int sims_pitch, int32_t* __restrict__ counts_host, int32_t epoch) {
+           float* __restrict__ sims_out, int sims_pitch, int32_t* __restrict__ counts_host, int32_t epoch,
+           const ufv_dyn_args* __restrict__ dyn) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const int len_words = (max_len + 31) / 32;
   float* s_norm = reinterpret_cast<float*>(dyn_smem);          // [max_len]
@@ -302,6 +307,10 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();                  // pooled rows come from kernel 2
   pdl_launch_dependents();
+  if (dyn != nullptr) {        // graph replay: per-call values come through the device block
+    epoch = dyn->epoch;
+    if (dyn->counts_out != 0) counts_out = reinterpret_cast<int32_t*>(dyn->counts_out);
+  }
   const int t_len = obj_len[o];
   const int slot = slot_off[o];
   const float* x = pooled + size_t(obj_start[o]) * c;
@@ -477,7 +486,7 @@ static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, cons
                       const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
                       float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
                       int cut_pitch_words, float* sims, int sims_pitch, int32_t* counts_host, int32_t epoch,
-                      cudaStream_t stream) {
+                      const ufv_dyn_args* dyn, cudaStream_t stream) {
   const int len_words = (max_len + 31) / 32;
   if (max_len <= kFusedMaxLen) {
     const size_t smem = size_t(max_len) * 8 + size_t(len_words) * 4 + size_t(len_words + 1) * 4 +
@@ -488,7 +497,7 @@ static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, cons
                         launch_kernel(kernel, dim3(n_obj), dim3(kTtmThreads), smem, stream, pooled, c, obj_start,
                                       obj_len, slot_off, k_keep, max_len, static_cast<T*>(tokens_out),
                                       tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims, sims_pitch,
-                                      counts_host, epoch));
+                                      counts_host, epoch, dyn));
   }
   if (max_len > k_keep) {
     const dim3 grid((max_len - 1 + kSimWarps - 1) / kSimWarps, n_obj);
@@ -505,17 +514,17 @@ static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, cons
                       launch_kernel(kernel, grid, dim3(kMergeThreads), smem, stream, pooled, c, obj_start,
                                     obj_len, slot_off, k_keep, max_len, static_cast<const float*>(sims),
                                     sims_pitch, static_cast<T*>(tokens_out), tokens_f32_out, counts_out,
-                                    cuts_out, cut_pitch_words, counts_host, epoch));
+                                    cuts_out, cut_pitch_words, counts_host, epoch, dyn));
 }
 
 }  // namespace ufv
 
-extern "C" int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
-                       const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
-                       int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
-                       int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
-                       int32_t epoch, void* stream) {
-  using namespace ufv;
+namespace ufv {
+int ttm_dispatch(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
+                 const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
+                 int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
+                 int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
+                 int32_t epoch, const ufv_dyn_args* dyn, void* stream) {
   UFV_REQUIRE(n_obj >= 0, UFV_E_SHAPE, "ufv_ttm: n_obj=%d", n_obj);
   if (n_obj == 0) return 0;
   UFV_REQUIRE(pooled && obj_start && obj_len && slot_off && tokens_out && counts_out, UFV_E_NULL,
@@ -531,22 +540,33 @@ extern "C" int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, con
               "ufv_ttm: sims_out (fp32 [n_obj * sims_pitch] scratch) is required when an object has more "
               "than k_keep frames");
   UFV_REQUIRE(sims_out == nullptr || sims_pitch >= max_len - 1, UFV_E_SHAPE, "ufv_ttm: sims_pitch too small");
-  UFV_REQUIRE(counts_host == nullptr || (epoch > 0 && epoch < 32768), UFV_E_SHAPE,
+  UFV_REQUIRE(counts_host == nullptr || dyn != nullptr || (epoch > 0 && epoch < 32768), UFV_E_SHAPE,
               "ufv_ttm: epoch %d must be in [1, 32767] when counts_host is given", epoch);
   UFV_REQUIRE(counts_host == nullptr || k_keep < 65536, UFV_E_SHAPE, "ufv_ttm: k_keep too large for the host word");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (out_dtype) {
     case UFV_F32:
       return launch_ttm<float>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep, tokens_out,
-                               tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, epoch, st);
+                               tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, epoch, dyn, st);
     case UFV_BF16:
       return launch_ttm<__nv_bfloat16>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep,
                                        tokens_out, tokens_f32_out, counts_out, cuts_out, cut_pitch_words,
-                                       sims_out, sims_pitch, counts_host, epoch, st);
+                                       sims_out, sims_pitch, counts_host, epoch, dyn, st);
     case UFV_F16:
       return launch_ttm<__half>(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep, tokens_out,
-                                tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, epoch, st);
+                                tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host, epoch, dyn, st);
     default:
       return fail(UFV_E_DTYPE, "ufv_ttm: unsupported output dtype %d", out_dtype);
   }
+}
+}  // namespace ufv
+
+extern "C" int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
+                       const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
+                       int out_dtype, float* tokens_f32_out, int32_t* counts_out, uint32_t* cuts_out,
+                       int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
+                       int32_t epoch, void* stream) {
+  return ufv::ttm_dispatch(pooled, c, obj_start, obj_len, slot_off, n_obj, max_len, k_keep, tokens_out, out_dtype,
+                           tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims_out, sims_pitch, counts_host,
+                           epoch, nullptr, stream);
 }
