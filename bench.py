@@ -228,6 +228,7 @@ def run_ours(a):
 
     enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
     enc.region_token_num = k
+    enc.requires_grad_(False)                 # forward-only path
     with torch.no_grad():
         for p, wt in zip((enc.feat_linear[0].weight, enc.feat_linear[0].bias,
                           enc.feat_linear[2].weight, enc.feat_linear[2].bias), synth.make_weights(0)):

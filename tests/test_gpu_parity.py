@@ -38,6 +38,7 @@ def cfg(c=1152, hid=3584):
 def make_encoder(dev, dtype="f32", k=8, aspect="square", weights=None, c=1152, hid=3584):
     enc = build_region_encoder(cfg(c, hid), aspect)
     enc.region_token_num = k
+    enc.requires_grad_(False)                 # forward-only path
     w = weights if weights is not None else synth.make_weights(0, c, hid)
     with torch.no_grad():
         for p, a in zip((enc.feat_linear[0].weight, enc.feat_linear[0].bias,
@@ -461,6 +462,37 @@ def test_region_splice_matches_the_reference_consumer_loop(dev):
     assert torch.equal(out[:n], want)
     src = row_src[:n].cpu().numpy()
     assert (src[:2] == [0, 1]).all() and src[2] == -1 and src[-1] == n_text - 1
+
+
+def test_training_path_gradients_match_the_reference_ops(dev):
+    """With grad enabled and trainable parameters / features, forward() is differentiable: gradients of
+    a scalar loss w.r.t. the projector weights and the features equal those of the reference's op
+    sequence (oracle/reference_port.py under torch autograd), fp32."""
+    from oracle import reference_port
+    feats_np, masks_np, ann = synth.make_batch(2, 6, 2, "blob", h=96, w=96, first_clip=900, ragged=True)
+    enc = make_encoder(dev, "f32", 3)
+    enc.requires_grad_(True)
+    feats = torch.from_numpy(feats_np).to(dev).requires_grad_(True)
+    masks = [torch.from_numpy(m).to(dev) for m in masks_np]
+    tokens, nums = enc(feats, masks, None, ann, None)
+    assert tokens.requires_grad
+    probe = torch.linspace(-1, 1, tokens.numel(), device=dev).reshape(tokens.shape)
+    (tokens * probe).sum().backward()
+    got = {"feats": feats.grad.clone(), "w1": enc.feat_linear[0].weight.grad.clone(),
+           "b2": enc.feat_linear[2].bias.grad.clone()}
+    feats2 = torch.from_numpy(feats_np).to(dev).requires_grad_(True)
+    ws = [p.detach().clone().requires_grad_(True) for p in (enc.feat_linear[0].weight, enc.feat_linear[0].bias,
+                                                            enc.feat_linear[2].weight, enc.feat_linear[2].bias)]
+    ref_tokens, ref_nums = reference_port.encode(feats2, [m.float() for m in masks], ann, 3, *ws)
+    assert nums == ref_nums and (tokens - ref_tokens).abs().max().item() <= 1e-5
+    (ref_tokens * probe).sum().backward()
+    scale = feats2.grad.abs().max().item()
+    assert (got["feats"] - feats2.grad).abs().max().item() <= 1e-4 * max(scale, 1.0)
+    assert (got["w1"] - ws[0].grad).abs().max().item() <= 1e-4 * max(ws[0].grad.abs().max().item(), 1.0)
+    assert (got["b2"] - ws[3].grad).abs().max().item() <= 1e-4 * max(ws[3].grad.abs().max().item(), 1.0)
+    with torch.no_grad():                                   # and the inference path still agrees
+        t2, n2 = enc(feats.detach(), masks, None, ann, None)
+    assert n2 == nums and (t2 - tokens.detach()).abs().max().item() <= 1e-5
 
 
 def test_long_objects_spread_over_many_ctas(dev):

@@ -19,6 +19,7 @@ def main():
     md = [torch.from_numpy(m).to(dev).float() for m in masks]
     enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
     enc.region_token_num = 8
+    enc.requires_grad_(False)
     enc = enc.to(dev).bfloat16()
     for _ in range(20):
         enc(ft, md, None, ann, None)
@@ -59,6 +60,7 @@ def fine_grained():
     md = [torch.from_numpy(m).to(dev).float() for m in masks]
     enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
     enc.region_token_num = 8
+    enc.requires_grad_(False)
     enc = enc.to(dev).bfloat16()
     for _ in range(10):
         enc(ft, md, None, ann, None)

@@ -105,6 +105,7 @@ def run(name, k=8, with_baselines=False):
     md = [torch.from_numpy(m).to(dev) for m in masks]          # uint8
     enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
     enc.region_token_num = k
+    enc.requires_grad_(False)                 # forward-only path
     enc = enc.to(dev).to(dt)
     base = baselines(name, feats, masks, ann, k, dt, enc, dev) if with_baselines else {}
     del feats

@@ -41,6 +41,7 @@ def main():
     md = [torch.from_numpy(m).to(dev) for m in masks]
     enc = build_region_encoder(types.SimpleNamespace(mm_hidden_size=1152, hidden_size=3584), "square")
     enc.region_token_num = a.k
+    enc.requires_grad_(False)
     enc = enc.to(dev).to(dt)
     plan = packer.build_plan(md, ann, ft.shape[0], a.k, dev)
     q = plan.n_masks

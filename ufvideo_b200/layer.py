@@ -466,12 +466,37 @@ class MaskExtractor(nn.Module):
             return tokens, _await_counts(plan, tokens.device), plan
         return tokens, counts.cpu().numpy(), plan
 
+    def _forward_with_grad(self, feats, masks, ann_indices):
+        """Training path (the region encoder is trainable in the reference, videorefer_arch.py:94-96):
+        kernels 1-3 through ``_PoolMerge`` (differentiable w.r.t. ``feats``), then the projector through
+        its own ``nn.Sequential`` so that autograd records it (cuBLAS GEMMs; the fused tcgen05 projector
+        is the inference path)."""
+        linears = self._linears()
+        device = linears[0].weight.device
+        if device.type != "cuda":
+            raise RuntimeError("MaskExtractor parameters must be on a CUDA device (no CPU path)")
+        feats = feats.to(device).contiguous()
+        f, n_patch, c = feats.shape
+        side = int(round(n_patch ** 0.5))
+        k_keep = int(self.region_token_num)
+        plan = packer.build_plan(masks, ann_indices, f, k_keep, device, self.image_aspect_ratio == "pad", side)
+        self.last_plan = plan
+        merged, counts = _PoolMerge.apply(feats, plan, k_keep, feats.dtype)
+        nums = counts.cpu().numpy()
+        if nums.tobytes() != plan.slots_bytes:                    # merge ties: drop the zero-filled slots
+            keep = np.concatenate([np.arange(s, s + n) for s, n in zip(plan.host["slot_off"], nums)])
+            merged = merged[torch.from_numpy(keep).to(device)]
+        return self.feat_linear(merged), [int(n) for n in nums]
+
     # -- the reference's forward -----------------------------------------------------------------
     def forward(self, feats, masks, X_features, ann_indices, frame_nums):
         """Same contract as layer.py:63-128: returns (mask_feats [N_tok, hidden], region_token_nums
         list[int]).  ``X_features`` and ``frame_nums`` are accepted and ignored, as in the reference
         (which reads only ``X_features.device`` in its fallbacks).  Forward only: no autograd graph
         is recorded (DESIGN.md, "next")."""
+        if torch.is_grad_enabled() and ((torch.is_tensor(feats) and feats.requires_grad)
+                                        or any(p.requires_grad for p in self.feat_linear.parameters())):
+            return self._forward_with_grad(feats, masks, ann_indices)
         tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, _awaited=True)
         # the one unavoidable D2H: the caller slices rows by these counts (videorefer_arch.py:307-311)
         if plan.run.get("args") is not None and plan.n_obj > 0:
@@ -490,6 +515,70 @@ class MaskExtractor(nn.Module):
             tokens.data_ptr(), plan.dev["slot_off"], counts.data_ptr(), plan.n_obj, packed.data_ptr(),
             tokens.shape[1] * tokens.element_size(), _stream_ptr(tokens.device)))
         return packed, nums
+
+
+class _PoolMerge(torch.autograd.Function):
+    """Kernels 1-3 as one differentiable op: feats -> merged tokens [m_pad, C] (model dtype).
+
+    Forward runs the CUDA kernels.  Backward (training parity) is the exact adjoint
+    of the forward arithmetic -- run means, masked mean -- written with plain torch ops for now: the
+    merge decisions are piecewise constant, exactly as under the reference's own autograd (its
+    comparisons and topk carry no gradient either, layer.py:17-27)."""
+
+    @staticmethod
+    def forward(ctx, feats, plan, k_keep, out_dtype):
+        dev = feats.device
+        patches = mask_to_patches(plan, dev, int(round(feats.shape[1] ** 0.5)))
+        pooled = mask_pool(feats, plan, patches)
+        merged, counts, extras = ttm(pooled, plan, k_keep, out_dtype, debug=True)
+        ctx.plan, ctx.k_keep, ctx.feat_shape, ctx.feat_dtype = plan, k_keep, feats.shape, feats.dtype
+        ctx.save_for_backward(patches["bits"], patches["cnt"], extras["cuts"], counts)
+        ctx.mark_non_differentiable(counts)
+        return merged, counts
+
+    @staticmethod
+    def backward(ctx, d_merged, _d_counts):
+        bits, cnt, cuts, counts = ctx.saved_tensors
+        plan, k_keep = ctx.plan, ctx.k_keep
+        dev = d_merged.device
+        h = plan.host
+        n_obj, q = plan.n_obj, plan.n_masks
+        obj_len = torch.from_numpy(h["obj_len"]).to(dev).long()
+        obj_start = torch.from_numpy(h["obj_start"]).to(dev).long()
+        slot_off = torch.from_numpy(h["slot_off"]).to(dev).long()
+        max_len = max(plan.max_len, 1)
+        # run id of token t of object o: number of cuts before t (merged objects) or t itself (T <= K)
+        t_idx = torch.arange(max_len, device=dev)
+        words = cuts.view(n_obj, -1).to(torch.int64) & 0xffffffff
+        cut = ((words[:, t_idx // 32] >> (t_idx % 32)) & 1)                     # [n_obj, max_len]
+        gid = torch.cumsum(cut, 1) - cut
+        gid = torch.where((obj_len <= k_keep)[:, None], t_idx[None, :].expand(n_obj, -1), gid)
+        valid = t_idx[None, :] < obj_len[:, None]
+        o_of = torch.arange(n_obj, device=dev)[:, None].expand(-1, max_len)[valid]
+        t_of = t_idx[None, :].expand(n_obj, -1)[valid]
+        g_of = gid[valid]
+        pooled_row = obj_start[o_of] + t_of
+        token_row = slot_off[o_of] + g_of
+        run_size = torch.zeros(d_merged.shape[0], device=dev).index_add_(0, token_row, torch.ones_like(g_of, dtype=torch.float32))
+        d_pooled = torch.zeros((q, d_merged.shape[1]), dtype=torch.float32, device=dev)
+        d_pooled[pooled_row] = d_merged.float()[token_row] / run_size[token_row][:, None]
+        # masked mean: pooled[j] = sum_{p on} feats[row_j, p] / (cnt_j + 1e-8)
+        denorm = cnt.float() + 1e-8
+        w = d_pooled / denorm[:, None]
+        frame_row = torch.empty(q, dtype=torch.long)
+        go, gm, gr = h["grp_off"], h["grp_member"], h["grp_row"]
+        for g in range(plan.n_groups):
+            frame_row[gm[go[g]:go[g + 1]]] = int(gr[g])
+        frame_row = frame_row.to(dev)
+        n_patch = ctx.feat_shape[1]
+        p_idx = torch.arange(n_patch, device=dev)
+        d_feats = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
+        bw = bits.view(q, -1).to(torch.int64) & 0xffffffff
+        for j0 in range(0, q, 32):                                            # bounded temporaries
+            j1 = min(q, j0 + 32)
+            on = ((bw[j0:j1][:, p_idx // 32] >> (p_idx % 32)) & 1).to(torch.float32)   # [b, n_patch]
+            d_feats.index_add_(0, frame_row[j0:j1], on[:, :, None] * w[j0:j1][:, None, :])
+        return d_feats.to(ctx.feat_dtype), None, None, None
 
 
 def build_region_encoder(config, image_aspect_ratio):
