@@ -32,7 +32,7 @@ extern "C" {
 #define UFV_ABI_VERSION 7
 
 /* element types */
-enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3 };
+enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3, UFV_RLE = 4 /* masks only */ };
 
 /* argument errors */
 enum {
@@ -48,7 +48,9 @@ enum {
 #define UFV_MAX_GROUP 8          /* object-frames pooled together from one staged frame tile */
 #define UFV_PLAN_PITCH 736       /* entries per group in the union-plan arrays (>= 729, % 16 == 0) */
 
-/* One object-frame's mask plane (32 bytes).  `addr` may point into device memory or into pinned,
+/* One object-frame's mask plane (32 bytes).  dtype UFV_RLE: a COCO run-length mask -- `addr` points to the
+ * int32 cumulative run ends, `pitch` = number of runs, `aux` = image height; pixel p is on iff the first
+ * run whose end exceeds p has an odd index (runs alternate, starting with zeros).  Dense dtypes:  `addr` may point into device memory or into pinned,
  * device-mapped HOST memory (ufv_device_address): the kernel then reads the mask in place over
  * PCIe, touching only the rows its taps need. */
 typedef struct ufv_mask_desc {
@@ -58,7 +60,7 @@ typedef struct ufv_mask_desc {
   int32_t tap_off;    /* offset of the plane's tap table inside `taps`, in int32 units          */
   int32_t group;      /* pool group this object-frame belongs to (index into grp_off)           */
   int32_t flags;      /* bit 0: read in row mode when the tap span fits (see ufv_mask_to_patches) */
-  int32_t reserved;
+  int32_t aux;        /* UFV_RLE: image height h (pixels are numbered column-major, p = x * h + y)  */
 } ufv_mask_desc;
 
 int ufv_abi_version(void);

@@ -96,6 +96,21 @@ def mask_to_patches(mask: np.ndarray, n_out: int = PATCH, pad_square: bool = Fal
     return on.reshape(-1)
 
 
+def rle_to_mask(rle: dict) -> np.ndarray:
+    """COCO run-length mask -> dense uint8 [H, W] (what pycocotools.mask.decode returns inside the
+    reference's annToMask, ufvideo/mm_utils.py:22-33): pixels are numbered column-major, runs alternate
+    off / on starting with off.  Uncompressed counts only (lists of ints)."""
+    h, w = (int(v) for v in rle["size"])
+    flat = np.zeros(h * w, dtype=np.uint8)
+    pos, val = 0, 0
+    for c in rle["counts"]:
+        if val:
+            flat[pos:pos + int(c)] = 1
+        pos += int(c)
+        val ^= 1
+    return flat.reshape((h, w), order="F")
+
+
 def pack_bits(on: np.ndarray) -> np.ndarray:
     """bool [..., n] -> uint32 [..., ceil(n/32)] little-endian bit order (bit p%32 of word p//32)."""
     n = on.shape[-1]

@@ -120,6 +120,38 @@ def test_pinned_host_masks_are_read_in_place(dev, hw, mask_dtype, read_mode):
         assert np.array_equal(bits_to_bool(bits), want)
 
 
+@pytest.mark.parametrize("hw", [(384, 384), (480, 854), (100, 37), (27, 27), (13, 13)])
+@pytest.mark.parametrize("pad", [False, True])
+def test_run_length_masks_give_the_same_bits_as_dense_masks(dev, hw, pad):
+    """COCO RLE dicts go to kernel 1 as cumulative run ends (one binary search per tap): same patch bits
+    as the dense mask the reference would have decoded with pycocotools (mm_utils.py:22-33)."""
+    from ufvideo_b200 import rle
+    h, w = hw
+    masks = np.concatenate([synth.masks_blob(h + w, 2, 2, h, w), synth.masks_sparse(h * w, 3, h, w, p=0.01),
+                            np.zeros((1, h, w), np.uint8), np.ones((1, h, w), np.uint8)])
+    want = np.stack([R.mask_to_patches(R.rle_to_mask(rle.encode(m)), pad_square=pad) for m in masks])
+    assert np.array_equal(want, np.stack([R.mask_to_patches(m, pad_square=pad) for m in masks]))
+    n = masks.shape[0]
+    for sample in ([rle.encode(m) for m in masks],
+                   [{"size": [h, w], "counts": rle.counts_to_string(rle.encode(m)["counts"])} for m in masks]):
+        plan = packer.build_plan([sample], [[list(range(n))]], n, 1, dev, pad_square=pad, use_cache=False)
+        out = layer.mask_to_patches(plan, dev)
+        assert np.array_equal(bits_to_bool(out["bits"]), want)
+        assert np.array_equal(out["cnt"].cpu().numpy(), want.sum(1))
+
+
+def test_forward_with_run_length_masks_equals_forward_with_dense_masks(dev):
+    from ufvideo_b200 import rle
+    case = gc.e2e_case("multi")
+    enc = make_encoder(dev, "f32", case["k"])
+    feats = torch.from_numpy(case["feats"]).to(dev)
+    dense = [torch.from_numpy(m).to(dev) for m in case["masks"]]
+    a, na = enc(feats, dense, None, case["ann"], None)
+    for _ in range(2):                                       # second call: cached plan, refreshed run data
+        b, nb = enc(feats, [[rle.encode(m) for m in ms] for ms in case["masks"]], None, case["ann"], None)
+        assert na == nb and torch.equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------
 # kernel 2
 # ---------------------------------------------------------------------------------------------
@@ -330,6 +362,27 @@ def test_forward_with_pinned_host_inputs_equals_device_inputs(dev):
     a, na = enc(feats.to(dev), [m.to(dev) for m in masks], None, case["ann"], None)
     b, nb = enc(feats.pin_memory(), [m.pin_memory() for m in masks], None, case["ann"], None)
     assert na == nb and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+def test_repeated_calls_replay_and_stay_identical(dev, dtype):
+    """From the second call of a batch structure on, bf16 / fp16 forward() replays a captured CUDA graph
+    (per-call values travel through the pinned block); results must not change, also with new mask data."""
+    case = gc.e2e_case("bf16")
+    enc = make_encoder(dev, dtype, 8)
+    feats = torch.from_numpy(case["feats"]).to(dev).to(TORCH_DT[dtype])
+    masks = [torch.from_numpy(m).to(dev) for m in case["masks"]]
+    first, n_first = enc(feats, masks, None, case["ann"], None)
+    for _ in range(4):
+        again, n_again = enc(feats, masks, None, case["ann"], None)
+        assert n_again == n_first and torch.equal(again, first) and again.data_ptr() != first.data_ptr()
+    if dtype != "f32":
+        assert enc.last_plan.run["graphs"], "the graph should have been captured by now"
+    flipped = [m.flip(0).contiguous() for m in masks]        # other mask content, same structure, new pointers
+    ref = make_encoder(dev, dtype, 8)
+    want, n_want = ref(feats, flipped, None, case["ann"], None)
+    got, n_got = enc(feats, flipped, None, case["ann"], None)
+    assert n_got == n_want and torch.equal(got, want)
 
 
 def test_list_and_tensor_mask_forms_agree(dev):

@@ -115,3 +115,33 @@ def test_plan_cache_reuses_structure_and_patches_mask_addresses():
     on_dev = p1.buffer[off:off + 96].numpy().view(packer.MASK_DESC)
     assert on_dev["addr"].tolist() == [b.data_ptr() + i * 256 for i in range(3)]
     assert packer.build_plan([a], [[[0, 1], [0]]], 2, 4, CPU) is not p1     # different structure
+
+
+def test_rle_codec_round_trips_and_matches_the_oracle_decode():
+    from ufvideo_b200 import rle
+    g = synth.rng_for(99)
+    for shape in [(5, 7), (384, 384), (3, 1), (1, 9), (27, 27)]:
+        for dens in (0.0, 0.3, 1.0):
+            m = (g.random(shape) < dens).astype(np.uint8)
+            r = rle.encode(m)
+            assert sum(r["counts"]) == m.size
+            assert np.array_equal(R.rle_to_mask(r), m)                       # oracle's independent decoder
+            packed = rle.counts_to_string(r["counts"])
+            assert rle.counts_from_string(packed).tolist() == r["counts"]    # pycocotools string codec
+            h, w, ends = rle.run_ends({"size": r["size"], "counts": packed})
+            assert (h, w) == shape and ends.tolist() == np.cumsum(r["counts"]).tolist()
+    with pytest.raises(ValueError):
+        rle.run_ends({"size": [2, 2], "counts": [3, 3]})
+
+
+def test_plan_accepts_run_length_samples_and_refreshes_their_descriptors():
+    from ufvideo_b200 import rle
+    masks = synth.masks_blob(5, 2, 3, 50, 70)
+    ann = [[[0, 1, 2], [0, 1, 2]]]
+    plan = packer.build_plan([[rle.encode(m) for m in masks]], ann, 3, 2, CPU)
+    d = plan.host["mask_desc"]
+    assert (d["dtype"] == _cabi.UFV_RLE).all() and (d["aux"] == 50).all() and not d["flags"].any()
+    assert d["pitch"].tolist() == [len(rle.encode(m)["counts"]) for m in masks]
+    again = packer.build_plan([[rle.encode(m) for m in masks[::-1]]], ann, 3, 2, CPU)   # same structure, new runs
+    assert again is plan and again.host["mask_desc"]["pitch"].tolist() == d["pitch"].tolist()
+    assert again.host["mask_desc"]["pitch"].tolist() == [len(rle.encode(m)["counts"]) for m in masks[::-1]]

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("UFV_B200_LIB") or os.path.join(HERE, "libufv_b200.so"
 CSRC = os.path.join(HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ufv_b200.h")
 
-UFV_F32, UFV_BF16, UFV_F16, UFV_U8 = 0, 1, 2, 3
+UFV_F32, UFV_BF16, UFV_F16, UFV_U8, UFV_RLE = 0, 1, 2, 3, 4
 BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8

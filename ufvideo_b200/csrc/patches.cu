@@ -49,6 +49,20 @@ static void shift_into_image(int32_t* t, int n, int offset, int extent) {
 }
 
 // ---- device ---------------------------------------------------------------------------------------
+// COCO run-length mask: cum[i] = end (exclusive) of run i in column-major pixel order; runs alternate
+// off / on starting with off.  Pixel q is on iff the first run with cum[i] > q has an odd index.
+__device__ __forceinline__ bool rle_positive(const int32_t* __restrict__ cum, int n_runs, int q) {
+  int lo = 0, hi = n_runs;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cum + mid) <= q) lo = mid + 1; else hi = mid;
+  }
+  return lo < n_runs && (lo & 1);
+}
+
+// one tap of an object-frame's mask: dense planes are indexed row-major, run-length masks column-major
+__device__ __forceinline__ bool tap_positive(const ufv_mask_desc& d, int r, int c);
+
 __device__ __forceinline__ bool mask_positive(uint64_t base, int64_t off, int dtype) {
   switch (dtype) {
     case UFV_U8:
@@ -60,6 +74,11 @@ __device__ __forceinline__ bool mask_positive(uint64_t base, int64_t off, int dt
     default:
       return __half2float(reinterpret_cast<const __half*>(base)[off]) > 0.0f;
   }
+}
+
+__device__ __forceinline__ bool tap_positive(const ufv_mask_desc& d, int r, int c) {
+  if (d.dtype == UFV_RLE) return rle_positive(reinterpret_cast<const int32_t*>(d.addr), d.pitch, c * d.aux + r);
+  return mask_positive(d.addr, int64_t(r) * d.pitch + c, d.dtype);
 }
 
 // "element > 0" flags of one 16-byte chunk, bit e = element e of the chunk
@@ -188,7 +207,7 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   }
   __syncthreads();
   const int cmin = s_span[0], cmax = s_span[1];
-  const bool row_mode = ROWS && (d.flags & 1) != 0 && cmax >= 0 && ((cmax - cmin + 1) * es + 30) >> 4 <= kRowChunks;
+  const bool row_mode = ROWS && (d.flags & 1) != 0 && d.dtype != UFV_RLE && cmax >= 0 && ((cmax - cmin + 1) * es + 30) >> 4 <= kRowChunks;
 
   constexpr int kIters = (UFV_BITS_WORDS * 32 + kPatchThreads - 1) / kPatchThreads;
   bool on[kIters];
@@ -249,10 +268,10 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
       if (p < n_patch) {
         const int i = p / n_out, jx = p - i * n_out;
         const int ra = h0[i], rb = h1[i], ca = w0[jx], cb = w1[jx];
-        const bool t00 = (ra >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + ca, d.dtype);
-        const bool t01 = (ra >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(ra) * d.pitch + cb, d.dtype);
-        const bool t10 = (rb >= 0 && ca >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + ca, d.dtype);
-        const bool t11 = (rb >= 0 && cb >= 0) && mask_positive(d.addr, int64_t(rb) * d.pitch + cb, d.dtype);
+        const bool t00 = (ra >= 0 && ca >= 0) && tap_positive(d, ra, ca);
+        const bool t01 = (ra >= 0 && cb >= 0) && tap_positive(d, ra, cb);
+        const bool t10 = (rb >= 0 && ca >= 0) && tap_positive(d, rb, ca);
+        const bool t11 = (rb >= 0 && cb >= 0) && tap_positive(d, rb, cb);
         on[it] = t00 | t01 | t10 | t11;
       }
     }

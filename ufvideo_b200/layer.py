@@ -325,7 +325,7 @@ class MaskExtractor(nn.Module):
         if two:                                   # the reference's depth=2 projector: one chained call
             epoch = plan.epoch = plan.epoch % 32767 + 1            # 1 .. 32767, the tag of this call's counts
             graph = None
-            if _awaited and USE_CUDA_GRAPH and q > 0 and plan.n_obj > 0 and m_pad > 0:
+            if _awaited and USE_CUDA_GRAPH and dt != _cabi.UFV_F32 and q > 0 and plan.n_obj > 0 and m_pad > 0:
                 # A caller that waits for the counts before its next call (forward, forward_padded) lets
                 # the launch sequence be replayed as a CUDA graph: the per-call values travel through the
                 # pinned block (kernel 1 forwards it to the device), everything else is constant.

@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, rle as _rle
 
 _MASK_DTYPES = {torch.uint8: _cabi.UFV_U8, torch.bool: _cabi.UFV_U8, torch.float32: _cabi.UFV_F32,
                 torch.bfloat16: _cabi.UFV_BF16, torch.float16: _cabi.UFV_F16}
@@ -25,7 +25,7 @@ FEAT_DTYPES = {torch.float32: _cabi.UFV_F32, torch.bfloat16: _cabi.UFV_BF16, tor
 
 # mirror of struct ufv_mask_desc (include/ufv_b200.h), 32 bytes
 MASK_DESC = np.dtype([("addr", "<u8"), ("pitch", "<i4"), ("dtype", "<i4"), ("tap_off", "<i4"),
-                      ("group", "<i4"), ("flags", "<i4"), ("reserved", "<i4")])
+                      ("group", "<i4"), ("flags", "<i4"), ("aux", "<i4")])
 assert MASK_DESC.itemsize == 32
 
 # A pinned host mask tensor is not copied: kernel 1 reads it through its mapped device address and
@@ -72,11 +72,46 @@ class EncodePlan:
     counts_np: np.ndarray | None = None           # numpy view of counts_pinned[:n_obj]
     counts_pinned: torch.Tensor | None = None     # pinned int32 [n_obj]: early read-back of the counts
     counts_dev_addr: int = 0                      # device-visible address of counts_pinned
+    keepalive: object = None                      # run-length sample buffers of the last call
+    rle_rows: list = field(default_factory=list)  # run-length samples: descriptor rows refreshed on every call
     cache_key: object = None                      # key under which the plan sits in the plan cache
     any_row_mode: int = 0                         # some descriptor asks for row mode (kernel 1 variant)
     epoch: int = 0                                # tag of the last call's counts words (1 .. 32767)
     expect_counts: list = field(default_factory=list)
     slots_bytes: bytes = b""                      # ``slots`` as bytes: the no-ties fast comparison
+
+
+class RleSample:
+    """One sample's masks given as COCO run-length dicts (ufvideo_b200/rle.py), uploaded as the int32
+    cumulative run ends of all its object-frames back to back.  Quacks like a mask tensor as far as the
+    packer needs; per-mask run counts and offsets replace the uniform row pitch / plane stride."""
+
+    dtype = "rle"
+
+    def __init__(self, rles, device):
+        parts = [_rle.run_ends(r) for r in rles]
+        sizes = {(h, w) for h, w, _ in parts}
+        if len(sizes) != 1:
+            raise ValueError("all run-length masks of one sample must share one image size")
+        (h, w), = sizes
+        self.shape = (len(parts), h, w)
+        self.n_runs = np.asarray([p[2].size for p in parts], dtype=np.int32)
+        self.run_off = np.concatenate([[0], np.cumsum(self.n_runs)[:-1]]).astype(np.int64)
+        ends = np.concatenate([p[2] for p in parts] + [np.zeros(1, np.int32)])      # never empty
+        staging = torch.from_numpy(ends)
+        if device.type == "cuda":
+            staging = staging.pin_memory()
+        self.buf = staging.to(device, non_blocking=True)
+        self.device = self.buf.device
+
+    def data_ptr(self):
+        return self.buf.data_ptr()
+
+    def stride(self, dim=None):
+        return ("rle",) if dim is None else 1
+
+    def element_size(self):
+        return 4
 
 
 def _as_mask_list(masks, device):
@@ -85,6 +120,9 @@ def _as_mask_list(masks, device):
     out = []
     for i in range(len(masks)):
         m = masks[i]
+        if isinstance(m, RleSample) or _rle.is_rle_sample(m):        # COCO run-length masks, never densified
+            out.append(m if isinstance(m, RleSample) else RleSample(m, device))
+            continue
         if not torch.is_tensor(m):
             m = torch.as_tensor(m)
         shape = m.shape
@@ -108,7 +146,7 @@ def _as_mask_list(masks, device):
 def _device_address(m: torch.Tensor) -> int:
     """Address kernel 1 reads the mask at: the tensor's own pointer on the device, the mapped
     device alias of a pinned host tensor otherwise (the kernel then reads it in place over PCIe)."""
-    if m.device.type != "cpu" or not m.is_pinned():
+    if isinstance(m, RleSample) or m.device.type != "cpu" or not m.is_pinned():
         return m.data_ptr()
     dev = ctypes.c_uint64(0)
     _cabi.check(_cabi.lib().ufv_device_address(ctypes.c_void_p(m.data_ptr()), ctypes.byref(dev)))
@@ -165,8 +203,8 @@ def _lookup_or_build(masks, ann_indices, ann_bytes, n_feat_rows, k_keep, device,
         plan = _plan_cache.get(key)
         if plan is not None:
             _plan_cache.move_to_end(key)
-            if plan.base_ptrs != ptrs:           # same structure, new mask tensors: patch addresses
-                _patch_addresses(plan, ptrs, device)
+            if plan.base_ptrs != ptrs or plan.rle_rows:   # same structure, new mask data: patch descriptors
+                _patch_addresses(plan, ptrs, device, masks)
             return plan
     plan = _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, ptrs)
     plan.cache_key = key
@@ -178,7 +216,8 @@ def _lookup_or_build(masks, ann_indices, ann_bytes, n_feat_rows, k_keep, device,
 
 
 def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, ptrs) -> EncodePlan:
-    pitch, dtype_id, tap_off, sample_of, plane_off, rows_all = [], [], [], [], [], []
+    pitch, dtype_id, tap_off, sample_of, plane_off, rows_all, aux = [], [], [], [], [], [], []
+    rle_rows = []                                # (sample, its descriptor rows, the mask plane of each row)
     taps, tap_chunks, tap_len = {}, [], 0
     obj_start, obj_len = [], []
     base = 0
@@ -202,10 +241,18 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
             else:
                 raise ValueError(f"sample {i}: {b} feature rows cannot pair with {q} masks")
         n_i = len(rows)
-        plane_off.append(planes * (m.stride(0) * esize))
         sample_of.append(np.full(n_i, i, dtype=np.int32))
-        pitch.append(np.full(n_i, m.stride(1), dtype=np.int32))
-        dtype_id.append(np.full(n_i, _MASK_DTYPES[m.dtype], dtype=np.int32))
+        if isinstance(m, RleSample):             # per-mask run count / offset instead of pitch / plane stride
+            rle_rows.append((i, np.arange(base, base + n_i), planes))
+            plane_off.append(m.run_off[planes] * 4)
+            pitch.append(m.n_runs[planes])
+            dtype_id.append(np.full(n_i, _cabi.UFV_RLE, dtype=np.int32))
+            aux.append(np.full(n_i, h, dtype=np.int32))
+        else:
+            plane_off.append(planes * (m.stride(0) * esize))
+            pitch.append(np.full(n_i, m.stride(1), dtype=np.int32))
+            dtype_id.append(np.full(n_i, _MASK_DTYPES[m.dtype], dtype=np.int32))
+            aux.append(np.zeros(n_i, dtype=np.int32))
         tap_off.append(np.full(n_i, toff, dtype=np.int32))
         rows_all.append(np.asarray(rows, dtype=np.int64))
         start = 0
@@ -245,7 +292,8 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
     desc["dtype"] = cat(dtype_id, np.int32)
     desc["tap_off"] = cat(tap_off, np.int32)
     desc["group"] = group_of
-    on_host = np.asarray([m.device.type == "cpu" for m in masks], dtype=bool)
+    desc["aux"] = cat(aux, np.int32)
+    on_host = np.asarray([m.device.type == "cpu" and not isinstance(m, RleSample) for m in masks], dtype=bool)
     rows_mode = on_host[plan_sample] if READ_MODE == "auto" else np.full(q_total, READ_MODE == "rows")
     desc["flags"] = rows_mode.astype(np.int32)
     any_row_mode = int(rows_mode.any())
@@ -270,22 +318,28 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
                       m_pad=int(slots.sum()), slots=slots, host=host,
                       sample_of=cat(sample_of, np.int32), plane_off=cat(plane_off, np.int64),
                       expect_counts=[int(s) for s in slots], slots_bytes=slots.tobytes(),
-                      any_row_mode=any_row_mode)
+                      any_row_mode=any_row_mode, rle_rows=rle_rows)
     plan.ticket = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)   # self-resetting
     _fill_addresses(plan, ptrs)
+    plan.keepalive = masks if rle_rows else None
     _upload(plan, device)
     return plan
 
 
-def _fill_addresses(plan: EncodePlan, ptrs) -> None:
+def _fill_addresses(plan: EncodePlan, ptrs, masks=None) -> None:
+    if masks is not None:
+        for i, rows, planes in plan.rle_rows:    # run-length data changes with every call
+            plan.plane_off[rows] = masks[i].run_off[planes] * 4
+            plan.host["mask_desc"]["pitch"][rows] = masks[i].n_runs[planes]
     if plan.n_masks:
         base = np.asarray(ptrs, dtype=np.uint64)
         plan.host["mask_desc"]["addr"] = base[plan.sample_of] + plan.plane_off.astype(np.uint64)
     plan.base_ptrs = tuple(ptrs)
 
 
-def _patch_addresses(plan: EncodePlan, ptrs, device) -> None:
-    _fill_addresses(plan, ptrs)
+def _patch_addresses(plan: EncodePlan, ptrs, device, masks=None) -> None:
+    _fill_addresses(plan, ptrs, masks)
+    plan.keepalive = masks                       # run-length buffers must outlive the launches that read them
     desc = plan.host["mask_desc"]
     staging = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy())
     if device.type == "cuda":
