@@ -129,6 +129,15 @@ int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, int n_patch
                   const uint8_t* grp_omask, int n_groups, int max_group, float* pooled_out,
                   void* stream);
 
+/* Adjoint of ufv_mask_pool w.r.t. the features (training; the reference gets it from autograd through
+ * layer.py:98-104,145-147).  w fp32 [n_masks, c] = d_pooled / (cnt + 1e-8); the object-frames that pool
+ * from feature row r are row_member[row_off[r] .. row_off[r+1]) (at most max_members per row);
+ * d_feats [n_rows, n_patch, c] of feat_dtype is written completely (rows nobody pools from: zeros):
+ *   d_feats[r, p, :] = sum over those object-frames j with patch p on (bits) of w[j, :]. */
+int ufv_mask_pool_backward(const float* w, const uint32_t* bits, const int32_t* row_off,
+                           const int32_t* row_member, int64_t n_rows, int max_members, int n_patch, int c,
+                           void* d_feats, int feat_dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Kernel 3: fused temporal token merge.  Replaces token_merge (layer.py:6-33), its dispatch
  * (layer.py:110-119) and the downcast (layer.py:123).

@@ -80,6 +80,7 @@ _SIGNATURES = {
                                       _p, _p, _p]),
     "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_int,
                                 C.c_int, _p, _p]),
+    "ufv_mask_pool_backward": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p]),
     "ufv_ttm": (C.c_int, [_p, C.c_int, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p,
                           _p, C.c_int, _p, C.c_int, _p, _i32, _p]),
     "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),

@@ -521,9 +521,10 @@ class _PoolMerge(torch.autograd.Function):
     """Kernels 1-3 as one differentiable op: feats -> merged tokens [m_pad, C] (model dtype).
 
     Forward runs the CUDA kernels.  Backward (training parity) is the exact adjoint
-    of the forward arithmetic -- run means, masked mean -- written with plain torch ops for now: the
-    merge decisions are piecewise constant, exactly as under the reference's own autograd (its
-    comparisons and topk carry no gradient either, layer.py:17-27)."""
+    of the forward arithmetic: the run means with a few small torch index ops, the masked mean -- the
+    part that touches a tensor the size of the features -- with ``ufv_mask_pool_backward``.  The merge
+    decisions are piecewise constant, exactly as under the reference's own autograd (its comparisons
+    and topk carry no gradient either, layer.py:17-27)."""
 
     @staticmethod
     def forward(ctx, feats, plan, k_keep, out_dtype):
@@ -564,21 +565,23 @@ class _PoolMerge(torch.autograd.Function):
         d_pooled[pooled_row] = d_merged.float()[token_row] / run_size[token_row][:, None]
         # masked mean: pooled[j] = sum_{p on} feats[row_j, p] / (cnt_j + 1e-8)
         denorm = cnt.float() + 1e-8
-        w = d_pooled / denorm[:, None]
-        frame_row = torch.empty(q, dtype=torch.long)
+        w = (d_pooled / denorm[:, None]).contiguous()
+        # adjoint of the masked mean: one streaming kernel writes d_feats (ufv_mask_pool_backward)
         go, gm, gr = h["grp_off"], h["grp_member"], h["grp_row"]
+        n_rows, n_patch, c = ctx.feat_shape
+        frame_of = np.empty(q, dtype=np.int64)
         for g in range(plan.n_groups):
-            frame_row[gm[go[g]:go[g + 1]]] = int(gr[g])
-        frame_row = frame_row.to(dev)
-        n_patch = ctx.feat_shape[1]
-        p_idx = torch.arange(n_patch, device=dev)
-        d_feats = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
-        bw = bits.view(q, -1).to(torch.int64) & 0xffffffff
-        for j0 in range(0, q, 32):                                            # bounded temporaries
-            j1 = min(q, j0 + 32)
-            on = ((bw[j0:j1][:, p_idx // 32] >> (p_idx % 32)) & 1).to(torch.float32)   # [b, n_patch]
-            d_feats.index_add_(0, frame_row[j0:j1], on[:, :, None] * w[j0:j1][:, None, :])
-        return d_feats.to(ctx.feat_dtype), None, None, None
+            frame_of[gm[go[g]:go[g + 1]]] = int(gr[g])
+        order = np.argsort(frame_of, kind="stable").astype(np.int32)          # object-frames grouped by feature row
+        per_row = np.bincount(frame_of, minlength=n_rows)
+        row_off = np.concatenate([[0], np.cumsum(per_row)]).astype(np.int32)
+        meta = torch.from_numpy(np.concatenate([row_off, order])).to(dev)
+        d_feats = torch.empty(ctx.feat_shape, dtype=ctx.feat_dtype, device=dev)
+        _cabi.check(_cabi.lib().ufv_mask_pool_backward(
+            w.data_ptr(), bits.data_ptr(), meta.data_ptr(), meta.data_ptr() + 4 * row_off.size,
+            n_rows, int(per_row.max()) if q else 0, n_patch, c, d_feats.data_ptr(),
+            packer.FEAT_DTYPES[ctx.feat_dtype], _stream_ptr(dev)))
+        return d_feats, None, None, None
 
 
 def build_region_encoder(config, image_aspect_ratio):
