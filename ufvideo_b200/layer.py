@@ -243,7 +243,12 @@ class MaskExtractor(nn.Module):
 
     # -- helpers -------------------------------------------------------------------------------
     def _linears(self):
-        return [m for m in self.feat_linear if isinstance(m, nn.Linear)]
+        cached = self.__dict__.get("_lin_cache")
+        if cached is None or cached[0] is not self.feat_linear or cached[1] != len(self.feat_linear):
+            cached = (self.feat_linear, len(self.feat_linear),
+                      [m for m in self.feat_linear if isinstance(m, nn.Linear)])
+            self.__dict__["_lin_cache"] = cached
+        return cached[2]
 
     def encode_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None, _awaited=False):
         """Kernels 1-4 without the host read-back: returns (tokens [m_pad, hid], counts int32

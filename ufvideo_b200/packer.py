@@ -153,23 +153,25 @@ def _device_address(m: torch.Tensor) -> int:
     return int(dev.value)
 
 
+def _same_indices(a, b) -> bool:
+    try:
+        return bool(a == b)
+    except Exception:   # noqa: BLE001 -- e.g. tensors inside the lists: take the slow path
+        return False
+
+
 _last_call: list = [None]     # (mask tensor objects, their data_ptrs and shapes, scalar args, ann bytes, plan)
 
 
 def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_square: bool = False,
                n_out: int = _cabi.MAX_PATCH_SIDE, use_cache: bool = True) -> EncodePlan:
     # Fastest path: the very same mask tensor objects (same storage, same shape) and the same index
-    # content as the previous call -> the previous plan, without re-deriving any descriptor.
+    # content as the previous call -> the previous plan, without re-deriving any descriptor.  The index
+    # lists are compared by value against a private copy (a nested list compare runs at C speed).
     last = _last_call[0]
     scalars = (n_feat_rows, k_keep, bool(pad_square), n_out, device, READ_MODE)
-    ann_bytes = None
-    if use_cache:
-        try:                                     # lists of python ints: one C-speed serialisation
-            ann_bytes = marshal.dumps(ann_indices)
-        except ValueError:                       # numpy / tensor scalars inside
-            ann_bytes = None
-    if (last is not None and ann_bytes is not None and last[3] == ann_bytes and last[2] == scalars
-            and len(masks) == len(last[0])):
+    if (use_cache and last is not None and last[2] == scalars and len(masks) == len(last[0])
+            and _same_indices(ann_indices, last[3])):
         same = True
         for m, (obj, ptr, shape) in zip(masks, last[0]):
             if m is not obj or m.data_ptr() != ptr or m.shape != shape:
@@ -177,11 +179,18 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
                 break
         if same and _plan_cache.get(last[4].cache_key) is last[4]:
             return last[4]
+    ann_bytes = None
+    if use_cache:
+        try:                                     # lists of python ints: one C-speed serialisation
+            ann_bytes = marshal.dumps(ann_indices)
+        except ValueError:                       # numpy / tensor scalars inside
+            ann_bytes = None
     plan = _lookup_or_build(masks, ann_indices, ann_bytes, n_feat_rows, k_keep, device, pad_square, n_out,
                             use_cache)
     if use_cache and ann_bytes is not None and torch.is_tensor(masks) is False:
         try:
-            _last_call[0] = ([(m, m.data_ptr(), m.shape) for m in masks], None, scalars, ann_bytes, plan)
+            _last_call[0] = ([(m, m.data_ptr(), m.shape) for m in masks], None, scalars,
+                             marshal.loads(ann_bytes), plan)
         except AttributeError:                   # non-tensor mask entries: no identity fast path
             _last_call[0] = None
     return plan
