@@ -336,7 +336,8 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
-    with ClockSampler(local, enabled=rank == 0) as clocks:
+    # the reference runs the model under torch.inference_mode() (ufvideo/__init__.py:122)
+    with ClockSampler(local, enabled=rank == 0) as clocks, torch.inference_mode():
         ms_step = timed(step_resident, a.steps, max(a.warmup, 3))
         ms_e2e = timed(step_e2e, a.steps, max(a.warmup, 3))
     clock_summary = clocks.summary()

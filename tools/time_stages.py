@@ -75,6 +75,30 @@ def main():
     res["k3 ttm"] = timed(lambda: layer.ttm(pooled, plan, a.k, dt))
     res["k4a linear1+gelu"] = timed(lambda: layer.linear(merged, l0.weight, l0.bias, True))
     res["k4b linear2"] = timed(lambda: layer.linear(hid, l2.weight, l2.bias, False))
+    # "next" rows: device-side <region> splice and the pool adjoint (training)
+    n_text = 2048
+    text = torch.randn((n_text, 3584), device=dev).to(dt)
+    pos = torch.arange(plan.n_obj, dtype=torch.int32, device=dev) * (n_text // max(plan.n_obj, 1))
+    tok_pad, cnt_dev, _ = enc.encode_padded(ft, md, ann)
+    res["splice (f1)"] = timed(lambda: layer.splice_regions(text, pos, tok_pad, cnt_dev, plan))
+    w_adj = torch.randn((q, 1152), device=dev)
+    go, gm, gr = plan.host["grp_off"], plan.host["grp_member"], plan.host["grp_row"]
+    frame_of = np.empty(q, dtype=np.int64)
+    for g in range(plan.n_groups):
+        frame_of[gm[go[g]:go[g + 1]]] = int(gr[g])
+    order = np.argsort(frame_of, kind="stable").astype(np.int32)
+    per_row = np.bincount(frame_of, minlength=ft.shape[0])
+    row_off = np.concatenate([[0], np.cumsum(per_row)]).astype(np.int32)
+    meta = torch.from_numpy(np.concatenate([row_off, order])).to(dev)
+    d_feats = torch.empty_like(ft)
+    from ufvideo_b200 import _cabi
+
+    def pool_bwd():
+        _cabi.check(_cabi.lib().ufv_mask_pool_backward(
+            w_adj.data_ptr(), bits.data_ptr(), meta.data_ptr(), meta.data_ptr() + 4 * row_off.size, ft.shape[0],
+            int(per_row.max()), 729, 1152, d_feats.data_ptr(), packer.FEAT_DTYPES[dt],
+            torch.cuda.current_stream(dev).cuda_stream))
+    res["pool adjoint (f3)"] = timed(pool_bwd)
     res["torch linear1"] = timed(lambda: torch.nn.functional.linear(merged, l0.weight, l0.bias))
     res["torch linear2"] = timed(lambda: torch.nn.functional.linear(hid, l2.weight, l2.bias))
     res["plan (host)"] = timed(lambda: packer.build_plan(md, ann, ft.shape[0], a.k, dev))
@@ -89,6 +113,12 @@ def main():
         fl = 2.0 * m * k_ * n_
         print(f"{name}: {fl/res[name][0]/1e6:.1f} TFLOP/s   weight-bytes bound {n_*k_*2/res[name][0]/1e3:.0f} GB/s")
     print(f"forward: {q/res['forward'][0]*1e6:.0f} object-frames/s")
+    t = res["pool adjoint (f3)"][0] * 1e-6
+    print(f"pool adjoint: writes {d_feats.numel() * d_feats.element_size() / 1e6:.0f} MB -> "
+          f"{d_feats.numel() * d_feats.element_size() / t / 1e9:.0f} GB/s")
+    t = res["splice (f1)"][0] * 1e-6
+    moved = 2 * (n_text - plan.n_obj + plan.m_pad) * 3584 * text.element_size()
+    print(f"splice: {moved / 1e6:.1f} MB read+written -> {moved / t / 1e9:.0f} GB/s")
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@ under "next" in DESIGN.md).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 
@@ -462,14 +463,23 @@ class MaskExtractor(nn.Module):
         run.setdefault("graph_args", []).append(g)
         return handle
 
+    def _on_module_device(self):
+        """Context that makes the module's GPU the current CUDA device (the C ABI launches on the current
+        device; torch ops guard themselves, raw launches do not).  A no-op in the common single-GPU case."""
+        dev = self.feat_linear[0].weight.device
+        if dev.type == "cuda" and torch.cuda.current_device() != dev.index:
+            return torch.cuda.device(dev)
+        return contextlib.nullcontext()
+
     def forward_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None):
         """forward() without the compaction: (tokens [m_pad, hidden] with object o's rows at
         plan.host['slot_off'][o], region_token_nums as an int32 numpy array read back from the merge
         kernel, plan).  What the clip-sharded driver gathers (sharding.all_gather_payload)."""
-        tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, out, counts_out, peer, _awaited=True)
-        if plan.run.get("args") is not None and plan.n_obj > 0:
-            return tokens, _await_counts(plan, tokens.device), plan
-        return tokens, counts.cpu().numpy(), plan
+        with self._on_module_device():
+            tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, out, counts_out, peer, _awaited=True)
+            if plan.run.get("args") is not None and plan.n_obj > 0:
+                return tokens, _await_counts(plan, tokens.device), plan
+            return tokens, counts.cpu().numpy(), plan
 
     def _forward_with_grad(self, feats, masks, ann_indices):
         """Training path (the region encoder is trainable in the reference, videorefer_arch.py:94-96):
@@ -495,6 +505,14 @@ class MaskExtractor(nn.Module):
 
     # -- the reference's forward -----------------------------------------------------------------
     def forward(self, feats, masks, X_features, ann_indices, frame_nums):
+        """Same contract as layer.py:63-128: returns (mask_feats [N_tok, hidden], region_token_nums
+        list[int]).  ``X_features`` and ``frame_nums`` are accepted and ignored, as in the reference
+        (which reads only ``X_features.device`` in its fallbacks).  Under autograd with trainable
+        parameters or features the differentiable path runs (``_forward_with_grad``)."""
+        with self._on_module_device():
+            return self._forward_impl(feats, masks, ann_indices)
+
+    def _forward_impl(self, feats, masks, ann_indices):
         """Same contract as layer.py:63-128: returns (mask_feats [N_tok, hidden], region_token_nums
         list[int]).  ``X_features`` and ``frame_nums`` are accepted and ignored, as in the reference
         (which reads only ``X_features.device`` in its fallbacks).  Forward only: no autograd graph
