@@ -517,6 +517,36 @@ def test_region_splice_matches_the_reference_consumer_loop(dev):
     assert (src[:2] == [0, 1]).all() and src[2] == -1 and src[-1] == n_text - 1
 
 
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_pool_adjoint_kernel_against_dense_torch(dev, dtype):
+    """ufv_mask_pool_backward: rows with <= 8 object-frames (register path), a row with 17 (L1 path) and a
+    row nobody pools from (zeros), against d_feats[r, p] = sum_j on[j, p] * w[j] computed densely."""
+    from ufvideo_b200 import _cabi
+    g = synth.rng_for(4242)
+    n_rows, n_patch, c = 4, 729, 1152
+    frame_of = np.array([0] * 3 + [2] * 17 + [3] * 8, dtype=np.int64)          # row 1: nobody
+    q = frame_of.size
+    on = g.random((q, n_patch)) < 0.4
+    w = g.standard_normal((q, c), dtype=np.float32)
+    bits = torch.from_numpy(R.pack_bits(on).view(np.int32)).to(dev)
+    bits24 = torch.zeros((q, 24), dtype=torch.int32, device=dev)
+    bits24[:, :23] = bits
+    order = np.argsort(frame_of, kind="stable").astype(np.int32)
+    row_off = np.concatenate([[0], np.cumsum(np.bincount(frame_of, minlength=n_rows))]).astype(np.int32)
+    meta = torch.from_numpy(np.concatenate([row_off, order])).to(dev)
+    wt = torch.from_numpy(w).to(dev)
+    out = torch.full((n_rows, n_patch, c), 7.0, dtype=TORCH_DT[dtype], device=dev)
+    _cabi.check(_cabi.lib().ufv_mask_pool_backward(
+        wt.data_ptr(), bits24.data_ptr(), meta.data_ptr(), meta.data_ptr() + 4 * row_off.size, n_rows, 17, n_patch, c,
+        out.data_ptr(), packer.FEAT_DTYPES[TORCH_DT[dtype]], torch.cuda.current_stream(dev).cuda_stream))
+    want = torch.zeros((n_rows, n_patch, c), dtype=torch.float64, device=dev)
+    want.index_add_(0, torch.from_numpy(frame_of).to(dev),
+                    torch.from_numpy(on).to(dev).double()[:, :, None] * wt.double()[:, None, :])
+    tol = 1e-5 if dtype == "f32" else 0.08
+    assert (out.double() - want).abs().max().item() <= tol
+    assert not out[1].any()
+
+
 def test_training_path_gradients_match_the_reference_ops(dev):
     """With grad enabled and trainable parameters / features, forward() is differentiable: gradients of
     a scalar loss w.r.t. the projector weights and the features equal those of the reference's op

@@ -281,65 +281,86 @@ static int dispatch_group(int max_group, const CUtensorMap& tmap, int use_tmap, 
 // ---- adjoint of the mask pool (training) --------------------------------------------
 // pooled[j] = sum over on patches of feats[row_j, p] / denorm_j   =>
 // d_feats[row, p, :] = sum over object-frames j on that row with patch p on of w[j, :],  w = d_pooled / denorm.
-// One CTA per (feature row, 128-channel slice): the w slices and patch bitmasks of every object-frame on
-// the row are staged in shared memory, then the 729 output rows are streamed out once (an HBM write
-// stream the size of the feature tensor); rows nobody pools from are written as zeros, so the output
-// needs no memset.  The sum runs over the row's object-frames in plan order: deterministic.
-constexpr int kBwdThreads = 128;
+// One CTA per (feature row, range of 81 patches): a thread owns 4 channels of every patch row, so a CTA
+// writes whole 2304-byte rows back to back -- one contiguous 186 KB stretch of d_feats (the first version
+// wrote 256-byte pieces 2304 bytes apart and reached 2.5 TB/s).  The w values of up to 8 object-frames
+// live in registers; rows with more object-frames re-read w through L1.  Rows nobody pools from are
+// written as zeros, so the output needs no memset.  The sum runs in plan order: deterministic.
+constexpr int kBwdThreads = 288;       // x 4 channels = 1152
+constexpr int kBwdSplit = 9;           // patch ranges per feature row
+constexpr int kBwdRegMembers = 8;
+
+template <typename T>
+__device__ __forceinline__ void store_quad(T* dst, float4 v);
+template <> __device__ __forceinline__ void store_quad<float>(float* dst, float4 v) {
+  *reinterpret_cast<float4*>(dst) = v;
+}
+template <> __device__ __forceinline__ void store_quad<__nv_bfloat16>(__nv_bfloat16* dst, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+template <> __device__ __forceinline__ void store_quad<__half>(__half* dst, float4 v) {
+  const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kBwdThreads)
 mask_pool_backward_kernel(const float* __restrict__ w, const uint32_t* __restrict__ bits,
                           const int32_t* __restrict__ row_off, const int32_t* __restrict__ row_member,
-                          int n_patch, int c, int n_slices, T* __restrict__ d_feats) {
+                          int n_patch, int c, T* __restrict__ d_feats) {
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(dyn_smem);        // [n_mem][UFV_BITS_WORDS]
+  int32_t* s_member = reinterpret_cast<int32_t*>(dyn_smem) + 0;    // placed after the bits below
   pdl_wait();
   pdl_launch_dependents();
-  const int row = blockIdx.x / n_slices;
-  const int slice = blockIdx.x - row * n_slices;
-  const int ch0 = slice * kPoolCh;
+  const int row = blockIdx.x / kBwdSplit;
+  const int part = blockIdx.x - row * kBwdSplit;
+  const int per_part = (n_patch + kBwdSplit - 1) / kBwdSplit;
+  const int p_begin = part * per_part, p_end = min(n_patch, p_begin + per_part);
   const int m0 = row_off[row];
   const int n_mem = row_off[row + 1] - m0;
-  float4* s_w = reinterpret_cast<float4*>(dyn_smem);                       // [n_mem][32] float4 = 128 channels
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_w + size_t(n_mem) * 32);   // [n_mem][UFV_BITS_WORDS]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n_mem * 32; i += kBwdThreads) {
-    const int m = i >> 5, q4 = i & 31;
-    const int ch = ch0 + q4 * 4;
-    s_w[i] = ch < c ? *reinterpret_cast<const float4*>(w + size_t(row_member[m0 + m]) * c + ch)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  s_member = reinterpret_cast<int32_t*>(s_bits + size_t(n_mem) * UFV_BITS_WORDS);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_mem; i += kBwdThreads) s_member[i] = row_member[m0 + i];
   for (int i = tid; i < n_mem * UFV_BITS_WORDS; i += kBwdThreads)
     s_bits[i] = bits[size_t(row_member[m0 + i / UFV_BITS_WORDS]) * UFV_BITS_WORDS + i % UFV_BITS_WORDS];
   __syncthreads();
-  const int ch = ch0 + lane * 4;
-  if (ch >= c) return;
-  T* out = d_feats + size_t(row) * n_patch * c + ch;
-  for (int p = warp; p < n_patch; p += kBwdThreads / 32) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int word = p >> 5;
-    const uint32_t bit = 1u << (p & 31);
-    for (int m = 0; m < n_mem; ++m) {
-      if (s_bits[m * UFV_BITS_WORDS + word] & bit) {      // warp-uniform
-        const float4 v = s_w[m * 32 + lane];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  for (int ch = tid * 4; ch < c; ch += kBwdThreads * 4) {          // one pass for c <= 1152
+    T* out = d_feats + size_t(row) * n_patch * c + ch;
+    if (n_mem <= kBwdRegMembers) {
+      float4 wv[kBwdRegMembers];
+#pragma unroll
+      for (int m = 0; m < kBwdRegMembers; ++m)
+        wv[m] = m < n_mem ? *reinterpret_cast<const float4*>(w + size_t(s_member[m]) * c + ch)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = p_begin; p < p_end; ++p) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int word = p >> 5;
+        const uint32_t bit = 1u << (p & 31);
+#pragma unroll
+        for (int m = 0; m < kBwdRegMembers; ++m) {
+          if (m < n_mem && (s_bits[m * UFV_BITS_WORDS + word] & bit)) {      // CTA-uniform
+            acc.x += wv[m].x; acc.y += wv[m].y; acc.z += wv[m].z; acc.w += wv[m].w;
+          }
+        }
+        store_quad<T>(out + size_t(p) * c, acc);
       }
-    }
-    T* dst = out + size_t(p) * c;
-    if (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(dst) = acc;
     } else {
-      const uint32_t lo = Elem<T>::kDtype == UFV_BF16
-                              ? uint32_t(__bfloat16_as_ushort(__float2bfloat16_rn(acc.x))) |
-                                    (uint32_t(__bfloat16_as_ushort(__float2bfloat16_rn(acc.y))) << 16)
-                              : uint32_t(__half_as_ushort(__float2half_rn(acc.x))) |
-                                    (uint32_t(__half_as_ushort(__float2half_rn(acc.y))) << 16);
-      const uint32_t hi = Elem<T>::kDtype == UFV_BF16
-                              ? uint32_t(__bfloat16_as_ushort(__float2bfloat16_rn(acc.z))) |
-                                    (uint32_t(__bfloat16_as_ushort(__float2bfloat16_rn(acc.w))) << 16)
-                              : uint32_t(__half_as_ushort(__float2half_rn(acc.z))) |
-                                    (uint32_t(__half_as_ushort(__float2half_rn(acc.w))) << 16);
-      *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+      for (int p = p_begin; p < p_end; ++p) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int word = p >> 5;
+        const uint32_t bit = 1u << (p & 31);
+        for (int m = 0; m < n_mem; ++m) {
+          if (s_bits[m * UFV_BITS_WORDS + word] & bit) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(w + size_t(s_member[m]) * c + ch));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+        }
+        store_quad<T>(out + size_t(p) * c, acc);
+      }
     }
   }
 }
@@ -348,13 +369,12 @@ template <typename T>
 static int launch_pool_backward(const float* w, const uint32_t* bits, const int32_t* row_off,
                                 const int32_t* row_member, int64_t n_rows, int max_members, int n_patch, int c,
                                 void* d_feats, cudaStream_t stream) {
-  const int n_slices = (c + kPoolCh - 1) / kPoolCh;
-  const size_t smem = size_t(max_members > 0 ? max_members : 1) * (32 * sizeof(float4) + UFV_BITS_WORDS * 4);
+  const size_t smem = size_t(max_members > 0 ? max_members : 1) * (UFV_BITS_WORDS * 4 + 4);
   auto kernel = mask_pool_backward_kernel<T>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   return check_launch("ufv_mask_pool_backward",
-                      launch_kernel(kernel, dim3(unsigned(n_rows) * n_slices), dim3(kBwdThreads), smem, stream, w,
-                                    bits, row_off, row_member, n_patch, c, n_slices, static_cast<T*>(d_feats)));
+                      launch_kernel(kernel, dim3(unsigned(n_rows) * kBwdSplit), dim3(kBwdThreads), smem, stream, w,
+                                    bits, row_off, row_member, n_patch, c, static_cast<T*>(d_feats)));
 }
 
 }  // namespace ufv
@@ -368,11 +388,10 @@ extern "C" int ufv_mask_pool_backward(const float* w, const uint32_t* bits, cons
   UFV_REQUIRE(w && bits && row_off && row_member && d_feats, UFV_E_NULL, "ufv_mask_pool_backward: null pointer");
   UFV_REQUIRE(n_patch >= 1 && n_patch <= UFV_MAX_PATCH_SIDE * UFV_MAX_PATCH_SIDE && c >= 8 && c % 8 == 0,
               UFV_E_SHAPE, "ufv_mask_pool_backward: n_patch=%d c=%d", n_patch, c);
-  UFV_REQUIRE(max_members <= 300, UFV_E_SHAPE, "ufv_mask_pool_backward: %d object-frames on one feature row",
+  UFV_REQUIRE(max_members <= 2000, UFV_E_SHAPE, "ufv_mask_pool_backward: %d object-frames on one feature row",
               max_members);
   UFV_REQUIRE(aligned16(w) && aligned16(d_feats), UFV_E_ALIGN, "ufv_mask_pool_backward: unaligned buffer");
-  UFV_REQUIRE(n_rows * ((c + kPoolCh - 1) / kPoolCh) < (int64_t(1) << 31), UFV_E_SHAPE,
-              "ufv_mask_pool_backward: grid too large");
+  UFV_REQUIRE(n_rows * kBwdSplit < (int64_t(1) << 31), UFV_E_SHAPE, "ufv_mask_pool_backward: grid too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (feat_dtype) {
     case UFV_F32: return launch_pool_backward<float>(w, bits, row_off, row_member, n_rows, max_members, n_patch, c, d_feats, st);
