@@ -81,6 +81,63 @@ __device__ __forceinline__ bool tap_positive(const ufv_mask_desc& d, int r, int 
   return mask_positive(d.addr, int64_t(r) * d.pitch + c, d.dtype);
 }
 
+// Tap mode for one dense element type: all 4 * ITERS tap loads of a thread are issued back to back (invalid
+// taps read element 0 and are masked afterwards), so the thread waits for ONE memory round trip instead of
+// one per tap -- with the dtype switch inside the tap the compiler serialised them (r01d: 65 % of the
+// kernel's stall samples sat on the compares behind the individual loads).
+template <typename E> __device__ __forceinline__ bool elem_positive(E v);
+template <> __device__ __forceinline__ bool elem_positive<uint8_t>(uint8_t v) { return v != 0; }
+template <> __device__ __forceinline__ bool elem_positive<float>(float v) { return v > 0.0f; }
+template <> __device__ __forceinline__ bool elem_positive<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v) > 0.0f;
+}
+template <> __device__ __forceinline__ bool elem_positive<__half>(__half v) { return __half2float(v) > 0.0f; }
+
+template <typename E> __device__ __forceinline__ uint32_t elem_bits(E v);
+template <> __device__ __forceinline__ uint32_t elem_bits<uint8_t>(uint8_t v) { return v; }
+template <> __device__ __forceinline__ uint32_t elem_bits<float>(float v) { return __float_as_uint(v); }
+template <> __device__ __forceinline__ uint32_t elem_bits<__nv_bfloat16>(__nv_bfloat16 v) {
+  return uint32_t(__bfloat16_as_ushort(v)) << 16;      // bf16 -> the fp32 with the same value
+}
+template <> __device__ __forceinline__ uint32_t elem_bits<__half>(__half v) { return __float_as_uint(__half2float(v)); }
+template <typename E> __device__ __forceinline__ bool bits_positive(uint32_t b) { return __uint_as_float(b) > 0.0f; }
+template <> __device__ __forceinline__ bool bits_positive<uint8_t>(uint32_t b) { return b != 0u; }
+
+template <typename E, int ITERS, int THREADS>
+__device__ __forceinline__ void gather_taps(const ufv_mask_desc& d, const int32_t* h0, const int32_t* h1,
+                                            const int32_t* w0, const int32_t* w1, int n_out, int n_patch, int tid,
+                                            bool (&on)[ITERS]) {
+  static_assert(ITERS <= 3, "the register fence below lists 12 values");
+  const E* __restrict__ base = reinterpret_cast<const E*>(d.addr);
+  uint32_t v[3][4] = {};
+  uint32_t ok = 0;                                        // bit 4 * it + t
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int p = it * THREADS + tid;
+    const bool live = p < n_patch;
+    const int i = live ? p / n_out : 0, jx = live ? p - i * n_out : 0;
+    const int r[2] = {h0[i], h1[i]}, c[2] = {w0[jx], w1[jx]};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int rr = r[t >> 1], cc = c[t & 1];
+      const bool valid = live && rr >= 0 && cc >= 0;
+      ok |= uint32_t(valid) << (4 * it + t);
+      v[it][t] = elem_bits<E>(base[valid ? int64_t(rr) * d.pitch + cc : int64_t(0)]);
+    }
+  }
+  // register fence: every load above is issued before any compare below (ptxas otherwise interleaves them
+  // three at a time and the thread pays four memory round trips instead of one)
+  asm volatile("" : "+r"(v[0][0]), "+r"(v[0][1]), "+r"(v[0][2]), "+r"(v[0][3]), "+r"(v[1][0]), "+r"(v[1][1]),
+                    "+r"(v[1][2]), "+r"(v[1][3]), "+r"(v[2][0]), "+r"(v[2][1]), "+r"(v[2][2]), "+r"(v[2][3]));
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) any |= ((ok >> (4 * it + t)) & 1u) && bits_positive<E>(v[it][t]);
+    on[it] = any;
+  }
+}
+
 // "element > 0" flags of one 16-byte chunk, bit e = element e of the chunk
 __device__ __forceinline__ uint32_t chunk_flags(uint4 v, int dtype) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -140,7 +197,7 @@ constexpr int kRowUnroll = 4;                    // chunk loads in flight per th
 // CTA, so resident CTAs are what hides it).
 template <bool ROWS> struct PatchCfg {
   static constexpr int kThreads = ROWS ? 384 : 256;
-  static constexpr int kMinCtas = ROWS ? 4 : 8;
+  static constexpr int kMinCtas = ROWS ? 4 : 5;   // 5 x 256 threads: 51 registers, room for 12 tap loads in flight
   static constexpr int kFlagRows = ROWS ? 2 * UFV_MAX_PATCH_SIDE : 1;
   static constexpr int kFlagCols = ROWS ? kRowChunks : 1;
 };
@@ -260,9 +317,17 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
       }
       on[it] = hit;
     }
-  } else {
+  } else if (d.dtype == UFV_F32) {
+    gather_taps<float, kIters, kPatchThreads>(d, h0, h1, w0, w1, n_out, n_patch, tid, on);
+  } else if (d.dtype == UFV_U8) {
+    gather_taps<uint8_t, kIters, kPatchThreads>(d, h0, h1, w0, w1, n_out, n_patch, tid, on);
+  } else if (d.dtype == UFV_BF16) {
+    gather_taps<__nv_bfloat16, kIters, kPatchThreads>(d, h0, h1, w0, w1, n_out, n_patch, tid, on);
+  } else if (d.dtype == UFV_F16) {
+    gather_taps<__half, kIters, kPatchThreads>(d, h0, h1, w0, w1, n_out, n_patch, tid, on);
+  } else {                                  // run-length masks: one binary search per tap
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {   // every tap of every iteration is in flight before the ballots
+    for (int it = 0; it < kIters; ++it) {
       const int p = it * kPatchThreads + tid;
       on[it] = false;
       if (p < n_patch) {
