@@ -212,6 +212,17 @@ void* tensor_map_encoder() {
   return fn;
 }
 
+// L2 promotion of the tiled loads: 256 B by default; UFV_TMAP_L2PROMO=0|64|128|256 overrides (developer sweeps).
+static CUtensorMapL2promotion l2_promotion() {
+  static const CUtensorMapL2promotion v = [] {
+    const char* e = getenv("UFV_TMAP_L2PROMO");
+    const int n = e ? atoi(e) : 256;
+    return n == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : n == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+           : n == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }();
+  return v;
+}
+
 // 2-D row-major [rows, cols] tensor map with a [box_rows, box_cols] box.  Encoding costs about a
 // microsecond of host time and the same few maps (features, tokens, weights) come back call after
 // call, so the last few are kept in a small per-thread table keyed by every encode parameter.
@@ -242,7 +253,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t r
   const CUresult r = encode(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE,
                             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(UFV_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
   e = Entry{base, rows, cols, box_rows, box_cols, dtype, swizzle128, true, *map};
   return 0;

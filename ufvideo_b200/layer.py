@@ -7,8 +7,10 @@ Same names, constructor, forward signature, parameter names and return types as 
 and ``videorefer_arch.py:236`` (call).  All arithmetic runs in the hand-written sm_100a kernels
 of ``libufv_b200.so`` through the C ABI in ``include/ufv_b200.h``; PyTorch only owns device
 memory and the stream.  There is no CPU or eager fallback: tensors must end up on a CUDA device
-and the shared library must be built.  Forward / inference only (the backward pass is listed
-under "next" in DESIGN.md).
+and the shared library must be built.  Under ``torch.no_grad()`` / ``inference_mode`` the fused
+inference path runs (one C call, replayed as a CUDA graph when a batch structure repeats); with
+autograd on and trainable parameters or features, a differentiable path runs instead
+(``_PoolMerge`` + the projector under torch autograd).
 """
 from __future__ import annotations
 

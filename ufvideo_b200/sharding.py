@@ -245,7 +245,7 @@ class PeerGather:
     def wait(self, step: int) -> None:
         """Make the current stream wait until every rank's rows of ``step`` are in this rank's copy."""
         slot = step % self.ring
-        rc = self._wait_fn(self._flags_ptr + slot * self.world * 4, self.world, step + 1, 0, self._timed_out_ptr,
+        rc = self._wait_fn(self._flags_ptr + slot * self.world * 4, self.world, step + 1, 10000, self._timed_out_ptr,
                            torch._C._cuda_getCurrentRawStream(self.device.index))
         if rc:
             _cabi.check(rc)
