@@ -171,25 +171,62 @@ def run_reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
+def _parse_cpu_list(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _topo_cpu_affinity(gpu_index: int):
+    """CPU affinity of a GPU as `nvidia-smi topo -m` reports it (works where sysfs hides the NUMA node)."""
+    out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    header = None
+    for line in out.splitlines():
+        cols = [c.strip() for c in line.split("\t") if c.strip()]
+        if not cols:
+            continue
+        if header is None and any("CPU Affinity" in c for c in cols):
+            header = cols
+            continue
+        if header is not None and cols[0] == f"GPU{gpu_index}":
+            # data rows carry one more leading column (the row label) than the header
+            idx = next(i for i, c in enumerate(header) if "CPU Affinity" in c) + 1
+            if idx < len(cols) and cols[idx][0].isdigit():
+                return _parse_cpu_list(cols[idx])
+    return None
+
+
 def bind_to_gpu_numa_node(local: int) -> str:
-    """Pin this rank (and therefore its first-touch pinned host buffers) to the CPUs of the NUMA node its
-    GPU hangs off: with one process per GPU the H2D stream then never crosses the socket interconnect."""
+    """Pin this rank (and therefore its first-touch pinned host buffers) to the CPUs next to its GPU: with one
+    process per GPU the H2D stream then never crosses the socket interconnect."""
     try:
         import torch
         prop = torch.cuda.get_device_properties(local)
         bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
-        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
-        if node < 0:
-            return "numa: single node"
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus, how = None, ""
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+            if node >= 0:
+                cpus = _parse_cpu_list(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+                how = f"sysfs node {node}"
+        except OSError:
+            pass
+        if cpus is None:
+            cpus = _topo_cpu_affinity(local)
+            how = "nvidia-smi topo"
+        if not cpus:
+            return "numa: no affinity information"
         allowed = cpus & os.sched_getaffinity(0)
         if not allowed:
-            return f"numa: node {node} has no allowed cpu"
+            return f"numa: {how}: no allowed cpu"
+        if allowed == os.sched_getaffinity(0):
+            return f"numa: {how}: all {len(allowed)} cpus are local"
         os.sched_setaffinity(0, allowed)
-        return f"numa: rank bound to node {node} ({len(allowed)} cpus)"
+        return f"numa: rank bound to {len(allowed)} cpus ({how})"
     except Exception as exc:   # noqa: BLE001 -- binding is an optimisation, never a requirement
         return f"numa: not bound ({type(exc).__name__})"
 
