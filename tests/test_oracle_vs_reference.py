@@ -49,3 +49,46 @@ def test_oracle_decisions_equal_reference_on_fresh_random_objects():
         want = ref.token_merge(torch.from_numpy(x)[None], t - k)[0].numpy()
         tok, cut, _ = R.token_merge(x, k)
         assert tok.shape == want.shape and np.abs(tok - want).max() <= 1e-5
+
+
+def _coherent_tokens(family, t, g):
+    base = g.standard_normal(1152, dtype=np.float32)
+    if family == "static":
+        return (base + 1e-3 * g.standard_normal((t, 1152), dtype=np.float32)).astype(np.float32)
+    if family == "walk":
+        return (base + np.cumsum(0.05 * g.standard_normal((t, 1152), dtype=np.float32), 0)).astype(np.float32)
+    return np.repeat(g.standard_normal((t // 4 + 1, 1152), dtype=np.float32), 4, 0)[:t].astype(np.float32)
+
+
+@pytest.mark.parametrize("family", ["walk", "static", "duplicates"])
+def test_coherent_families_agree_or_are_ulp_ambiguous(family, capsys):
+    """where adjacent tokens are nearly parallel the reference's own merge decisions
+    hinge on ATen's fp32 reduction order (its CPU and CUDA builds disagree with each other there).  The
+    oracle's canonical order may then legitimately cut elsewhere -- but only at similarities that sit
+    within a few ulp of the reference's threshold.  Reports the agreement rate; every disagreement must be
+    of that kind."""
+    g = synth.rng_for({"walk": 11, "static": 12, "duplicates": 13}[family])
+    agree = total = 0
+    for trial in range(60):
+        t = int(g.choice([16, 32, 64, 256]))
+        k = int(g.choice([4, 8]))
+        x = _coherent_tokens(family, t, g)
+        xt = torch.from_numpy(x)[None]
+        with torch.no_grad():
+            ref_out = ref.token_merge(xt, t - k)[0].numpy()
+            s_ref = torch.sum(torch.nn.functional.normalize(xt[:, :-1], dim=-1)
+                              * torch.nn.functional.normalize(xt[:, 1:], dim=-1), dim=-1)[0].numpy()
+        kth_ref = np.sort(s_ref)[::-1][t - k - 1]
+        ref_cut = s_ref < kth_ref
+        tok, cut, _ = R.token_merge(x, k)
+        total += 1
+        if np.array_equal(cut, ref_cut):
+            agree += 1
+            assert tok.shape == ref_out.shape and np.abs(tok - ref_out).max() <= 1e-5
+            continue
+        ulp = np.spacing(np.float32(abs(kth_ref)))
+        for i in np.flatnonzero(cut != ref_cut):                 # the decisions that differ are ties in disguise
+            assert abs(float(s_ref[i]) - float(kth_ref)) <= 8 * ulp, (family, t, k, i, s_ref[i], kth_ref)
+    with capsys.disabled():
+        print(f"\n[TTM {family}] oracle == reference decisions on {agree}/{total} objects; "
+              f"all others differ only at similarities within 8 ulp of the reference's threshold")
