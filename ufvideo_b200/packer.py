@@ -10,6 +10,7 @@ patched).
 from __future__ import annotations
 
 import ctypes
+import itertools
 import marshal
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -225,55 +226,64 @@ def _lookup_or_build(masks, ann_indices, ann_bytes, n_feat_rows, k_keep, device,
 
 
 def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, ptrs) -> EncodePlan:
-    pitch, dtype_id, tap_off, sample_of, plane_off, rows_all, aux = [], [], [], [], [], [], []
+    # Per-sample scalars first (python), then one np.repeat per descriptor field: the per-row work is numpy's.
+    n_s = len(masks)
+    s_pitch, s_dtype, s_tap, s_aux, s_plane_stride = (np.zeros(n_s, np.int64) for _ in range(5))
+    counts = np.zeros(n_s, np.int64)
+    rows_all, planes_all, obj_start, obj_len = [], [], [], []
     rle_rows = []                                # (sample, its descriptor rows, the mask plane of each row)
     taps, tap_chunks, tap_len = {}, [], 0
-    obj_start, obj_len = [], []
     base = 0
+    chain = itertools.chain.from_iterable
     for i, m in enumerate(masks):
         q, h, w = m.shape
-        esize = m.element_size()
         tkey = (h, w)
         toff = taps.get(tkey)
         if toff is None:
             toff = taps[tkey] = tap_len
             tap_chunks.append(tap_table(h, w, n_out, pad_square))
             tap_len += 4 * n_out
-        rows = [int(r) for obj in ann_indices[i] for r in obj]            # layer.py:92-95
-        b = len(rows)
+        sample = ann_indices[i]
+        lens = np.fromiter(map(len, sample), dtype=np.int64, count=len(sample))
+        rows = np.fromiter(chain(sample), dtype=np.int64, count=int(lens.sum()))       # layer.py:92-95
+        b = rows.size
         planes = np.arange(q, dtype=np.int64)
         if b != q:                               # torch broadcasting of x * mask, layer.py:147
             if b == 1:
-                rows = rows * q
+                rows = np.repeat(rows, q)
             elif q == 1:
                 planes = np.zeros(b, dtype=np.int64)
             else:
                 raise ValueError(f"sample {i}: {b} feature rows cannot pair with {q} masks")
-        n_i = len(rows)
-        sample_of.append(np.full(n_i, i, dtype=np.int32))
+        n_i = rows.size
+        counts[i], s_tap[i] = n_i, toff
         if isinstance(m, RleSample):             # per-mask run count / offset instead of pitch / plane stride
             rle_rows.append((i, np.arange(base, base + n_i), planes))
-            plane_off.append(m.run_off[planes] * 4)
-            pitch.append(m.n_runs[planes])
-            dtype_id.append(np.full(n_i, _cabi.UFV_RLE, dtype=np.int32))
-            aux.append(np.full(n_i, h, dtype=np.int32))
+            s_dtype[i], s_aux[i] = _cabi.UFV_RLE, h
         else:
-            plane_off.append(planes * (m.stride(0) * esize))
-            pitch.append(np.full(n_i, m.stride(1), dtype=np.int32))
-            dtype_id.append(np.full(n_i, _MASK_DTYPES[m.dtype], dtype=np.int32))
-            aux.append(np.zeros(n_i, dtype=np.int32))
-        tap_off.append(np.full(n_i, toff, dtype=np.int32))
-        rows_all.append(np.asarray(rows, dtype=np.int64))
-        start = 0
-        for obj in ann_indices[i]:               # running offset over pooled rows, layer.py:112-119
-            t = max(0, min(len(obj), n_i - start))
-            obj_start.append(base + start)
-            obj_len.append(t)
-            start += len(obj)
+            s_pitch[i], s_dtype[i] = m.stride(1), _MASK_DTYPES[m.dtype]
+            s_plane_stride[i] = m.stride(0) * m.element_size()
+        rows_all.append(rows)
+        planes_all.append(planes)
+        starts = np.cumsum(lens) - lens          # running offset over pooled rows, layer.py:112-119
+        obj_start.append(base + starts)
+        obj_len.append(np.clip(np.minimum(lens, n_i - starts), 0, None))
         base += n_i
 
+    cat = lambda parts, dt: np.concatenate(parts).astype(dt, copy=False) if parts else np.zeros(0, dt)  # noqa: E731
+    planes_cat = cat(planes_all, np.int64)
+    sample_of = [np.repeat(np.arange(n_s, dtype=np.int32), counts)]
+    pitch = [np.repeat(s_pitch, counts).astype(np.int32)]
+    dtype_id = [np.repeat(s_dtype, counts).astype(np.int32)]
+    tap_off = [np.repeat(s_tap, counts).astype(np.int32)]
+    aux = [np.repeat(s_aux, counts).astype(np.int32)]
+    plane_off = [planes_cat * np.repeat(s_plane_stride, counts)]
+    for i, rows_i, planes in rle_rows:           # run-length samples: per-mask values
+        plane_off[0][rows_i] = masks[i].run_off[planes] * 4
+        pitch[0][rows_i] = masks[i].n_runs[planes]
+    obj_start = cat(obj_start, np.int64).tolist()
+    obj_len = cat(obj_len, np.int64).tolist()
     q_total = base
-    cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)  # noqa: E731
     rows_all = cat(rows_all, np.int64)
     if q_total and (rows_all.min() < 0 or rows_all.max() >= n_feat_rows):
         raise IndexError(f"ann_indices refer to feature rows outside [0, {n_feat_rows})")
