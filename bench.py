@@ -283,7 +283,7 @@ def run_ours(a):
         # Preferred: the all-gather fused into the last Linear (ufv_linear_gather): its epilogue stores
         # every tile into all ranks' gathered buffers over NVLink.  UFV_BENCH_GATHER=nccl (or a failed
         # symmetric-memory rendezvous) falls back to one asynchronous NCCL all-gather of the payload.
-        if os.environ.get("UFV_BENCH_GATHER", "fused") != "nccl":
+        if os.environ.get("UFV_BENCH_GATHER", "fused") not in ("nccl", "none"):
             try:
                 pg = sharding.PeerGather(pad_rows, pad_objs, 3584, torch.bfloat16, dev)
                 gather_kind = ("fused into the last Linear: tcgen05 epilogue stores tiles to every rank over NVLink ("
@@ -320,8 +320,10 @@ def run_ours(a):
             else:
                 item[0].wait()
 
+    no_gather = world > 1 and os.environ.get("UFV_BENCH_GATHER") == "none"   # developer knob: ranks without collection
+
     def step_resident():
-        if world > 1:
+        if world > 1 and not no_gather:
             return gather_step(feats_dev, masks_dev)
         return enc(feats_dev, masks_dev, None, ann, None)[0]
 
