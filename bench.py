@@ -438,7 +438,10 @@ def run_ours(a):
                                   f"{mask_bytes_full / 1e6:.0f} MB read in place over PCIe by kernel 1, "
                                   f"{mask_bytes_read / 1e6:.0f} MB touched"),
                    "l2": f"inputs larger than L2: {feats_dev.numel() * 2 / 1e6:.0f} MB of features per step vs 126 MB",
-                   "collective": gather_kind, "host_binding": numa_note},
+                   "collective": gather_kind, "host_binding": numa_note,
+                   "per_step_work": ("all five kernels run on the step's inputs every step (masks re-read, features "
+                                     "re-streamed, weights re-read); only the host-side descriptor arrays of the batch "
+                                     "structure and the captured launch sequence (CUDA graph) are reused across steps")},
         "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": (6 if pg is not None else 5) * a.steps,   # kernels 1, 2, 3, 4a, 4b (+ flag wait)
