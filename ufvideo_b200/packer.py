@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes
 import itertools
 import marshal
+import weakref
 from collections import OrderedDict
 from dataclasses import dataclass, field
 
@@ -174,8 +175,8 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
     if (use_cache and last is not None and last[2] == scalars and len(masks) == len(last[0])
             and _same_indices(ann_indices, last[3])):
         same = True
-        for m, (obj, ptr, shape) in zip(masks, last[0]):
-            if m is not obj or m.data_ptr() != ptr or m.shape != shape:
+        for m, (ref, ptr, shape) in zip(masks, last[0]):      # weak references: no mask tensor is kept alive
+            if m is not ref() or m.data_ptr() != ptr or m.shape != shape:
                 same = False
                 break
         if same and _plan_cache.get(last[4].cache_key) is last[4]:
@@ -190,9 +191,9 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
                             use_cache)
     if use_cache and ann_bytes is not None and torch.is_tensor(masks) is False:
         try:
-            _last_call[0] = ([(m, m.data_ptr(), m.shape) for m in masks], None, scalars,
+            _last_call[0] = ([(weakref.ref(m), m.data_ptr(), m.shape) for m in masks], None, scalars,
                              marshal.loads(ann_bytes), plan)
-        except AttributeError:                   # non-tensor mask entries: no identity fast path
+        except (AttributeError, TypeError):      # non-tensor mask entries: no identity fast path
             _last_call[0] = None
     return plan
 
@@ -340,7 +341,7 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
                       any_row_mode=any_row_mode, rle_rows=rle_rows)
     plan.ticket = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)   # self-resetting
     _fill_addresses(plan, ptrs)
-    plan.keepalive = masks if rle_rows else None
+    plan.keepalive = [m for m in masks if isinstance(m, RleSample)] if rle_rows else None
     _upload(plan, device)
     return plan
 
@@ -358,7 +359,8 @@ def _fill_addresses(plan: EncodePlan, ptrs, masks=None) -> None:
 
 def _patch_addresses(plan: EncodePlan, ptrs, device, masks=None) -> None:
     _fill_addresses(plan, ptrs, masks)
-    plan.keepalive = masks                       # run-length buffers must outlive the launches that read them
+    # run-length buffers must outlive the launches that read them (dense mask tensors belong to the caller)
+    plan.keepalive = [m for m in masks if isinstance(m, RleSample)] if masks is not None else None
     desc = plan.host["mask_desc"]
     staging = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy())
     if device.type == "cuda":
