@@ -136,17 +136,22 @@ def gather_rows(x: torch.Tensor, row_map: torch.Tensor):
     return out
 
 
-def _await_counts(plan: packer.EncodePlan, device) -> np.ndarray:
+def _await_counts(plan: packer.EncodePlan, device, idle_work=None) -> np.ndarray:
     """Poll the pinned words kernel 3 writes, (epoch << 16) | count per object, until all of them
-    carry this call's epoch; returns the int32 counts."""
+    carry this call's epoch; returns the int32 counts.  ``idle_work`` (optional callable) runs once
+    first: the host has ~60 us to kill here, which is where the next call's output tensor gets allocated."""
     words, epoch = plan.counts_np[:plan.n_obj], plan.epoch
+    if idle_work is not None:
+        idle_work()
+    last = plan.n_obj - 1
     spins = 0
     while True:
-        snap = words.copy()
-        if ((snap >> 16) == epoch).all():
-            return snap & 0xffff
+        if (int(words[last]) >> 16) == epoch:    # cheap scalar pre-check before the vector compare
+            snap = words.copy()
+            if ((snap >> 16) == epoch).all():
+                return snap & 0xffff
         spins += 1
-        if spins & 0x3fff == 0:                  # every few ms: surface a failed launch instead of hanging
+        if spins & 0xffff == 0:                  # every few ms: surface a failed launch instead of hanging
             if torch.cuda.current_stream(device).query():
                 snap = words.copy()
                 if ((snap >> 16) == epoch).all():
@@ -266,35 +271,48 @@ class MaskExtractor(nn.Module):
         struct and the pinned counts buffer live in the cached plan and are reused as long as the
         same pointers come back on the same stream (stream order makes the reuse safe)."""
         linears = self._linears()
-        w1 = linears[0].weight
+        two = len(linears) == 2
+        if two:                                   # parameter tensors straight from the module dicts (no __getattr__)
+            p0, p1 = linears[0]._parameters, linears[1]._parameters
+            w1 = p0["weight"]
+            wptrs = (w1.data_ptr(), p0["bias"].data_ptr(), p1["weight"].data_ptr(), p1["bias"].data_ptr())
+        else:
+            w1 = linears[0].weight
+            wptrs = tuple(p.data_ptr() for lin in linears for p in (lin.weight, lin.bias))
         device = w1.device
         if device.type != "cuda":
             raise RuntimeError("MaskExtractor parameters must be on a CUDA device (no CPU path)")
         if not torch.is_tensor(feats):
             raise TypeError("feats must be a tensor [F, n_patch, C]")
-        if feats.device != device:
-            feats = feats.to(device, non_blocking=True)
-        if not feats.is_contiguous():
-            feats = feats.contiguous()
-        if feats.dim() != 3:
-            raise ValueError(f"feats must be [F, n_patch, C], got {tuple(feats.shape)}")
-        dt = _feat_dtype(feats)
-        if w1.dtype != feats.dtype:
-            raise TypeError(f"feature dtype {feats.dtype} != projector dtype {w1.dtype}")
-        f, n_patch, c = feats.shape
-        side = int(round(n_patch ** 0.5))         # layer.py:100
-        if side * side != n_patch or side > _cabi.MAX_PATCH_SIDE:
-            raise ValueError(f"n_patch={n_patch} is not a square grid with side <= {_cabi.MAX_PATCH_SIDE}")
+        stream = torch._C._cuda_getCurrentRawStream(device.index)
+        # everything derived from (features, parameters, stream) is memoised: a repeated call pays one tuple compare
+        memo = self.__dict__.get("_feat_memo")
+        key = (feats.data_ptr(), feats.shape, feats.dtype, feats.device, feats.is_contiguous(), wptrs, stream)
+        if memo is not None and memo[0] == key:
+            dt, f, c, side, hid, sig = memo[1]
+        else:
+            if feats.device != device:
+                feats = feats.to(device, non_blocking=True)
+            if not feats.is_contiguous():
+                feats = feats.contiguous()
+            if feats.dim() != 3:
+                raise ValueError(f"feats must be [F, n_patch, C], got {tuple(feats.shape)}")
+            dt = _feat_dtype(feats)
+            if w1.dtype != feats.dtype:
+                raise TypeError(f"feature dtype {feats.dtype} != projector dtype {w1.dtype}")
+            f, n_patch, c = feats.shape
+            side = int(round(n_patch ** 0.5))     # layer.py:100
+            if side * side != n_patch or side > _cabi.MAX_PATCH_SIDE:
+                raise ValueError(f"n_patch={n_patch} is not a square grid with side <= {_cabi.MAX_PATCH_SIDE}")
+            hid = linears[-1].weight.shape[0]
+            sig = (feats.data_ptr(), dt, f, c, hid, stream, two, wptrs)
+            if feats.data_ptr() == key[0]:        # the caller's own tensor was used as is: safe to memoise
+                self.__dict__["_feat_memo"] = (key, (dt, f, c, side, hid, sig))
         k_keep = int(self.region_token_num)
         plan = packer.build_plan(masks, ann_indices, f, k_keep, device,
                                  self.image_aspect_ratio == "pad", side)
         self.last_plan = plan
-        hid = linears[-1].weight.shape[0]
         q, m_pad = plan.n_masks, plan.m_pad
-        stream = torch._C._cuda_getCurrentRawStream(device.index)
-        two = len(linears) == 2
-        sig = (feats.data_ptr(), dt, f, c, hid, stream, two,
-               tuple(p.data_ptr() for lin in linears for p in (lin.weight, lin.bias)))
         run = plan.run
         if run is None or run["sig"] != sig:
             shape_sig = (dt, f, c, hid, two, k_keep, side)
@@ -315,7 +333,9 @@ class MaskExtractor(nn.Module):
         if peer is not None and not two:
             raise ValueError("peer gather needs the depth-2 projector path")
         if out is None:
-            tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
+            tokens = run.pop("spare_out", None)   # allocated while the previous call waited for its counts
+            if tokens is None or tokens.dtype != feats.dtype:
+                tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
         else:
             tokens = out
         if out is not None or counts_out is not None:
@@ -377,7 +397,7 @@ class MaskExtractor(nn.Module):
                                                 ptr["bits"], ptr["cnt"],
                                                 None, 0, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
                                                 ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], stream))
-            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, n_patch, c, ptr["cnt"], d["grp_row"],
+            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, side * side, c, ptr["cnt"], d["grp_row"],
                                           d["grp_off"], d["grp_member"], ptr["grp_nu"], ptr["grp_ulist"],
                                           ptr["grp_omask"], plan.n_groups, plan.max_group, ptr["pooled"], stream))
             _cabi.check(lib.ufv_ttm(ptr["pooled"], c, d["obj_start"], d["obj_len"], d["slot_off"],
@@ -534,9 +554,12 @@ class MaskExtractor(nn.Module):
         tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, _awaited=True)
         # the one unavoidable D2H: the caller slices rows by these counts (videorefer_arch.py:307-311)
         if plan.run.get("args") is not None and plan.n_obj > 0:
-            # the merge kernel stores the counts straight into pinned host memory and stamps the
-            # call's epoch behind them; the projector may still be running when this returns
-            region_token_nums = _await_counts(plan, tokens.device)
+            # the merge kernel stores the counts straight into pinned host memory, tagged with the call's
+            # epoch; the projector may still be running when this returns
+            run = plan.run
+            region_token_nums = _await_counts(
+                plan, tokens.device,
+                lambda: run.__setitem__("spare_out", torch.empty_like(tokens)) if "spare_out" not in run else None)
         else:
             region_token_nums = counts.cpu().numpy()
         if region_token_nums.tobytes() == plan.slots_bytes:   # no ties: every object kept min(T, K) tokens
