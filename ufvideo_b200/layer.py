@@ -28,6 +28,8 @@ from . import _cabi, packer
 # batch structure on (UFV_NO_GRAPH=1 disables: developer A/B knob).
 USE_CUDA_GRAPH = os.environ.get("UFV_NO_GRAPH") is None
 
+_NULL_CONTEXT = contextlib.nullcontext()
+
 _vp = ctypes.c_void_p
 _ELEM_BYTES = {torch.float32: 4, torch.int32: 4, torch.bfloat16: 2, torch.float16: 2, torch.uint8: 1}
 
@@ -497,10 +499,10 @@ class MaskExtractor(nn.Module):
     def _on_module_device(self):
         """Context that makes the module's GPU the current CUDA device (the C ABI launches on the current
         device; torch ops guard themselves, raw launches do not).  A no-op in the common single-GPU case."""
-        dev = self.feat_linear[0].weight.device
+        dev = self._linears()[0]._parameters["weight"].device
         if dev.type == "cuda" and torch.cuda.current_device() != dev.index:
             return torch.cuda.device(dev)
-        return contextlib.nullcontext()
+        return _NULL_CONTEXT
 
     def forward_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None):
         """forward() without the compaction: (tokens [m_pad, hidden] with object o's rows at
@@ -548,8 +550,8 @@ class MaskExtractor(nn.Module):
         list[int]).  ``X_features`` and ``frame_nums`` are accepted and ignored, as in the reference
         (which reads only ``X_features.device`` in its fallbacks).  Forward only: no autograd graph
         is recorded (DESIGN.md, "next")."""
-        if torch.is_grad_enabled() and ((torch.is_tensor(feats) and feats.requires_grad)
-                                        or any(p.requires_grad for p in self.feat_linear.parameters())):
+        if torch.is_grad_enabled() and ((torch.is_tensor(feats) and feats.requires_grad) or any(
+                p is not None and p.requires_grad for lin in self._linears() for p in lin._parameters.values())):
             return self._forward_with_grad(feats, masks, ann_indices)
         tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, _awaited=True)
         # the one unavoidable D2H: the caller slices rows by these counts (videorefer_arch.py:307-311)
