@@ -145,3 +145,68 @@ def test_plan_accepts_run_length_samples_and_refreshes_their_descriptors():
     again = packer.build_plan([[rle.encode(m) for m in masks[::-1]]], ann, 3, 2, CPU)   # same structure, new runs
     assert again is plan and again.host["mask_desc"]["pitch"].tolist() == d["pitch"].tolist()
     assert again.host["mask_desc"]["pitch"].tolist() == [len(rle.encode(m)["counts"]) for m in masks[::-1]]
+
+
+# ---------------------------------------------------------------------------------------------
+# property test: the packer against a direct restatement of the reference's bookkeeping
+# ---------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@st.composite
+def _batches(draw):
+    n_samples = draw(st.integers(1, 3))
+    n_rows, samples = 0, []
+    for _ in range(n_samples):
+        frames = draw(st.integers(1, 6))
+        n_obj = draw(st.integers(1, 11))
+        objs = [draw(st.lists(st.integers(0, frames - 1), min_size=0, max_size=7)) for _ in range(n_obj)]
+        if sum(len(o) for o in objs) == 0:
+            objs[0] = [0]
+        samples.append((frames, [[n_rows + f for f in o] for o in objs]))
+        n_rows += frames
+    k = draw(st.integers(1, 5))
+    return n_rows, samples, k
+
+
+@settings(max_examples=60, deadline=None)
+@given(_batches())
+def test_plan_matches_a_direct_restatement_of_the_reference_loop(batch):
+    """layer.py:92-95 flattens each sample's index lists (objects in order, frames in order) and pairs
+    flattened position j with mask plane j; :112-119 walks the pooled rows object by object; :121-125
+    concatenates min(T, K)-or-fewer tokens per object.  The plan must encode exactly that, and its groups
+    must partition the object-frames by feature row with at most MAX_GROUP members each."""
+    n_rows, samples, k = batch
+    masks = [torch.zeros((sum(len(o) for o in objs), 9, 11), dtype=torch.uint8) for _, objs in samples]
+    ann = [objs for _, objs in samples]
+    plan = packer.build_plan(masks, ann, n_rows, k, CPU, use_cache=False)
+    h = plan.host
+    want_rows, want_start, want_len = [], [], []
+    for _, objs in samples:                                   # the reference's loops, restated
+        flat = [r for o in objs for r in o]
+        start = len(want_rows)
+        for o in objs:
+            want_start.append(start)
+            want_len.append(len(o))
+            start += len(o)
+        want_rows.extend(flat)
+    assert plan.n_masks == len(want_rows) and plan.n_obj == len(want_len)
+    assert h["obj_start"].tolist() == want_start and h["obj_len"].tolist() == want_len
+    slots = [min(t, k) for t in want_len]
+    assert plan.slots.tolist() == slots and plan.m_pad == sum(slots)
+    assert h["slot_off"].tolist() == [sum(slots[:i]) for i in range(len(slots))]
+    # groups: a partition of the object-frames, each group on one feature row, at most MAX_GROUP members
+    go, gm, gr = h["grp_off"], h["grp_member"], h["grp_row"]
+    assert sorted(gm.tolist()) == list(range(len(want_rows))) and go[0] == 0 and go[-1] == len(want_rows)
+    for g in range(plan.n_groups):
+        members = gm[go[g]:go[g + 1]]
+        assert 1 <= len(members) <= _cabi.MAX_GROUP
+        assert {want_rows[j] for j in members} == {int(gr[g])}
+        assert (h["mask_desc"]["group"][members] == g).all()
+    # mask planes: descriptor j points at plane j of its sample (uint8, contiguous: pitch 11, plane 99 bytes)
+    off = 0
+    for m in masks:
+        q = m.shape[0]
+        d = h["mask_desc"][off:off + q]
+        assert (d["addr"] == m.data_ptr() + np.arange(q, dtype=np.uint64) * 99).all() and (d["pitch"] == 11).all()
+        off += q
