@@ -321,6 +321,7 @@ class MaskExtractor(nn.Module):
             if run is not None and run["shape_sig"] == shape_sig:
                 # same sizes, other pointers / stream: keep the workspace, rebind, drop captured graphs
                 self._drop_graphs(run)
+                run.pop("spare_out", None)        # was allocated for the previous stream
                 run["sig"] = sig
                 if two:
                     a = run["args"]
