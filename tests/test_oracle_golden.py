@@ -86,3 +86,49 @@ def test_encode_matches_reference_module(golden_dir, name):
     tol = 1e-5 if dt == "f32" else 1e-2
     assert out["tokens"].shape == g["tokens"].shape
     assert np.abs(out["tokens"] - g["tokens"]).max() <= tol
+
+
+# ---------------------------------------------------------------------------------------------
+# property tests: the integer restatement of the resize against ATen itself, and the torch-CPU port
+# (the timed CPU baseline) against the numpy oracle -- neither needs the reference tree
+# ---------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.integers(1, 140), st.integers(1, 140), st.floats(0.0, 1.0), st.integers(0, 2 ** 31 - 1), st.booleans())
+def test_tap_or_equals_aten_bilinear_threshold_for_any_size(h, w, density, seed, pad):
+    """layer.py:137-143 on arbitrary sizes (up- and down-sampling, non-square, multiples of 27 where a tap
+    weight is exactly zero), with and without the 'pad' mode of layer.py:77-86: interp(mask) > 0 computed by
+    ATen equals the OR over the taps with non-zero weight."""
+    import torch
+    import torch.nn.functional as F
+    g = synth.rng_for(seed)
+    mask = (g.random((h, w)) < density).astype(np.float32)
+    t = torch.from_numpy(mask)[None, None]
+    if pad:
+        side = max(h, w)
+        t = F.pad(t, ((side - w) // 2, (side - w) - (side - w) // 2, (side - h) // 2, (side - h) - (side - h) // 2))
+    if t.shape[-2:] != (27, 27):
+        t = F.interpolate(t, size=(27, 27), mode="bilinear", align_corners=False)
+    want = (t > 0)[0, 0].reshape(-1).numpy()
+    assert np.array_equal(R.mask_to_patches(mask, pad_square=pad), want)
+
+
+@settings(max_examples=12, deadline=None)
+@given(st.integers(2, 9), st.integers(1, 3), st.integers(1, 5), st.integers(0, 10_000))
+def test_cpu_baseline_port_agrees_with_the_oracle(frames, n_obj, k, seed):
+    """oracle/reference_port.py (ATen ops, what bench.py times as the CPU baseline) and
+    oracle/restatement.py (numpy, the parity oracle) are two restatements of layer.py:63-128: same counts,
+    tokens within the fp32 bar."""
+    import torch
+    from oracle import reference_port
+    feats, masks, ann = synth.make_clip(seed, frames, n_obj, "blob", 48, 60, c=64, n_patch=729, ragged=True)
+    g = synth.rng_for(seed + 1)
+    w = [g.uniform(-0.1, 0.1, s).astype(np.float32) for s in ((32, 64), (32,), (32, 32), (32,))]
+    o = R.encode(feats, [masks], [ann], k, "f32", w)
+    with torch.no_grad():
+        tok, counts = reference_port.encode(torch.from_numpy(feats), [torch.from_numpy(masks).float()], [ann], k,
+                                            *[torch.from_numpy(a) for a in w])
+    assert counts == o["counts"]
+    assert np.abs(tok.numpy() - o["tokens"]).max() <= 1e-5
