@@ -65,6 +65,9 @@ typedef struct ufv_mask_desc {
 
 int ufv_abi_version(void);
 const char* ufv_last_error(void);
+/* sizeof() of an ABI struct as this library was compiled, by name ("ufv_mask_desc", "ufv_peer_args",
+ * "ufv_dyn_args", "ufv_encode_args"); -1 for an unknown name.  Lets a binding verify its struct mirrors. */
+int ufv_struct_size(const char* name);
 
 /* Device-visible address of a pinned (page-locked, mapped) host buffer, so that kernels can read
  * host-resident masks in place.  Returns 0 and sets *dev_addr, or the cudaError_t when `host_ptr`

@@ -23,6 +23,16 @@ def test_library_exports_every_symbol_the_header_declares():
     assert lib.ufv_abi_version() == _cabi.ABI_VERSION
 
 
+def test_ctypes_struct_mirrors_have_the_sizes_the_library_was_compiled_with():
+    lib = _cabi.lib()
+    import ctypes
+    assert lib.ufv_struct_size(b"ufv_mask_desc") == packer.MASK_DESC.itemsize == 32
+    assert lib.ufv_struct_size(b"ufv_peer_args") == ctypes.sizeof(_cabi.PeerArgs)
+    assert lib.ufv_struct_size(b"ufv_dyn_args") == ctypes.sizeof(_cabi.DynArgs) == 256
+    assert lib.ufv_struct_size(b"ufv_encode_args") == ctypes.sizeof(_cabi.EncodeArgs)
+    assert lib.ufv_struct_size(b"nope") == -1
+
+
 def test_argument_errors_are_reported_not_crashed():
     lib = _cabi.lib()
     assert lib.ufv_tap_table(0, 5, 27, 0, None) == -1            # UFV_E_NULL

@@ -74,6 +74,7 @@ assert C.sizeof(DynArgs) == 256
 _SIGNATURES = {
     "ufv_abi_version": (C.c_int, []),
     "ufv_last_error": (C.c_char_p, []),
+    "ufv_struct_size": (C.c_int, [C.c_char_p]),
     "ufv_device_address": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "ufv_tap_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p,

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace ufv {
 
@@ -159,6 +160,15 @@ __global__ void splice_rows_kernel(const uint4* __restrict__ text, int n_text, c
 extern "C" int ufv_abi_version(void) { return UFV_ABI_VERSION; }
 
 extern "C" const char* ufv_last_error(void) { return ufv::g_error; }
+
+extern "C" int ufv_struct_size(const char* name) {
+  if (name == nullptr) return -1;
+  if (strcmp(name, "ufv_mask_desc") == 0) return int(sizeof(ufv_mask_desc));
+  if (strcmp(name, "ufv_peer_args") == 0) return int(sizeof(ufv_peer_args));
+  if (strcmp(name, "ufv_dyn_args") == 0) return int(sizeof(ufv_dyn_args));
+  if (strcmp(name, "ufv_encode_args") == 0) return int(sizeof(ufv_encode_args));
+  return -1;
+}
 
 extern "C" int ufv_device_address(const void* host_ptr, uint64_t* dev_addr_host) {
   using namespace ufv;
