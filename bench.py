@@ -12,9 +12,9 @@ value   device-resident inputs, CUDA events around exactly K steps, max over ran
 e2e     the same step through the module's public forward() with HOST (pinned) feats and masks:
         the H2D of the inputs and the D2H of the projected tokens are inside the timed region.
 roofline  the dominant kernel (segmented mask pool, HBM-bound) timed alone with CUDA events.
-cpu_baseline  the oracle's torch-CPU port of the reference on a bounded sample (rank 0, N=1).
---impl reference  times that CPU port alone (the reference is Python and cannot travel to the GPU
-        box; oracle/reference_port.py issues the reference's ATen calls op for op).
+cpu_baseline  the reference's CPU implementation of the whole workload on all host cores (rank 0, N=1):
+        the real ufvideo/model/layer.py when a reference tree is reachable, else its torch-CPU port.
+--impl reference  times that CPU implementation alone, all 8 clips of configs[1] per step.
 """
 from __future__ import annotations
 
@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--objects", type=int, default=WORKLOAD["objects"])
     ap.add_argument("--family", default=WORKLOAD["family"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default="", metavar="FILE",
+                    help="developer knob: trace the steady-state device-resident step with CUPTI (torch.profiler) "
+                         "and write the per-kernel timeline of a few steps to FILE instead of benchmarking")
     return ap.parse_args()
 
 
@@ -127,44 +130,75 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's torch-CPU port of the reference on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(a, steps: int, warmup: int, sample_clips: int = 2, min_seconds: float = 0.0):
+def cpu_reference_run(a, steps: int, warmup: int, sample_clips: int | None = None, min_seconds: float = 0.0):
+    """The reference's CPU implementation of the path on all host cores.  The real ``layer.py`` is used
+    whenever a reference tree is reachable ($UFV_REF, /root/reference, baseline/_ref: kind "reference");
+    otherwise (the GPU box: a Python reference cannot travel) the op-for-op torch-CPU port of it under
+    oracle/ (kind "port", validated bit-identical to the real module by tests/test_oracle_vs_reference.py)."""
     import torch
 
-    from oracle import reference_port
+    from oracle import ref_loader, reference_port
     from ufvideo_b200 import synth
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    feats, masks, ann = synth.make_batch(sample_clips, a.frames, a.objects, a.family)
+    n_clips = a.clips if sample_clips is None else min(sample_clips, a.clips)
+    feats, masks, ann = synth.make_batch(n_clips, a.frames, a.objects, a.family)
     weights = [torch.from_numpy(w) for w in synth.make_weights(0)]
     ft = torch.from_numpy(feats)                       # fp32: CPU bf16 kernels are not the reference's CPU path
     mt = [torch.from_numpy(m).float() for m in masks]
     q = sum(m.shape[0] for m in masks)
+    ref = ref_loader.load_reference_layer()
+    if ref is not None:
+        kind = "reference"
+        enc = ref.build_region_encoder(ref_loader.reference_config(), "square")
+        enc.region_token_num = WORKLOAD["k"]
+        with torch.no_grad():
+            for p, w in zip((enc.feat_linear[0].weight, enc.feat_linear[0].bias,
+                             enc.feat_linear[2].weight, enc.feat_linear[2].bias), weights):
+                p.copy_(w)
+        enc = enc.eval()
+
+        def run():
+            return enc(ft, mt, ft, ann, None)
+    else:
+        kind = "port"
+
+        def run():
+            return reference_port.encode(ft, mt, ann, WORKLOAD["k"], *weights)
     with torch.no_grad():
         for _ in range(warmup):
-            reference_port.encode(ft, mt, ann, WORKLOAD["k"], *weights)
+            run()
         t0 = time.perf_counter()
         done = 0
         while done < steps or time.perf_counter() - t0 < min_seconds:
-            reference_port.encode(ft, mt, ann, WORKLOAD["k"], *weights)
+            run()
             done += 1
         dt = time.perf_counter() - t0
-    sample = (f"{sample_clips} of the workload's clips ({q} object-frames: {sample_clips} x {a.frames} frames x "
-              f"{a.objects} objects), fp32, {done} timed passes after {warmup} warm-up")
-    return q * done / dt, dt / done, cores, sample, done
+    which = ("the reference's own ufvideo/model/layer.py (" + os.path.dirname(os.path.dirname(os.path.dirname(
+        ref_loader.reference_layer_path()))) + ")" if kind == "reference"
+        else "oracle/reference_port.py, the op-for-op torch-CPU port of layer.py (no reference tree on this box)")
+    whole = n_clips == a.clips
+    sample = (("the whole workload: " if whole else f"{n_clips} of the workload's {a.clips} clips: ")
+              + f"{n_clips} clips x {a.frames} frames x {a.objects} objects = {q} object-frames per pass, fp32, "
+              f"{cores} threads, {done} timed passes after {warmup} warm-up; {which}")
+    return q * done / dt, dt / done, cores, sample, done, kind, whole
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, sec, cores, sample, done = cpu_reference_run(a, a.steps, a.warmup)
+    value, sec, cores, sample, done, kind, whole = cpu_reference_run(a, a.steps, max(a.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": done, "warmup": max(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "step": "bounded CPU sample: " + sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(a),
+                   "step": ("one pass of the reference's CPU implementation over " + sample +
+                            "; one rank's share of the workload (weak scaling: every rank holds the same "
+                            "amount), timed on rank 0's host cores")},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,6 +263,44 @@ def bind_to_gpu_numa_node(local: int) -> str:
         return f"numa: rank bound to {len(allowed)} cpus ({how})"
     except Exception as exc:   # noqa: BLE001 -- binding is an optimisation, never a requirement
         return f"numa: not bound ({type(exc).__name__})"
+
+
+def write_timeline(path, step, drain, barrier, rank, world, steps: int = 8):
+    """Per-kernel start / duration / gap table of the steady-state step as CUPTI sees it inside the real
+    pipeline (graph replay, programmatic dependent launch, concurrent kernels) -- what ncu's serialised,
+    cold-cache launch list cannot show.  Times under the tracer are not bench values."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+
+    for _ in range(10):
+        step()
+    drain()
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(steps):
+            step()
+        drain()
+        torch.cuda.synchronize()
+    barrier()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ev.sort(key=lambda e: e.time_range.start)
+    lines = [f"# rank {rank} of {world}: {steps} traced steps; columns: start us (from the first kernel), "
+             f"duration us, gap to the previous kernel's end us (negative = overlap), name"]
+    if ev:
+        t0 = ev[0].time_range.start
+        prev_end = t0
+        for e in ev:
+            st, en = e.time_range.start, e.time_range.end
+            lines.append(f"{st - t0:10.1f} {en - st:8.1f} {st - prev_end:8.1f}  {e.name[:110]}")
+            prev_end = max(prev_end, en)
+        total = prev_end - t0
+        lines.append(f"# span {total:.1f} us over {steps} steps = {total / steps:.1f} us per step")
+    out = path if world == 1 else f"{path}.rank{rank}"
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
+    with open(out, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    if rank == 0:
+        print(f"[bench] timeline written to {out} ({len(ev)} device events)", file=sys.stderr)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -375,6 +447,13 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
+    if a.timeline:
+        with torch.inference_mode():
+            write_timeline(a.timeline, step_resident, drain, barrier, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # the reference runs the model under torch.inference_mode() (ufvideo/__init__.py:122)
     with ClockSampler(local, enabled=rank == 0) as clocks, torch.inference_mode():
         ms_step = timed(step_resident, a.steps, max(a.warmup, 3))
@@ -408,8 +487,8 @@ def run_ours(a):
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        v, sec, cores, sample, done = cpu_reference_run(a, steps=3, warmup=1, min_seconds=10.0)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        v, sec, cores, sample, done, kind, _ = cpu_reference_run(a, steps=3, warmup=1, min_seconds=10.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
     total_q = q * world
     # pinned host masks are read in place by kernel 1 (row mode): only the 2 x 27 source rows of each

@@ -93,8 +93,8 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  * for masks in HBM) or, when desc.flags bit 0 is set and the tap columns of a row span <= 4 KB,
  * in row mode (the source rows of every output row are read with coalesced 16-byte loads: few,
  * wide requests, the efficient pattern over PCIe for pinned host masks).  Both give the same bits.
- * The 16-byte chunks read in row mode are aligned down/up around the tap span, so a mask plane
- * must not begin or end closer than 16 bytes to an unmapped page (true for any allocator).
+ * Row mode reads 16-byte chunks aligned around the tap span of each source row; the first and last
+ * chunk of a row are clamped to the span, so no byte outside the tapped columns is ever touched.
  *   desc[n_masks]        one ufv_mask_desc per object-frame
  *   any_row_mode         non-zero iff some descriptor sets flags bit 0 (selects the kernel variant
  *                        that carries the row-mode flag table; 0 = lean tap-mode kernel)
@@ -208,8 +208,10 @@ typedef struct ufv_peer_args {
 int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
                       const ufv_peer_args* peer_host, void* stream);
 
-/* Block the stream until flags[0 .. n) (int32, local memory) all equal `value` (acquire.sys loads).
- * Gives up after ~timeout_ms (0 = 2000) and stores 1 to *timed_out (device int32, optional). */
+/* Block the stream until flags[0 .. n) (int32, local memory) have all reached `value` (>=, acquire.sys
+ * loads; step counters only grow).  Gives up after ~timeout_ms (0 = 2000) and stores 1 to *timed_out
+ * (optional int32 in device memory or device-mapped pinned host memory, where the host can poll it
+ * without synchronising). */
 int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,
                    void* stream);
 

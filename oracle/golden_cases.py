@@ -16,7 +16,10 @@ from ufvideo_b200 import synth
 # ---- (1) resize / binarise: SURVEY.md appendix B.1 -------------------------------------------
 RESIZE_SIZES = [(384, 384), (336, 336), (378, 378), (720, 1280), (480, 854), (1080, 1920),
                 (100, 37), (54, 54), (28, 28), (13, 13), (27, 27), (81, 81), (27, 100),
-                (100, 27), (26, 29), (1, 1), (2, 500)]
+                (100, 27), (26, 29), (1, 1), (2, 500),
+                # sizes where ATen's fused source-index evaluation decides a tap (round 2), and the largest
+                # video frames the eval drivers see
+                (3, 3), (5, 5), (9, 9), (3, 5), (1, 3), (2049, 2049), (9, 2049), (2160, 3840)]
 RESIZE_DENSITIES = [0.5, 0.05, 0.002]
 
 

@@ -12,7 +12,10 @@ import importlib.util
 import os
 import types
 
-_CANDIDATES = (os.environ.get("UFV_REF", ""), "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# $UFV_REF, the build container's read-only tree, or an install of the reference under baseline/_ref
+# (git-ignored; nothing in this repository puts reference sources there)
+_CANDIDATES = (os.environ.get("UFV_REF", ""), "/root/reference", os.path.join(_REPO, "baseline", "_ref"))
 
 
 def reference_layer_path():

@@ -86,6 +86,35 @@ def test_patch_bits_match_reference_golden(dev, golden_dir, mask_dtype, read_mod
         row += m["n"]
 
 
+@pytest.mark.parametrize("pad", [False, True])
+def test_patch_bits_equal_cuda_aten_interpolate_threshold(dev, pad):
+    """Kernel 1 against ATen's own CUDA bilinear kernel run on this GPU (layer.py:137-143, with the 'pad'
+    mode of layer.py:77-86): every input size 1..60 (up-sampling, the multiples of 27 where a tap weight is
+    exactly zero, and 3 / 5 / 9 where only the fused evaluation of the source index matches ATen), 81, 2049
+    (the fourth such size) and the 4K video frame sizes -- square and paired with another size."""
+    import torch.nn.functional as F
+    sizes = list(range(1, 61)) + [81, 2049, 2160, 3840]
+    shapes = [(n, n) for n in sizes] + [(n, sizes[(7 * i + 3) % len(sizes)]) for i, n in enumerate(sizes)]
+    for h, w in shapes:
+        g = torch.Generator(device="cpu").manual_seed(h * 4099 + w)
+        n = 3 if h * w <= 2049 * 2049 else 2
+        dens = torch.tensor([0.5, 0.02, 0.3])[:n, None, None]
+        masks = (torch.rand((n, h, w), generator=g) < dens).float().to(dev)
+        masks[0, 0, 0] = 1.0
+        masks[-1, h - 1, w - 1] = 1.0
+        ref = masks[None]
+        if pad:
+            side = max(h, w)
+            ref = F.pad(ref, ((side - w) // 2, (side - w) - (side - w) // 2, (side - h) // 2, (side - h) - (side - h) // 2))
+        if ref.shape[-2:] != (27, 27):
+            ref = F.interpolate(ref, size=(27, 27), mode="bilinear", align_corners=False)
+        want = (ref > 0)[0].reshape(n, -1).cpu().numpy()
+        plan = packer.build_plan([masks], [[list(range(n))]], n, 1, dev, pad_square=pad, use_cache=False)
+        out = layer.mask_to_patches(plan, dev)
+        assert np.array_equal(bits_to_bool(out["bits"]), want), (h, w, pad)
+        assert np.array_equal(out["cnt"].cpu().numpy(), want.sum(1)), (h, w, pad)
+
+
 def test_patch_bits_pad_mode_and_strided_masks(dev):
     masks = synth.masks_blob(3, 2, 3, 480, 854)
     want = np.stack([R.mask_to_patches(m, pad_square=True) for m in masks])
@@ -383,6 +412,74 @@ def test_repeated_calls_replay_and_stay_identical(dev, dtype):
     want, n_want = ref(feats, flipped, None, case["ann"], None)
     got, n_got = enc(feats, flipped, None, case["ann"], None)
     assert n_got == n_want and torch.equal(got, want)
+
+
+def test_pageable_host_masks_are_recopied_on_every_call(dev):
+    """Masks in pageable host memory are copied by the packer: the copy must outlive the launches that read
+    it, and a second call with the SAME tensor objects but edited content must see the new content (the
+    identity fast path may not skip the copy).  Same for the zero mask that replaces an empty sample."""
+    case = gc.e2e_case("bf16")
+    enc = make_encoder(dev, "bf16", 8)
+    ref = make_encoder(dev, "bf16", 8)
+    feats = torch.from_numpy(case["feats"]).to(dev).bfloat16()
+    host = [torch.from_numpy(m.copy()).float() for m in case["masks"]]          # pageable CPU tensors
+    assert not host[0].is_pinned()
+    for round_ in range(3):
+        want, n_want = ref(feats, [m.to(dev) for m in host], None, case["ann"], None)
+        junk = [torch.randn(1 << 20, device=dev) for _ in range(4)]                # churn the caching allocator
+        got, n_got = enc(feats, host, None, case["ann"], None)
+        del junk
+        assert n_got == n_want and torch.equal(got, want), round_
+        for m in host:                                                           # in-place edit, same objects
+            m.copy_(m.flip(1) if round_ == 0 else m.roll(17, 2))
+    # strided (non-contiguous) device masks are copied too
+    wide = torch.zeros((host[0].shape[0], host[0].shape[1], host[0].shape[2] * 2), device=dev)
+    wide[:, :, ::2] = host[0].to(dev)
+    a, na = enc(feats, [wide[:, :, ::2]] + [m.to(dev) for m in host[1:]], None, case["ann"], None)
+    b, nb = ref(feats, [m.to(dev) for m in host], None, case["ann"], None)
+    assert na == nb and torch.equal(a, b)
+
+
+def test_empty_sample_twice_and_next_to_a_real_sample(dev):
+    """layer.py:73-75 on repeated calls: the substituted zero mask is process-owned, never a dangling copy."""
+    feats_np = synth.features(600, 4)
+    feats = torch.from_numpy(feats_np).to(dev)
+    real = synth.masks_blob(5, 1, 2, 64, 64)
+    enc = make_encoder(dev, "f32", 8)
+    empty = torch.zeros((0, 336, 336), dtype=torch.uint8)
+    outs = []
+    for _ in range(3):
+        junk = torch.randn(1 << 20, device=dev)
+        t, c = enc(feats, [empty, torch.from_numpy(real).to(dev)], None, [[[1]], [[2, 3]]], None)
+        del junk
+        outs.append((t.clone(), c))
+    o = R.encode(feats_np, [np.zeros((0, 336, 336), np.uint8), real], [[[1]], [[2, 3]]], 8, "f32", synth.make_weights(0))
+    for t, c in outs:
+        assert c == o["counts"] and np.abs(t.cpu().numpy() - o["tokens"]).max() <= 1e-5
+        assert torch.equal(t, outs[0][0])
+
+
+def test_two_modules_and_two_streams_share_a_plan_without_interfering(dev):
+    """Run state is per (module, stream): a second module or stream hitting the same cached plan neither
+    drops the first one's captured graph nor shares its pinned counts words."""
+    case = gc.e2e_case("bf16")
+    a, b = make_encoder(dev, "bf16", 8), make_encoder(dev, "bf16", 8)
+    feats = torch.from_numpy(case["feats"]).to(dev).bfloat16()
+    masks = [torch.from_numpy(m).to(dev) for m in case["masks"]]
+    first, n_first = a(feats, masks, None, case["ann"], None)
+    side = torch.cuda.Stream(dev)
+    for _ in range(3):
+        x, nx = a(feats, masks, None, case["ann"], None)
+        y, ny = b(feats, masks, None, case["ann"], None)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            z, nz = a(feats, masks, None, case["ann"], None)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        assert nx == ny == nz == n_first
+        assert torch.equal(x, first) and torch.equal(y, first) and torch.equal(z, first)
+    plan = a.last_plan
+    assert plan is b.last_plan and len(plan.runs) == 3
+    assert sum(bool(r["graphs"]) for r in plan.runs.values()) >= 2
 
 
 def test_list_and_tensor_mask_forms_agree(dev):

@@ -83,7 +83,7 @@ def fine_grained():
         t0 = time.perf_counter()
         tokens, counts, plan = enc.encode_padded(ft, md, ann)
         t1 = time.perf_counter()
-        layer._await_counts(plan, dev)
+        layer._await_counts(plan, plan.run, dev)
         t2 = time.perf_counter()
         acc["encode_padded total"] += t1 - t0
         acc["await counts"] += t2 - t1

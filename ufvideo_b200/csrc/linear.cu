@@ -385,7 +385,7 @@ __global__ void peer_tail_only_kernel(const __grid_constant__ ufv_peer_args peer
   }
 }
 
-// ---- receiver side of the fused all-gather: spin until every rank's flag carries `value` ------------
+// ---- receiver side of the fused all-gather: spin until every rank's flag has reached `value` ---------
 __global__ void wait_flags_kernel(const int32_t* __restrict__ flags, int n, int32_t value, long long timeout_ns,
                                   int32_t* __restrict__ timed_out) {
   pdl_wait();
@@ -397,12 +397,14 @@ __global__ void wait_flags_kernel(const int32_t* __restrict__ flags, int n, int3
   for (;;) {
     int32_t v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
-    if (v == value) return;
-    __nanosleep(200);
+    if (v >= value) return;          // step counters only grow: a peer that is already further along also counts
     long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     if (t1 - t0 > timeout_ns) {
-      if (timed_out != nullptr) *timed_out = 1;
+      if (timed_out != nullptr) {     // may point into pinned host memory: the host sees it without a sync
+        *reinterpret_cast<volatile int32_t*>(timed_out) = 1;
+        __threadfence_system();
+      }
       return;
     }
   }

@@ -17,16 +17,21 @@
 namespace ufv {
 
 // ---- host: tap table ------------------------------------------------------------------------------
-// fp32 arithmetic in the same order ATen uses (area_pixel_compute_source_index, then
-// guard_index_and_lambda): scale = in / out; src = max(scale * (i + 0.5) - 0.5, 0);
-// i0 = min(floor(src), in - 1); lambda1 = clamp(src - i0, 0, 1); lambda0 = 1 - lambda1;
-// i1 = i0 + (i0 < in - 1).  A tap is kept iff its lambda is > 0.
+// fp32 arithmetic exactly as ATen evaluates it (area_pixel_compute_source_index, then
+// guard_index_and_lambda): scale = in / out; src = max(fma(scale, i + 0.5, -0.5), 0) -- ATen's
+// `scale * (dst + 0.5) - 0.5` is compiled to ONE fused multiply-add on both of its back ends (gcc
+// -ffp-contract for the CPU kernels, nvcc's default contraction for CUDA), i.e. a single rounding of the
+// exact product minus 0.5.  Rounding the product first moves src across an integer for n_in = 3, 5, 9 and
+// 2049 (out = 27) and changes one tap each.  i0 = min(floor(src), in - 1); lambda1 = clamp(src - i0, 0, 1);
+// lambda0 = 1 - lambda1; i1 = i0 + (i0 < in - 1).  A tap is kept iff its lambda is > 0.
 static void axis_taps(int n_in, int n_out, int32_t* t0, int32_t* t1) {
-  const volatile float scale = static_cast<float>(n_in) / static_cast<float>(n_out);
+  const float scale = static_cast<float>(n_in) / static_cast<float>(n_out);
   for (int i = 0; i < n_out; ++i) {
-    volatile float a = static_cast<float>(i) + 0.5f;   // volatile: no fma contraction, no x87 excess
-    volatile float b = scale * a;
-    volatile float src = b - 0.5f;
+    // the product scale * (i + 0.5) has at most 24 + 6 significant bits and the subtraction of 0.5 stays
+    // inside 53 bits: the double expression is exact, and its single rounding to fp32 IS the fma result
+    // (no dependence on the host compiler's contraction flags or on fmaf being hardware-backed)
+    const double exact = static_cast<double>(scale) * (static_cast<double>(i) + 0.5) - 0.5;
+    volatile float src = static_cast<float>(exact);
     if (src < 0.0f) src = 0.0f;
     int i0 = static_cast<int>(floorf(src));
     if (i0 > n_in - 1) i0 = n_in - 1;
@@ -173,6 +178,24 @@ __device__ __forceinline__ uint32_t chunk_flags(uint4 v, int dtype) {
   return f;
 }
 
+// One 16-byte chunk of a source row in row mode.  Chunks are aligned to 16 bytes around the tap span
+// [lo, hi) of the row, so the first and the last chunk of a row may reach past the span: those are
+// assembled from element loads of the in-span elements only (zeros elsewhere), and the kernel never
+// touches a byte outside the columns its taps name -- caller-owned pinned host memory included.
+__device__ __forceinline__ uint4 load_chunk_clamped(uint64_t chunk_addr, uint64_t lo, uint64_t hi, int es) {
+  if (chunk_addr >= lo && chunk_addr + 16 <= hi) return *reinterpret_cast<const uint4*>(chunk_addr);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  for (int b = 0; b < 16; b += es) {
+    const uint64_t a = chunk_addr + b;
+    if (a < lo || a + es > hi) continue;
+    const uint32_t e = es == 4   ? *reinterpret_cast<const uint32_t*>(a)
+                       : es == 2 ? uint32_t(*reinterpret_cast<const uint16_t*>(a))
+                                 : uint32_t(*reinterpret_cast<const uint8_t*>(a));
+    w[b >> 2] |= e << (8 * (b & 3));
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // exclusive prefix of per-word popcounts, computed by warp 0; s_prefix[UFV_BITS_WORDS] = total
 __device__ __forceinline__ void word_prefix(const uint32_t* s_words, int32_t* s_prefix, int tid) {
   if (tid < 32) {
@@ -287,7 +310,7 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
           const uint64_t first = d.addr + uint64_t(int64_t(max(r, 0)) * d.pitch + cmin) * es;
           const int mis = int(first & 15u);
           if (r >= 0 && chunk[u] < ((mis + span_bytes + 15) >> 4))
-            v[u] = reinterpret_cast<const uint4*>(first - mis)[chunk[u]];
+            v[u] = load_chunk_clamped(first - mis + 16ull * chunk[u], first, first + span_bytes, es);
         }
       }
 #pragma unroll

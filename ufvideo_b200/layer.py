@@ -138,11 +138,11 @@ def gather_rows(x: torch.Tensor, row_map: torch.Tensor):
     return out
 
 
-def _await_counts(plan: packer.EncodePlan, device, idle_work=None) -> np.ndarray:
+def _await_counts(plan: packer.EncodePlan, run: dict, device, idle_work=None) -> np.ndarray:
     """Poll the pinned words kernel 3 writes, (epoch << 16) | count per object, until all of them
     carry this call's epoch; returns the int32 counts.  ``idle_work`` (optional callable) runs once
     first: the host has ~60 us to kill here, which is where the next call's output tensor gets allocated."""
-    words, epoch = plan.counts_np[:plan.n_obj], plan.epoch
+    words, epoch = run["counts_np"][:plan.n_obj], run["epoch"]
     if idle_work is not None:
         idle_work()
     last = plan.n_obj - 1
@@ -315,13 +315,17 @@ class MaskExtractor(nn.Module):
                                  self.image_aspect_ratio == "pad", side)
         self.last_plan = plan
         q, m_pad = plan.n_masks, plan.m_pad
-        run = plan.run
+        # Run state (workspace, argument struct, pinned counts words, captured graphs) belongs to ONE
+        # (module, stream) pair: two modules or two streams that meet on the same cached plan neither rebind
+        # nor race on each other's buffers.  plan.run is the state of the latest call (introspection).
+        run_key = (id(self), stream)
+        run = plan.runs.get(run_key)
         if run is None or run["sig"] != sig:
             shape_sig = (dt, f, c, hid, two, k_keep, side)
             if run is not None and run["shape_sig"] == shape_sig:
-                # same sizes, other pointers / stream: keep the workspace, rebind, drop captured graphs
-                self._drop_graphs(run)
-                run.pop("spare_out", None)        # was allocated for the previous stream
+                # same sizes, other pointers: keep the workspace, rebind, drop captured graphs
+                packer.release_run(run)
+                run.pop("spare_out", None)
                 run["sig"] = sig
                 if two:
                     a = run["args"]
@@ -330,9 +334,12 @@ class MaskExtractor(nn.Module):
                     a.w2, a.b2 = linears[1].weight.data_ptr(), linears[1].bias.data_ptr()
             else:
                 if run is not None:
-                    self._drop_graphs(run)
-                run = plan.run = self._prepare_run(plan, sig, feats, linears, side, k_keep, device)
+                    packer.release_run(run)
+                run = plan.runs[run_key] = self._prepare_run(plan, sig, feats, linears, side, k_keep, device)
                 run["shape_sig"] = shape_sig
+                while len(plan.runs) > packer.RUNS_PER_PLAN:      # oldest (module, stream) pair goes first
+                    packer.release_run(plan.runs.pop(next(iter(plan.runs))))
+        plan.run = self._last_run = run
         if peer is not None and not two:
             raise ValueError("peer gather needs the depth-2 projector path")
         if out is None:
@@ -362,7 +369,7 @@ class MaskExtractor(nn.Module):
         ptr = run["ptr"]
         d = plan.dev
         if two:                                   # the reference's depth=2 projector: one chained call
-            epoch = plan.epoch = plan.epoch % 32767 + 1            # 1 .. 32767, the tag of this call's counts
+            epoch = run["epoch"] = run["epoch"] % 32767 + 1        # 1 .. 32767, the tag of this call's counts
             graph = None
             if _awaited and USE_CUDA_GRAPH and dt != _cabi.UFV_F32 and q > 0 and plan.n_obj > 0 and m_pad > 0:
                 # A caller that waits for the counts before its next call (forward, forward_padded) lets
@@ -443,13 +450,13 @@ class MaskExtractor(nn.Module):
 
         run = {"sig": sig, "ws": ws, "ptr": ptr, "view": view,
                "counts": view("counts", torch.int32, (plan.n_obj,)), "graphs": {}, "awaited_calls": 0,
-               "validated": set()}
+               "validated": set(), "epoch": 0}
         if two:
             d = plan.dev
-            if plan.counts_pinned is None:        # pinned int32 [n_obj]: (epoch << 16) | count per object
-                plan.counts_pinned = torch.zeros((max(plan.n_obj, 1),), dtype=torch.int32).pin_memory()
-                plan.counts_np = plan.counts_pinned.numpy()
-                plan.counts_dev_addr = packer._device_address(plan.counts_pinned)
+            # pinned int32 [n_obj]: (epoch << 16) | count per object, written by kernel 3, polled by the host
+            run["counts_pinned"] = torch.zeros((max(plan.n_obj, 1),), dtype=torch.int32).pin_memory()
+            run["counts_np"] = run["counts_pinned"].numpy()
+            counts_dev_addr = packer._device_address(run["counts_pinned"])
             a = _cabi.EncodeArgs(
                 feats=feats.data_ptr(), feat_dtype=dt, n_patch_side=side, n_rows=f, c=c, hid=hid,
                 mask_desc=d["mask_desc"], taps=d["taps"], n_masks=q, idx_pitch=0,
@@ -461,7 +468,7 @@ class MaskExtractor(nn.Module):
                 obj_len=d["obj_len"], slot_off=d["slot_off"], n_obj=plan.n_obj, max_len=plan.max_len,
                 k_keep=k_keep, m_pad=m_pad, merged=ptr["merged"], counts=ptr["counts"],
                 sims=ptr["sims"], sims_pitch=max(plan.max_len, 1),
-                counts_host=plan.counts_dev_addr, epoch=0,
+                counts_host=counts_dev_addr, epoch=0,
                 w1=linears[0].weight.data_ptr(), b1=linears[0].bias.data_ptr(),
                 w2=linears[1].weight.data_ptr(), b2=linears[1].bias.data_ptr(),
                 hidden=ptr["hidden"], tokens_out=None)
@@ -474,14 +481,6 @@ class MaskExtractor(nn.Module):
             run["dyn_peer_addr"] = pinned.data_ptr() + _cabi.DynArgs.peer.offset
             run["dyn_src_addr"] = packer._device_address(pinned)
         return run
-
-    @staticmethod
-    def _drop_graphs(run):
-        for handle in run["graphs"].values():
-            _cabi.lib().ufv_encode_graph_destroy(handle)
-        run["graphs"].clear()
-        run["awaited_calls"] = 0
-        run.pop("graph_args", None)
 
     def _capture_graph(self, run, peer):
         """Capture the launch sequence of this run once (include/ufv_b200.h: ufv_encode_graph_create)."""
@@ -511,8 +510,9 @@ class MaskExtractor(nn.Module):
         kernel, plan).  What the clip-sharded driver gathers (sharding.all_gather_payload)."""
         with self._on_module_device():
             tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, out, counts_out, peer, _awaited=True)
-            if plan.run.get("args") is not None and plan.n_obj > 0:
-                return tokens, _await_counts(plan, tokens.device), plan
+            run = self._last_run
+            if run.get("args") is not None and plan.n_obj > 0:
+                return tokens, _await_counts(plan, run, tokens.device), plan
             return tokens, counts.cpu().numpy(), plan
 
     def _forward_with_grad(self, feats, masks, ann_indices):
@@ -556,12 +556,12 @@ class MaskExtractor(nn.Module):
             return self._forward_with_grad(feats, masks, ann_indices)
         tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, _awaited=True)
         # the one unavoidable D2H: the caller slices rows by these counts (videorefer_arch.py:307-311)
-        if plan.run.get("args") is not None and plan.n_obj > 0:
+        run = self._last_run
+        if run.get("args") is not None and plan.n_obj > 0:
             # the merge kernel stores the counts straight into pinned host memory, tagged with the call's
             # epoch; the projector may still be running when this returns
-            run = plan.run
             region_token_nums = _await_counts(
-                plan, tokens.device,
+                plan, run, tokens.device,
                 lambda: run.__setitem__("spare_out", torch.empty_like(tokens)) if "spare_out" not in run else None)
         else:
             region_token_nums = counts.cpu().numpy()

@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes
 import itertools
 import marshal
+import threading
 import weakref
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -38,6 +39,25 @@ READ_MODE = "auto"          # "auto": row mode for host-resident masks, tap mode
 _tap_cache: dict = {}
 _plan_cache: "OrderedDict[tuple, EncodePlan]" = OrderedDict()
 PLAN_CACHE_SIZE = 16
+RUNS_PER_PLAN = 4           # (module, stream) pairs that keep their own run state on one cached plan
+_lock = threading.RLock()   # plan cache, tap cache and the identity fast path are process-wide
+
+
+def release_run(run: dict) -> None:
+    """Destroy the CUDA graph execs a run captured (a graph still executing is released by the driver when
+    it completes).  Called when a run is rebound to other pointers and when its plan leaves the cache."""
+    for handle in run["graphs"].values():
+        _cabi.lib().ufv_encode_graph_destroy(handle)
+    run["graphs"].clear()
+    run["awaited_calls"] = 0
+    run.pop("graph_args", None)
+
+
+def _evict(plan: "EncodePlan") -> None:
+    for run in plan.runs.values():
+        release_run(run)
+    plan.runs.clear()
+    plan.run = None
 
 
 def tap_table(h: int, w: int, n_out: int, pad_square: bool) -> np.ndarray:
@@ -70,15 +90,15 @@ class EncodePlan:
     sample_of: np.ndarray | None = None           # int32 [q] sample each object-frame came from
     plane_off: np.ndarray | None = None           # int64 [q] byte offset of its plane in that sample
     base_ptrs: tuple = ()                         # mask tensor base addresses baked into ``buffer``
-    run: dict | None = None                       # workspace + ctypes EncodeArgs of the last call (layer.py)
-    counts_np: np.ndarray | None = None           # numpy view of counts_pinned[:n_obj]
-    counts_pinned: torch.Tensor | None = None     # pinned int32 [n_obj]: early read-back of the counts
-    counts_dev_addr: int = 0                      # device-visible address of counts_pinned
-    keepalive: object = None                      # run-length sample buffers of the last call
+    run: dict | None = None                       # run state of the latest call (introspection; layer.py)
+    runs: dict = field(default_factory=dict)      # (module id, stream) -> workspace, EncodeArgs, pinned counts
+                                                  # words, captured graphs of that pair (layer.py)
+    keepalive: object = None                      # buffers the packer itself created for the last call (copies of
+                                                  # host / strided / exotic masks, run-length uploads): the
+                                                  # descriptors point into them
     rle_rows: list = field(default_factory=list)  # run-length samples: descriptor rows refreshed on every call
     cache_key: object = None                      # key under which the plan sits in the plan cache
     any_row_mode: int = 0                         # some descriptor asks for row mode (kernel 1 variant)
-    epoch: int = 0                                # tag of the last call's counts words (1 .. 32767)
     expect_counts: list = field(default_factory=list)
     slots_bytes: bytes = b""                      # ``slots`` as bytes: the no-ties fast comparison
 
@@ -118,20 +138,30 @@ class RleSample:
 
 def _as_mask_list(masks, device):
     """Reference contract: list of [q_i, H_i, W_i] tensors, or one
-    [B, q, H, W] tensor whose len() is the sample count."""
-    out = []
+    [B, q, H, W] tensor whose len() is the sample count.
+
+    Returns (list, temporaries).  ``temporaries`` are the buffers created HERE -- device copies of
+    pageable-host / other-device / non-contiguous / exotic-dtype masks, the zero mask that stands in for
+    an empty sample, uploaded run-length buffers.  Their addresses go into the plan's descriptors, so the
+    plan must keep them alive until its next call replaces them, and a call that needed any of them may not
+    be short-cut by the identity fast path (their content has to be copied again)."""
+    out, temps = [], []
     for i in range(len(masks)):
         m = masks[i]
         if isinstance(m, RleSample) or _rle.is_rle_sample(m):        # COCO run-length masks, never densified
-            out.append(m if isinstance(m, RleSample) else RleSample(m, device))
+            if not isinstance(m, RleSample):
+                m = RleSample(m, device)
+            temps.append(m)                      # also caller-built RleSamples: the plan pins what it points into
+            out.append(m)
             continue
         if not torch.is_tensor(m):
             m = torch.as_tensor(m)
+        given = m
         shape = m.shape
         if len(shape) != 3:
             raise ValueError(f"masks[{i}] must be [q, H, W], got {tuple(shape)}")
         if shape[0] == 0:                        # layer.py:73-75: substitute one all-zero mask
-            m = torch.zeros((1, 336, 336), dtype=torch.uint8, device=device)
+            m = _zero_mask(device)
         if m.dtype not in _MASK_DTYPES:          # exotic dtypes: binarise once on the device
             m = (m.to(device) > 0).to(torch.uint8)
         if m.device != device:
@@ -141,8 +171,21 @@ def _as_mask_list(masks, device):
                 m = m.to(device, non_blocking=True)
         if m.stride(-1) != 1:
             m = m.contiguous()
+        if m is not given and (not torch.is_tensor(given) or m.data_ptr() != given.data_ptr() or m.device != given.device):
+            temps.append(m)
         out.append(m)
-    return out
+    return out, temps
+
+
+_zero_masks: dict = {}
+
+
+def _zero_mask(device):
+    """The all-zero 336 x 336 mask of layer.py:73-75, one per device for the life of the process (read-only)."""
+    z = _zero_masks.get(device)
+    if z is None:
+        z = _zero_masks[device] = torch.zeros((1, 336, 336), dtype=torch.uint8, device=device)
+    return z
 
 
 def _device_address(m: torch.Tensor) -> int:
@@ -167,6 +210,11 @@ _last_call: list = [None]     # (mask tensor objects, their data_ptrs and shapes
 
 def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_square: bool = False,
                n_out: int = _cabi.MAX_PATCH_SIDE, use_cache: bool = True) -> EncodePlan:
+    with _lock:
+        return _build_plan_locked(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, use_cache)
+
+
+def _build_plan_locked(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, use_cache) -> EncodePlan:
     # Fastest path: the very same mask tensor objects (same storage, same shape) and the same index
     # content as the previous call -> the previous plan, without re-deriving any descriptor.  The index
     # lists are compared by value against a private copy (a nested list compare runs at C speed).
@@ -189,7 +237,11 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
             ann_bytes = None
     plan = _lookup_or_build(masks, ann_indices, ann_bytes, n_feat_rows, k_keep, device, pad_square, n_out,
                             use_cache)
-    if use_cache and ann_bytes is not None and torch.is_tensor(masks) is False:
+    if plan.keepalive:
+        # some mask was copied / converted for this call: the next call must take the slow path again so that
+        # the copy is refreshed (in-place edits of host masks) and the descriptors point at live memory
+        _last_call[0] = None
+    elif use_cache and ann_bytes is not None and torch.is_tensor(masks) is False:
         try:
             _last_call[0] = ([(weakref.ref(m), m.data_ptr(), m.shape) for m in masks], None, scalars,
                              marshal.loads(ann_bytes), plan)
@@ -200,7 +252,7 @@ def build_plan(masks, ann_indices, n_feat_rows: int, k_keep: int, device, pad_sq
 
 def _lookup_or_build(masks, ann_indices, ann_bytes, n_feat_rows, k_keep, device, pad_square, n_out,
                      use_cache) -> EncodePlan:
-    masks = _as_mask_list(masks, device)
+    masks, temps = _as_mask_list(masks, device)
     if len(ann_indices) != len(masks):
         raise ValueError("ann_indices and masks disagree on the number of samples")
     ptrs = tuple(_device_address(m) for m in masks)
@@ -216,13 +268,17 @@ def _lookup_or_build(masks, ann_indices, ann_bytes, n_feat_rows, k_keep, device,
             _plan_cache.move_to_end(key)
             if plan.base_ptrs != ptrs or plan.rle_rows:   # same structure, new mask data: patch descriptors
                 _patch_addresses(plan, ptrs, device, masks)
+            # buffers made for this call replace those of the previous one; the old ones return to the caching
+            # allocator, which hands them out again only to work ordered after the launches that read them
+            plan.keepalive = temps or None
             return plan
     plan = _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, ptrs)
+    plan.keepalive = temps or None
     plan.cache_key = key
     if key is not None:
         _plan_cache[key] = plan
         while len(_plan_cache) > PLAN_CACHE_SIZE:
-            _plan_cache.popitem(last=False)
+            _evict(_plan_cache.popitem(last=False)[1])
     return plan
 
 
@@ -341,7 +397,6 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
                       any_row_mode=any_row_mode, rle_rows=rle_rows)
     plan.ticket = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)   # self-resetting
     _fill_addresses(plan, ptrs)
-    plan.keepalive = [m for m in masks if isinstance(m, RleSample)] if rle_rows else None
     _upload(plan, device)
     return plan
 
@@ -359,8 +414,6 @@ def _fill_addresses(plan: EncodePlan, ptrs, masks=None) -> None:
 
 def _patch_addresses(plan: EncodePlan, ptrs, device, masks=None) -> None:
     _fill_addresses(plan, ptrs, masks)
-    # run-length buffers must outlive the launches that read them (dense mask tensors belong to the caller)
-    plan.keepalive = [m for m in masks if isinstance(m, RleSample)] if masks is not None else None
     desc = plan.host["mask_desc"]
     staging = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy())
     if device.type == "cuda":
@@ -382,4 +435,4 @@ def _upload(plan: EncodePlan, device) -> None:
     plan.buffer = staging.to(device, non_blocking=True)
     p0 = plan.buffer.data_ptr()
     plan.dev = {name: p0 + off for name, off in offsets.items()}
-    plan.run = None
+    _evict(plan)

@@ -191,10 +191,15 @@ class PeerGather:
                              and self.flag_h.has_multicast_support and self.buf_h.multicast_ptr
                              and self.flag_h.multicast_ptr)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
-        self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
+        # time-out word of ufv_wait_flags: pinned host memory the wait kernel writes through its mapped
+        # address, so wait() / gathered() / check() notice a time-out without synchronising
+        from . import packer
+        self.timed_out = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._timed_out_np = self.timed_out.numpy()
+        self._timed_out_dev = packer._device_address(self.timed_out)
         self.step = 0
         self._wait_fn = _cabi.lib().ufv_wait_flags
-        self._flags_ptr, self._timed_out_ptr = self.flags.data_ptr(), self.timed_out.data_ptr()
+        self._flags_ptr, self._timed_out_ptr = self.flags.data_ptr(), self._timed_out_dev
         self._static = {}                         # slot -> (slots bytes, tokens view, counts view)
         self._args = [self._make_args(s) for s in range(ring)]
 
@@ -243,7 +248,10 @@ class PeerGather:
         return a, cached[1], cached[2], step
 
     def wait(self, step: int) -> None:
-        """Make the current stream wait until every rank's rows of ``step`` are in this rank's copy."""
+        """Make the current stream wait until every rank's rows of ``step`` are in this rank's copy.
+        Raises if an earlier wait on this object gave up (a peer never raised its flag): the stream would
+        otherwise run on over a half-filled gathered buffer."""
+        self.check()
         slot = step % self.ring
         rc = self._wait_fn(self._flags_ptr + slot * self.world * 4, self.world, step + 1, 10000, self._timed_out_ptr,
                            torch._C._cuda_getCurrentRawStream(self.device.index))
@@ -252,8 +260,11 @@ class PeerGather:
 
     def gathered(self, step: int) -> torch.Tensor:
         """This rank's copy of the gathered result of ``step``: [world, pad_rows + tail, hid]."""
+        self.check()
         return self.buf[step % self.ring]
 
     def check(self) -> None:
-        if int(self.timed_out.item()):
-            raise RuntimeError("PeerGather: timed out waiting for a peer's arrival flag")
+        """Raise if a wait kernel that has already run gave up (reads one pinned host word, no sync)."""
+        if int(self._timed_out_np[0]):
+            raise RuntimeError("PeerGather: timed out waiting for a peer's arrival flag; the gathered "
+                               "buffer of that step is incomplete")
