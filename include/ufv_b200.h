@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UFV_ABI_VERSION 7
+#define UFV_ABI_VERSION 8
 
 /* element types */
 enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3, UFV_RLE = 4 /* masks only */ };
@@ -170,9 +170,14 @@ int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t*
  *   `dtype` (the reference rounds the hidden activation between modules, layer.py:55-59).
  * UFV_BF16 / UFV_F16: tcgen05 tensor-core GEMM with TMEM accumulators (fp32 accumulate);
  * UFV_F32: fp32 CUDA-core GEMM.  x, w, y row-major, 16-byte aligned, k % 8 == 0, n % 8 == 0.
+ * Few tokens (m <= 512) and a deep contraction (k >= 2048): K is split over a thread-block cluster
+ * whose CTAs exchange fp32 partial tiles through `ws` (device scratch of at least
+ * ufv_linear_ws_bytes(m, n, k, dtype) bytes, 16-byte aligned; contents are don't-care on entry and exit).
+ * With ws == null (or too small) the full-K kernel runs instead: same result up to fp32 summation order.
  * -------------------------------------------------------------------------------------------*/
+int64_t ufv_linear_ws_bytes(int m, int n, int k, int dtype);
 int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-               int dtype, int gelu, void* stream);
+               int dtype, int gelu, void* ws, int64_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 4 fused with the result-collection all-gather (multi-GPU, clips sharded over ranks).
@@ -206,7 +211,7 @@ typedef struct ufv_peer_args {
 /* y[m, n] = x . w^T + bias (bf16 / fp16, no activation), written to every peer->dst instead of a
  * local y. */
 int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
-                      const ufv_peer_args* peer_host, void* stream);
+                      const ufv_peer_args* peer_host, void* ws, int64_t ws_bytes, void* stream);
 
 /* Block the stream until flags[0 .. n) (int32, local memory) have all reached `value` (>=, acquire.sys
  * loads; step counters only grow).  Gives up after ~timeout_ms (0 = 2000) and stores 1 to *timed_out
@@ -253,6 +258,8 @@ typedef struct ufv_encode_args {
   /* projector: feat_linear.0 / feat_linear.2 (layer.py:55-59) */
   const void* w1; const void* b1; const void* w2; const void* b2;
   void* hidden; void* tokens_out;
+  /* scratch of the split-K Linears (ufv_linear): max over the two layers of ufv_linear_ws_bytes; may be null */
+  void* gemm_ws; int64_t gemm_ws_bytes;
   /* optional: fuse the result-collection all-gather into the last Linear (ufv_linear_gather);
    * tokens_out is then unused */
   const ufv_peer_args* peer;

@@ -40,7 +40,7 @@ def test_argument_errors_are_reported_not_crashed():
     assert lib.ufv_tap_table(0, 5, 27, 0, buf.ctypes.data) == -2  # UFV_E_SHAPE
     assert b"out of range" in lib.ufv_last_error()
     with pytest.raises(_cabi.UfvError):
-        _cabi.check(lib.ufv_linear(None, None, None, None, 4, 8, 8, 1, 0, None))
+        _cabi.check(lib.ufv_linear(None, None, None, None, 4, 8, 8, 1, 0, None, 0, None))
 
 
 @pytest.mark.parametrize("hw", [(384, 384), (720, 1280), (480, 854), (100, 37), (27, 27), (81, 81),

@@ -21,7 +21,7 @@ BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 8
 PLAN_PITCH = 736
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -57,7 +57,8 @@ class EncodeArgs(C.Structure):
         ("merged", _p), ("counts", _p), ("sims", _p), ("sims_pitch", _i32), ("reserved0", _i32),
         ("counts_host", _p), ("epoch", _i32), ("reserved", _i32),
         ("w1", _p), ("b1", _p), ("w2", _p), ("b2", _p),
-        ("hidden", _p), ("tokens_out", _p), ("peer", C.POINTER(PeerArgs)),
+        ("hidden", _p), ("tokens_out", _p), ("gemm_ws", _p), ("gemm_ws_bytes", _i64),
+        ("peer", C.POINTER(PeerArgs)),
         ("dyn_src", _p), ("dyn_dev", _p),
     ]
 
@@ -84,8 +85,10 @@ _SIGNATURES = {
     "ufv_mask_pool_backward": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p]),
     "ufv_ttm": (C.c_int, [_p, C.c_int, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p,
                           _p, C.c_int, _p, C.c_int, _p, _i32, _p]),
-    "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
-    "ufv_linear_gather": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PeerArgs), _p]),
+    "ufv_linear_ws_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _i64, _p]),
+    "ufv_linear_gather": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PeerArgs), _p, _i64,
+                                    _p]),
     "ufv_wait_flags": (C.c_int, [_p, C.c_int, _i32, C.c_int, _p, _p]),
     "ufv_encode_graph_create": (C.c_int, [C.POINTER(EncodeArgs), C.POINTER(_p)]),
     "ufv_encode_graph_launch": (C.c_int, [_p, _p]),

@@ -19,7 +19,7 @@ int ttm_dispatch(const float* pooled, int c, const int32_t* obj_start, const int
                  int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
                  int32_t epoch, const ufv_dyn_args* dyn, void* stream);
 int last_linear_dyn(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
-                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* stream);
+                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes, void* stream);
 
 static_assert(sizeof(ufv_dyn_args) == 256, "ufv_dyn_args must stay 256 bytes (kernel 1 copies 64 words)");
 
@@ -253,16 +253,19 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
   if (rc != 0) return rc;
   if (a->m_pad == 0)
     return a->peer != nullptr
-               ? ufv_linear_gather(nullptr, nullptr, nullptr, 0, a->hid, a->hid, a->feat_dtype, a->peer, stream)
+               ? ufv_linear_gather(nullptr, nullptr, nullptr, 0, a->hid, a->hid, a->feat_dtype, a->peer, nullptr, 0, stream)
                : 0;
-  rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, stream);
+  rc = ufv_linear(a->merged, a->w1, a->b1, a->hidden, a->m_pad, a->hid, a->c, a->feat_dtype, 1, a->gemm_ws,
+                  a->gemm_ws_bytes, stream);
   if (rc != 0) return rc;
   if (dyn_mode)             // output pointer / all-gather destinations are read from the device block
-    return last_linear_dyn(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, dyn, stream);
+    return last_linear_dyn(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, dyn,
+                           a->gemm_ws, a->gemm_ws_bytes, stream);
   if (a->peer != nullptr)   // last Linear fused with the all-gather: tiles go straight to every rank
-    return ufv_linear_gather(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, stream);
+    return ufv_linear_gather(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, a->gemm_ws,
+                             a->gemm_ws_bytes, stream);
   return ufv_linear(a->hidden, a->w2, a->b2, a->tokens_out, a->m_pad, a->hid, a->hid, a->feat_dtype, 0,
-                    stream);
+                    a->gemm_ws, a->gemm_ws_bytes, stream);
 }
 
 // ---- graph replay ---------------------------------------------------------------------------------------

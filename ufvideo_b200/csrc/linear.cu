@@ -148,6 +148,35 @@ __device__ __forceinline__ void peer_store16(const ufv_peer_args& peer, bool mul
   }
 }
 
+// Closing protocol of the fused all-gather, called by every thread of every CTA after its remote stores are
+// fenced: the CTA that finishes last forwards the tail (reserved rows + token counts) and then raises this
+// rank's arrival flag in every destination: flag >= flag_value  =>  every byte of the call landed.
+__device__ __forceinline__ void peer_finish(const ufv_peer_args& peer, unsigned n_ctas) {
+  __shared__ int s_is_last;
+  if (threadIdx.x == 0) s_is_last = (atomicAdd(peer.ticket, 1u) == n_ctas - 1);
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  for (int wi = threadIdx.x; wi < peer.tail_words; wi += kGemmThreads) {
+    const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(peer.tail_src) + wi);
+    if (peer.multimem) {
+      st_multimem_u32(peer.tail_dst[0] + 4ull * wi, v);
+    } else {
+      for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint32_t*>(peer.tail_dst[d] + 4ull * wi) = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (peer.multimem) {
+      st_multimem_release_u32(peer.flag[0], uint32_t(peer.flag_value));
+    } else {
+      for (int d = 0; d < peer.n_dst; ++d) st_release_sys_u32(peer.flag[d], uint32_t(peer.flag_value));
+    }
+    *peer.ticket = 0u;                 // self-reset for the next call
+  }
+}
+
 template <typename T, int BN, bool GELU, bool PEER>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -332,34 +361,223 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  if (PEER) {
-    // The CTA that finishes last forwards the tail (reserved rows + token counts) and then raises this
-    // rank's arrival flag in every destination: flag == flag_value  =>  every byte of the call landed.
-    __shared__ int s_is_last;
-    if (threadIdx.x == 0) s_is_last = (atomicAdd(peer.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_is_last) {
-      __threadfence();
-      for (int wi = threadIdx.x; wi < peer.tail_words; wi += kGemmThreads) {
-        const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(peer.tail_src) + wi);
-        if (peer.multimem) {
-          st_multimem_u32(peer.tail_dst[0] + 4ull * wi, v);
-        } else {
-          for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint32_t*>(peer.tail_dst[d] + 4ull * wi) = v;
-        }
+  if (PEER) peer_finish(peer, gridDim.x);
+}
+
+// ================================ split-K variant (few tokens) =====================================
+// With M <= 256 tokens a Linear is a stream over its weights, and what bounds the persistent kernel
+// above is not HBM but the 64 B/clk each SM can pull from L2: a full-K CTA of a 128 x BN tile ingests
+// (128 + BN) x K x 2 bytes, of which the 128 token rows are the same bytes every other n-tile CTA pulls
+// (M = 256, K = 3584, BN = 64: 1.38 MB per SM, 154 MB through the crossbar for 26 MB of weights).  Wide
+// tiles cut the re-reads but leave too few CTAs -- so K is split over a thread-block CLUSTER of S CTAs:
+// each computes the 128 x BN partial of its k-range in TMEM (BN = 256, S = 4: 0.67 MB per SM), then the
+// cluster reduce-scatters the partials through L2: the tile is cut into 32 x 32 units (one tcgen05.ld of a
+// warp), unit u belongs to CTA u mod S; every CTA stores the units it does not own into its fp32 slab
+// (laid out so that a warp's store is one contiguous 512 B), one barrier.cluster (release / acquire,
+// hardware co-scheduling: no flags, no spinning), then each owner adds the S partials of its units in the
+// fixed order s = 0 .. S-1 -- its own straight from TMEM -- and runs the usual epilogue.  The result
+// does not depend on timing, and not on M either (S is chosen from n and k alone inside this regime).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int BN> struct SplitCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBudget = kTileBudget - kPeerStageBytes;
+  static constexpr int kStages = kBudget / kStageBytes < 8 ? kBudget / kStageBytes : 8;
+  static constexpr int kSmem = kStages * kStageBytes + 1024;
+  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kChunks = BN / 32;              // 32-column chunks of the tile
+  static constexpr int kUnitFloats = 32 * 32;          // one unit: 32 rows x 32 columns
+  static constexpr int kTileFloats = kBM * BN;
+};
+
+template <typename T, int BN, bool GELU, bool PEER>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                     const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k,
+                     float* __restrict__ slab, const __grid_constant__ ufv_peer_args peer_param,
+                     const ufv_dyn_args* __restrict__ dyn) {
+  using Cfg = SplitCfg<BN>;
+  __shared__ uint4 s_stage[PEER ? kEpiWarps : 1][PEER ? 32 : 1][5];
+  extern __shared__ uint8_t dyn_smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_split = int(gridDim.x);                  // == cluster size: the cluster spans grid dimension x
+  const int split = int(cluster_ctarank());
+  const int n0 = int(blockIdx.y) * BN, m0 = int(blockIdx.z) * kBM;
+  const int tile_id = int(blockIdx.z) * int(gridDim.y) + int(blockIdx.y);
+  const int num_kb = (k + kBK - 1) / kBK;
+  const int kb_begin = int((long long)split * num_kb / n_split);
+  const int kb_end = int((long long)(split + 1) * num_kb / n_split);    // host guarantees n_split <= num_kb
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(&s_tmem_base, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (dyn != nullptr) y = reinterpret_cast<T*>(dyn->tokens_out);
+  const ufv_peer_args& peer = (PEER && dyn != nullptr) ? dyn->peer : peer_param;
+  const bool peer_mm = PEER && peer.multimem != 0;
+  const uint64_t peer_dst0 = PEER ? peer.dst[0] : 0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* a_dst = tiles + size_t(s) * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        tma_load_2d(a_dst, &tmap_x, kb * kBK, m0, &full_bar[s]);
+        tma_load_2d(a_dst + Cfg::kABytes, &tmap_w, kb * kBK, n0, &full_bar[s]);
       }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        if (peer.multimem) {
-          st_multimem_release_u32(peer.flag[0], uint32_t(peer.flag_value));
-        } else {
-          for (int d = 0; d < peer.n_dst; ++d) st_release_sys_u32(peer.flag[d], uint32_t(peer.flag_value));
-        }
-        *peer.ticket = 0u;                 // self-reset for the next call
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(Elem<T>::kDtype == UFV_BF16 ? 1 : 0, BN);
+      for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(tiles + size_t(s) * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk)
+          umma_f16(tmem_base, smem_desc_sw128(a_addr + kk * kUmmaK * 2), smem_desc_sw128(b_addr + kk * kUmmaK * 2),
+                   idesc, (it | kk) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_full);
+    }
+  }
+
+  // ---- reduce-scatter of the partial tiles through L2 ------------------------------------------------------
+  const int quarter = warp & 3;             // TMEM lanes this warp may read (warps 2 .. 9 only)
+  const int half = (warp - 2) >> 2;
+  const uint32_t tmem_lane = tmem_base + (uint32_t(quarter * 32) << 16);
+  float* my_slab = slab + (size_t(tile_id) * n_split + split) * Cfg::kTileFloats;
+  if (warp >= 2) {
+    mbar_wait(&acc_full, 0);
+    tc_fence_after_sync();
+    if (n_split > 1) {
+#pragma unroll 1
+      for (int c = half; c < Cfg::kChunks; c += 2) {
+        if (n0 + c * 32 >= n || (quarter + c) % n_split == split) continue;      // outside the matrix / owned here
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_lane + uint32_t(c * 32), v);
+        tmem_ld_wait();
+        uint4* dst = reinterpret_cast<uint4*>(my_slab + size_t(quarter * Cfg::kChunks + c) * Cfg::kUnitFloats) + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j * 32] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
   }
+  if (n_split > 1) cluster_sync_all();      // every thread of every CTA: partial stores released, then acquired
+  if (warp >= 2) {
+    const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c = half; c < Cfg::kChunks; c += 2) {
+      const int gcol = n0 + c * 32;
+      if (gcol >= n || (n_split > 1 && (quarter + c) % n_split != split)) continue;
+      float acc[32];
+#pragma unroll 1
+      for (int s = 0; s < n_split; ++s) {
+        uint32_t v[32];
+        if (s == split) {
+          tmem_ld_32x32(tmem_lane + uint32_t(c * 32), v);
+          tmem_ld_wait();
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(
+                                 slab + (size_t(tile_id) * n_split + s) * Cfg::kTileFloats +
+                                 size_t(quarter * Cfg::kChunks + c) * Cfg::kUnitFloats) + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 q4 = __ldcg(src + j * 32);
+            v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = s == 0 ? __uint_as_float(v[i]) : __fadd_rn(acc[i], __uint_as_float(v[i]));
+      }
+      const bool live_row = PEER || row < m;   // rows past m: nothing to store, but the lane stays in the loop
+      uint32_t packed[16];
+      const uint4* bsrc = reinterpret_cast<const uint4*>(bias + gcol);          // n % 32 == 0 on this path
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint4 bq = __ldg(bsrc + q4);
+        const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 bf = Pack8<T>::unpack(bw[j]);
+          const int i = q4 * 8 + j * 2;
+          float a = acc[i] + bf.x;
+          float b = acc[i + 1] + bf.y;
+          if (GELU) {
+            a = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(a)));
+            b = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(b)));
+          }
+          packed[i >> 1] = Pack8<T>::two(a, b);
+        }
+      }
+      if (PEER) {
+        uint4(*stage)[5] = s_stage[warp - 2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          stage[lane][i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        __syncwarp();
+        const int row_base = m0 + quarter * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2), cc = lane & 3;
+          if (row_base + r < m)
+            peer_store16(peer, peer_mm, peer_dst0, (size_t(row_base + r) * n + gcol) * sizeof(T) + 16 * cc, stage[r][cc]);
+        }
+        __syncwarp();
+      } else if (live_row) {
+        T* dst = y + size_t(row) * n + gcol;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<uint4*>(dst)[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+      }
+      __syncwarp();                            // the loop top holds warp-collective tcgen05.ld
+    }
+  }
+  if (PEER) __threadfence_system();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (PEER) peer_finish(peer, gridDim.x * gridDim.y * gridDim.z);
 }
 
 // an empty shard (no token rows) still has to forward its tail and raise its flag
@@ -475,9 +693,80 @@ static int choose_bn(int m, int n) {
   return best_bn;
 }
 
+// ---- split-K configuration ------------------------------------------------------------------------------
+// Chosen from (n, k) and the number of 128-token tiles only, so that inside one regime the summation
+// order -- and with it every output bit -- is independent of how many tokens a call carries:
+//   k >= 2048 (the 3584 -> 3584 Linear):   1-2 token tiles (M <= 256): BN = 256, S = 4  (<= 112 CTAs, 14 k-blocks each)
+//                                          3-4 token tiles (M <= 512): BN = 256, S = 2
+//   otherwise, or when the clusters would not fit one wave: full-K persistent kernel (S = 1).
+// UFV_GEMM_SPLIT = 0 disables, = S forces S (with UFV_GEMM_SPLIT_BN = 64 | 128 | 256): developer sweeps.
+struct SplitChoice { int s; int bn; };
+
+static SplitChoice choose_split(int m, int n, int k) {
+  const char* env_s = getenv("UFV_GEMM_SPLIT");          // read per call: tests and sweeps toggle it
+  const char* env_bn = getenv("UFV_GEMM_SPLIT_BN");
+  const int tiles_m = (m + kBM - 1) / kBM;
+  const int num_kb = (k + kBK - 1) / kBK;
+  SplitChoice c{1, 256};
+  if (n % 32 != 0) return c;
+  if (env_s != nullptr) {
+    c.s = atoi(env_s);
+    if (env_bn != nullptr) c.bn = atoi(env_bn);
+    if (c.bn != 64 && c.bn != 128 && c.bn != 256) c.bn = 256;
+  } else if (num_kb >= 32) {
+    c.s = tiles_m <= 2 ? 4 : tiles_m <= 4 ? 2 : 1;
+  }
+  if (c.s < 2 || c.s > 8 || c.s > num_kb) return SplitChoice{1, c.bn};
+  const long ctas = long(tiles_m) * ((n + c.bn - 1) / c.bn) * c.s;
+  if (ctas > sm_count()) return SplitChoice{1, c.bn};     // the clusters must be co-resident in one wave
+  return c;
+}
+
+static size_t split_ws_bytes(int m, int n, int k) {
+  const SplitChoice c = choose_split(m, n, k);
+  if (c.s <= 1) return 0;
+  return size_t((m + kBM - 1) / kBM) * ((n + c.bn - 1) / c.bn) * c.s * kBM * c.bn * sizeof(float);
+}
+
+template <typename T, int BN>
+static int launch_splitk(const void* x, const void* w, const void* bias, void* y, int m, int n, int k, int gelu,
+                         int n_split, float* slab, const ufv_peer_args* peer, const ufv_dyn_args* dyn,
+                         cudaStream_t stream) {
+  CUtensorMap tx, tw;
+  int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
+  if (rc != 0) return rc;
+  rc = make_tensor_map_2d(&tw, w, Elem<T>::kDtype, uint64_t(n), uint64_t(k), BN, kBK, 1);
+  if (rc != 0) return rc;
+  const dim3 grid(n_split, (n + BN - 1) / BN, (m + kBM - 1) / kBM);
+  const int variant = peer != nullptr ? 2 : gelu ? 1 : 0;
+  auto kernel = variant == 2   ? linear_splitk_kernel<T, BN, false, true>
+                : variant == 1 ? linear_splitk_kernel<T, BN, true, false>
+                               : linear_splitk_kernel<T, BN, false, false>;
+  static bool configured[3] = {false, false, false};
+  if (!configured[variant]) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<BN>::kSmem);
+    configured[variant] = true;
+  }
+  static const ufv_peer_args no_peer = {};
+  return check_launch("ufv_linear (tcgen05, split-K cluster)",
+                      launch_kernel_cluster(kernel, grid, dim3(kGemmThreads), SplitCfg<BN>::kSmem, stream,
+                                            unsigned(n_split), tx, tw, static_cast<const T*>(bias),
+                                            static_cast<T*>(y), m, n, k, slab, peer != nullptr ? *peer : no_peer, dyn));
+}
+
 template <typename T>
 static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                       int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, cudaStream_t stream) {
+                       int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes,
+                       cudaStream_t stream) {
+  const SplitChoice sc = choose_split(m, n, k);
+  if (sc.s > 1 && ws != nullptr && size_t(ws_bytes) >= split_ws_bytes(m, n, k)) {
+    float* slab = static_cast<float*>(ws);
+    switch (sc.bn) {
+      case 256: return launch_splitk<T, 256>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, stream);
+      case 128: return launch_splitk<T, 128>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, stream);
+      default: return launch_splitk<T, 64>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, stream);
+    }
+  }
   switch (choose_bn(m, n)) {
     case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
     case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
@@ -594,9 +883,15 @@ linear_f32_skinny_kernel(const float* __restrict__ x, const float* __restrict__ 
 
 }  // namespace ufv
 
+extern "C" int64_t ufv_linear_ws_bytes(int m, int n, int k, int dtype) {
+  if (m <= 0 || n <= 0 || k <= 0 || (dtype != UFV_BF16 && dtype != UFV_F16)) return 0;
+  return int64_t(ufv::split_ws_bytes(m, n, k));
+}
+
 extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                          int dtype, int gelu, void* stream) {
+                          int dtype, int gelu, void* ws, int64_t ws_bytes, void* stream) {
   using namespace ufv;
+  UFV_REQUIRE(ws == nullptr || aligned16(ws), UFV_E_ALIGN, "ufv_linear: ws must be 16-byte aligned");
   UFV_REQUIRE(m >= 0 && n >= 1 && k >= 1, UFV_E_SHAPE, "ufv_linear: m=%d n=%d k=%d", m, n, k);
   if (m == 0) return 0;
   UFV_REQUIRE(x && w && bias && y, UFV_E_NULL, "ufv_linear: null pointer");
@@ -621,27 +916,28 @@ extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* 
   }
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "ufv_linear: unsupported dtype %d", dtype);
   UFV_REQUIRE(k % 8 == 0 && n % 8 == 0, UFV_E_SHAPE, "ufv_linear: k=%d and n=%d must be multiples of 8", k, n);
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, st);
-  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, st);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, ws, ws_bytes, st);
+  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, ws, ws_bytes, st);
 }
 
 namespace ufv {
 // last Linear of the chained path in graph-replay mode (tensor-core dtypes only): the output pointer and,
 // with `peer`, the all-gather destinations are read from the device block `dyn` at run time
 int last_linear_dyn(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
-                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* stream) {
+                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes, void* stream) {
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "graph replay: bf16 / fp16 only (dtype %d)", dtype);
   UFV_REQUIRE(m >= 1 && k % 8 == 0 && n % 32 == 0, UFV_E_SHAPE, "graph replay: m=%d n=%d k=%d", m, n, k);
   UFV_REQUIRE(x && w && bias && dyn && aligned16(x) && aligned16(w), UFV_E_NULL, "graph replay: bad pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, st);
-  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, st);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, ws, ws_bytes, st);
+  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, ws, ws_bytes, st);
 }
 }  // namespace ufv
 
 extern "C" int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int n, int k,
-                                 int dtype, const ufv_peer_args* peer, void* stream) {
+                                 int dtype, const ufv_peer_args* peer, void* ws, int64_t ws_bytes, void* stream) {
   using namespace ufv;
+  UFV_REQUIRE(ws == nullptr || aligned16(ws), UFV_E_ALIGN, "ufv_linear_gather: ws must be 16-byte aligned");
   UFV_REQUIRE(m >= 0 && n >= 1 && k >= 1, UFV_E_SHAPE, "ufv_linear_gather: m=%d n=%d k=%d", m, n, k);
   UFV_REQUIRE(peer && (m == 0 || (x && w && bias)), UFV_E_NULL, "ufv_linear_gather: null pointer");
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE,
@@ -660,8 +956,8 @@ extern "C" int ufv_linear_gather(const void* x, const void* w, const void* bias,
     return check_launch("ufv_linear_gather (empty shard)",
                         launch_kernel(peer_tail_only_kernel, dim3(1), dim3(256), 0, st, *peer));
   UFV_REQUIRE(aligned16(x) && aligned16(w), UFV_E_ALIGN, "ufv_linear_gather: x / w must be 16-byte aligned");
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, st);
-  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, st);
+  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, st);
+  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, st);
 }
 
 extern "C" int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,

@@ -19,6 +19,8 @@
 // Roofline: L2 (pooled rows were just written by kernel 2); reads ~3 T C 4 bytes per object.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace ufv {
 
 constexpr int kSimWarps = 4;                 // adjacent pairs per CTA of the similarity kernel
@@ -152,7 +154,7 @@ ttm_merge_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
                  float* __restrict__ tokens_f32_out, int32_t* __restrict__ counts_out,
                  uint32_t* __restrict__ cuts_out, int cut_pitch_words, int32_t* __restrict__ counts_host,
                  int32_t epoch, const ufv_dyn_args* __restrict__ dyn) {
-  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
   const int len_words = (max_len + 31) / 32;
   float* s_sim = reinterpret_cast<float*>(dyn_smem);                 // [max_len]
   uint32_t* s_cutw = reinterpret_cast<uint32_t*>(s_sim + max_len);   // [len_words]
@@ -285,7 +287,15 @@ ttm_merge_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
 constexpr int kTtmThreads = 512;
 constexpr int kTtmWarps = kTtmThreads / 32;
 constexpr int kFusedMaxLen = 64;
+constexpr size_t kTtmMaxSmem = 220 * 1024;   // staged rows + small arrays (227 KB per CTA on sm_100, minus static)
 
+// The object's T pooled rows (T * C * 4 bytes, contiguous) are first pulled into shared memory with the TMA
+// engine -- one bulk copy per row, all in flight at once, ONE L2 round trip -- and every later phase
+// (norms, adjacent dots, run means: three dependent passes over the rows) reads them from there.  Reading
+// them from L2 in every phase made this kernel a chain of ~600-cycle round trips on 32 of 148 SMs: 17 us
+// inside the pipeline for a few microseconds of work (profiles/r02a_timeline_n1.txt).  `stage_rows` = 0
+// keeps the global reads (objects too long for shared memory).  The arithmetic and its order are the same
+// either way.
 template <typename T>
 __global__ void __launch_bounds__(kTtmThreads)
 ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restrict__ obj_start,
@@ -293,29 +303,46 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
            int max_len, T* __restrict__ tokens_out, float* __restrict__ tokens_f32_out,
            int32_t* __restrict__ counts_out, uint32_t* __restrict__ cuts_out, int cut_pitch_words,
            float* __restrict__ sims_out, int sims_pitch, int32_t* __restrict__ counts_host, int32_t epoch,
-           const ufv_dyn_args* __restrict__ dyn) {
-  extern __shared__ __align__(16) uint8_t dyn_smem[];
+           const ufv_dyn_args* __restrict__ dyn, int stage_rows) {
+  extern __shared__ __align__(128) uint8_t dyn_smem[];
   const int len_words = (max_len + 31) / 32;
   float* s_norm = reinterpret_cast<float*>(dyn_smem);          // [max_len]
   float* s_sim = s_norm + max_len;                             // [max_len]
   uint32_t* s_cutw = reinterpret_cast<uint32_t*>(s_sim + max_len);   // [len_words]
   int32_t* s_wpre = reinterpret_cast<int32_t*>(s_cutw + len_words);  // [len_words + 1]
   int32_t* s_gend = s_wpre + len_words + 1;                    // [k_keep + 1]
+  // staged rows start at the next 128-byte boundary after the small arrays (same formula on the host)
+  float* s_rows = reinterpret_cast<float*>(dyn_smem + ((size_t(max_len) * 8 + size_t(len_words) * 8 + 4 +
+                                                        size_t(k_keep + 1) * 4 + 127) & ~size_t(127)));
   __shared__ float s_kth;
+  __shared__ __align__(8) uint64_t s_rows_bar;
 
   const int o = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the object's extent is plan data (uploaded before kernel 1 ran): fetched while the pool kernel drains
+  const int t_len = obj_len[o];
+  const int slot = slot_off[o];
+  const int start = obj_start[o];
+  if (stage_rows && tid == 0) {
+    mbar_init(&s_rows_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
   pdl_wait();                  // pooled rows come from kernel 2
   pdl_launch_dependents();
   if (dyn != nullptr) {        // graph replay: per-call values come through the device block
     epoch = dyn->epoch;
     if (dyn->counts_out != 0) counts_out = reinterpret_cast<int32_t*>(dyn->counts_out);
   }
-  const int t_len = obj_len[o];
-  const int slot = slot_off[o];
-  const float* x = pooled + size_t(obj_start[o]) * c;
+  const float* x = pooled + size_t(start) * c;
   const int c4 = c >> 2;
   const int n_slots = min(t_len, k_keep);
+  const bool staged = stage_rows && t_len > k_keep;
+  if (staged && warp == 0) {
+    if (lane == 0) mbar_arrive_expect_tx(&s_rows_bar, uint32_t(t_len) * uint32_t(c) * 4u);
+    __syncwarp();
+    for (int t = lane; t < t_len; t += 32) bulk_g2s(s_rows + size_t(t) * c, x + size_t(t) * c, uint32_t(c) * 4u, &s_rows_bar);
+  }
 
   if (cuts_out != nullptr)
     for (int w = tid; w < cut_pitch_words; w += kTtmThreads) cuts_out[size_t(o) * cut_pitch_words + w] = 0u;
@@ -324,15 +351,14 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
     for (int u = tid; u < t_len * c4; u += kTtmThreads) {
       const int t = u / c4, q = u - t * c4;
       const float4 v = *reinterpret_cast<const float4*>(x + size_t(t) * c + q * 4);
-      const size_t dst = size_t(slot + t) * c + q * 4;
-      if (tokens_f32_out != nullptr) *reinterpret_cast<float4*>(tokens_f32_out + dst) = v;
-      tokens_out[dst + 0] = Elem<T>::from_f32(v.x);
-      tokens_out[dst + 1] = Elem<T>::from_f32(v.y);
-      tokens_out[dst + 2] = Elem<T>::from_f32(v.z);
-      tokens_out[dst + 3] = Elem<T>::from_f32(v.w);
+      store_token<T>(tokens_out, tokens_f32_out, size_t(slot + t) * c + q * 4, v);
     }
     if (tid == 0) publish_count(counts_out, counts_host, epoch, o, t_len);
     return;
+  }
+  if (staged) {                 // from here on the rows are read from shared memory
+    mbar_wait(&s_rows_bar, 0);
+    x = s_rows;
   }
 
   // ---- 1. norms: one warp per token (kTtmBatch float4 loads in flight per lane) -----------------
@@ -471,12 +497,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
       acc.z = __fdiv_rn(acc.z, n);
       acc.w = __fdiv_rn(acc.w, n);
     }
-    const size_t dst = size_t(slot + g) * c + q * 4;
-    if (tokens_f32_out != nullptr) *reinterpret_cast<float4*>(tokens_f32_out + dst) = acc;
-    tokens_out[dst + 0] = Elem<T>::from_f32(acc.x);
-    tokens_out[dst + 1] = Elem<T>::from_f32(acc.y);
-    tokens_out[dst + 2] = Elem<T>::from_f32(acc.z);
-    tokens_out[dst + 3] = Elem<T>::from_f32(acc.w);
+    store_token<T>(tokens_out, tokens_f32_out, size_t(slot + g) * c + q * 4, acc);
   }
 }
 
@@ -489,15 +510,22 @@ static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, cons
                       const ufv_dyn_args* dyn, cudaStream_t stream) {
   const int len_words = (max_len + 31) / 32;
   if (max_len <= kFusedMaxLen) {
-    const size_t smem = size_t(max_len) * 8 + size_t(len_words) * 4 + size_t(len_words + 1) * 4 +
-                        size_t(k_keep + 1) * 4;
+    const size_t small = (size_t(max_len) * 8 + size_t(len_words) * 8 + 4 + size_t(k_keep + 1) * 4 + 127) & ~size_t(127);
+    const size_t rows = size_t(max_len) * c * sizeof(float);
+    static const bool no_stage = getenv("UFV_TTM_NO_STAGE") != nullptr;      // developer A/B knob
+    const int stage_rows = !no_stage && c % 4 == 0 && small + rows <= kTtmMaxSmem ? 1 : 0;
+    const size_t smem = small + (stage_rows ? rows : 0);
     auto kernel = ttm_fused_kernel<T>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    static size_t configured = 48 * 1024;     // the attribute only ever grows; a benign race sets it twice
+    if (smem > configured) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTtmMaxSmem));
+      configured = kTtmMaxSmem;
+    }
     return check_launch("ufv_ttm (fused)",
                         launch_kernel(kernel, dim3(n_obj), dim3(kTtmThreads), smem, stream, pooled, c, obj_start,
                                       obj_len, slot_off, k_keep, max_len, static_cast<T*>(tokens_out),
                                       tokens_f32_out, counts_out, cuts_out, cut_pitch_words, sims, sims_pitch,
-                                      counts_host, epoch, dyn));
+                                      counts_host, epoch, dyn, stage_rows));
   }
   if (max_len > k_keep) {
     const dim3 grid((max_len - 1 + kSimWarps - 1) / kSimWarps, n_obj);

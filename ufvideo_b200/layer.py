@@ -125,8 +125,12 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, gelu: bool
     m, k = x.shape
     n = weight.shape[0]
     y = torch.empty((m, n), dtype=x.dtype, device=x.device)
-    _cabi.check(_cabi.lib().ufv_linear(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
-                                       m, n, k, _feat_dtype(x), int(gelu), _stream_ptr(x.device)))
+    lib = _cabi.lib()
+    ws_bytes = int(lib.ufv_linear_ws_bytes(m, n, k, _feat_dtype(x)))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device) if ws_bytes else None   # split-K scratch
+    _cabi.check(lib.ufv_linear(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), m, n, k,
+                               _feat_dtype(x), int(gelu), ws.data_ptr() if ws_bytes else None, ws_bytes,
+                               _stream_ptr(x.device)))
     return y
 
 
@@ -432,7 +436,10 @@ class MaskExtractor(nn.Module):
         q, m_pad, g = plan.n_masks, plan.m_pad, max(plan.n_groups, 1)
         es = feats.element_size()
         # one workspace allocation, carved into 256-byte aligned pieces
-        sizes = (("bits", q * _cabi.BITS_WORDS * 4), ("cnt", q * 4), ("pooled", q * c * 4),
+        lib = _cabi.lib()
+        gemm_ws = max(int(lib.ufv_linear_ws_bytes(m_pad, hid, c, dt)), int(lib.ufv_linear_ws_bytes(m_pad, hid, hid, dt))) \
+            if two and m_pad else 0
+        sizes = (("bits", q * _cabi.BITS_WORDS * 4), ("cnt", q * 4), ("pooled", q * c * 4), ("gemm_ws", gemm_ws),
                  ("merged", m_pad * c * es), ("hidden", m_pad * hid * es), ("counts", plan.n_obj * 4),
                  ("sims", plan.n_obj * max(plan.max_len, 1) * 4), ("dyn", 256),
                  ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.PLAN_PITCH))
@@ -471,7 +478,8 @@ class MaskExtractor(nn.Module):
                 counts_host=counts_dev_addr, epoch=0,
                 w1=linears[0].weight.data_ptr(), b1=linears[0].bias.data_ptr(),
                 w2=linears[1].weight.data_ptr(), b2=linears[1].bias.data_ptr(),
-                hidden=ptr["hidden"], tokens_out=None)
+                hidden=ptr["hidden"], tokens_out=None,
+                gemm_ws=ptr["gemm_ws"] if gemm_ws else None, gemm_ws_bytes=gemm_ws)
             run["args"] = a
             run["args_ref"] = ctypes.byref(a)
             # per-call block of the graph-replay mode: pinned, written by the host, forwarded by kernel 1
