@@ -555,8 +555,9 @@ def test_ties_in_the_middle_keep_object_order(dev):
     assert np.abs(tokens.cpu().numpy() - o["tokens"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("m", [0, 40, 256, 700])
-def test_linear_gather_stores_tiles_tail_and_flags_to_every_destination(dev, m):
+def test_linear_gather_stores_tiles_tail_and_flags_to_every_destination(dev, m, split):
     """ufv_linear_gather on one GPU with two local "ranks" as destinations (one st per peer): both
     copies equal ufv_linear's output, the tail is forwarded, flags carry the step value, the ticket
     resets.  (The multimem.st path needs NVSwitch multicast: covered by bench.py's self-check at N > 1.)"""
@@ -579,8 +580,9 @@ def test_linear_gather_stores_tiles_tail_and_flags_to_every_destination(dev, m):
         tail_src.data_ptr(), ticket.data_ptr(), tail_words, 2, 0, 7)
     stream = torch.cuda.current_stream(dev).cuda_stream
     lib = _cabi.lib()
-    ws_bytes = int(lib.ufv_linear_ws_bytes(m, n, k, _cabi.UFV_BF16))      # > 0 for the few-token cases: cluster split-K
-    assert (ws_bytes > 0) == (0 < m <= 512)
+    os.environ["UFV_GEMM_SPLIT_DEFAULT"] = "1" if split else "0"         # with and without the cluster split-K kernel
+    ws_bytes = int(lib.ufv_linear_ws_bytes(m, n, k, _cabi.UFV_BF16))
+    assert (ws_bytes > 0) == (split and 0 < m <= 512)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     for rep in range(2):                                     # twice: the ticket must have reset itself
         a.flag_value = 7 + rep
@@ -593,6 +595,7 @@ def test_linear_gather_stores_tiles_tail_and_flags_to_every_destination(dev, m):
         for c, tl in zip(copies, tails):
             assert torch.equal(c[:m], want) and not c[m:].any()
             assert torch.equal(tl, tail_src)
+    os.environ.pop("UFV_GEMM_SPLIT_DEFAULT", None)
     _cabi.check(lib.ufv_wait_flags(flags.data_ptr(), 2, 99, 50, timed_out.data_ptr(), stream))   # never arrives
     torch.cuda.synchronize()
     assert int(timed_out.item()) == 1
@@ -731,6 +734,83 @@ def test_long_objects_spread_over_many_ctas(dev):
         assert n == want.shape[0]
         assert np.array_equal(ex["sims"][o, : b - a - 1].cpu().numpy(), sims)
         assert np.array_equal(ex["tokens_f32"][8 * o: 8 * o + n].cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json shapes through forward(), against the oracle (clips are independent, so the oracle runs on
+# selected clips / objects only and still pins every quantity of those rows)
+# ---------------------------------------------------------------------------------------------
+def _forward_vs_oracle(dev, feats, masks, ann, k, clips, mask_dtype=torch.uint8, dtype="bf16"):
+    """Run forward() on the whole batch; for every clip index in ``clips`` run the oracle on that clip alone and
+    require: region_token_nums equal, pooled rows bit-identical, merged tokens bit-identical, projected tokens
+    within the 16-bit tolerance."""
+    enc = make_encoder(dev, dtype, k)
+    ft = torch.from_numpy(feats).to(dev).to(TORCH_DT[dtype])
+    md = [torch.from_numpy(m).to(dev).to(mask_dtype) for m in masks]
+    tokens, counts = enc(ft, md, None, ann, None)
+    pooled = enc._debug["pooled"].cpu().numpy()
+    merged = enc._debug["merged"].float().cpu().numpy()
+    plan = enc.last_plan
+    slot_off = plan.host["slot_off"]
+    tok = tokens.float().cpu().numpy()
+    w = tuple(R.round_to(a, dtype) for a in synth.make_weights(0))
+    q_off = np.concatenate([[0], np.cumsum([m.shape[0] for m in masks])])
+    o_off = np.concatenate([[0], np.cumsum([len(a) for a in ann])])
+    t_off = np.concatenate([[0], np.cumsum(counts)])
+    assert tok.shape[0] == t_off[-1]
+    for i in clips:
+        rows = sorted({r for obj in ann[i] for r in obj})
+        remap = {r: j for j, r in enumerate(rows)}
+        ann_i = [[[remap[r] for r in obj] for obj in ann[i]]]
+        o = R.encode(R.round_to(feats[rows], dtype), [masks[i]], ann_i, k, dtype, w)
+        a, b = int(o_off[i]), int(o_off[i + 1])
+        assert counts[a:b] == o["counts"], i
+        assert np.array_equal(pooled[q_off[i]:q_off[i + 1]], o["pooled"]), i
+        want_rows = np.concatenate([np.arange(slot_off[j], slot_off[j] + counts[j]) for j in range(a, b)])
+        assert np.array_equal(merged[want_rows], o["merged"]), i
+        assert np.abs(tok[t_off[a]:t_off[b]] - o["tokens"]).max() <= TOL[dtype], i
+    return enc, tokens, counts
+
+
+@pytest.mark.parametrize("mask_dtype", [torch.uint8, torch.float32])
+def test_c3_share_sparse_masks_vs_oracle(dev, mask_dtype):
+    """BASELINE configs[2], one GPU's share: 8 of 64 clips x 32 frames x 8 objects, sparse / irregular masks
+    (every 7th mask all-zero), K = 8: 2048 object-frames, 512 tokens."""
+    feats, masks, ann = synth.make_batch(8, 32, 8, "sparse")
+    _, tokens, counts = _forward_vs_oracle(dev, feats, masks, ann, 8, clips=(0, 5, 7), mask_dtype=mask_dtype)
+    assert len(counts) == 64 and tokens.shape[1] == 3584
+
+
+def test_c4_long_clip_16_objects_vs_oracle(dev):
+    """BASELINE configs[3], one clip: 256 frames x 16 objects (two or more pool passes per frame, the split
+    similarity / merge kernels, r = 248 merges per object)."""
+    feats, masks, ann = synth.make_batch(1, 256, 16, "blob")
+    enc, tokens, counts = _forward_vs_oracle(dev, feats, masks, ann, 8, clips=(0,))
+    assert counts == [8] * 16 and tuple(tokens.shape) == (128, 3584)
+    assert enc.last_plan.max_len == 256
+
+
+def test_c5_wide_ragged_64_objects_vs_oracle(dev):
+    """BASELINE configs[4] corner: 1 clip x 64 frames x 64 objects, ragged T_o in [1, 64] (objects shorter
+    than K pass through, many objects per frame)."""
+    feats, masks, ann = synth.make_batch(1, 64, 64, "blob", ragged=True)
+    enc, tokens, counts = _forward_vs_oracle(dev, feats, masks, ann, 8, clips=(0,))
+    assert counts == [min(len(o), 8) for o in ann[0]]
+
+
+def test_c5_long_512_frames_vs_oracle(dev):
+    """BASELINE configs[4] corner: 1 clip x 512 frames x 4 objects, dense masks, T = 512 per object."""
+    feats, masks, ann = synth.make_batch(1, 512, 4, "dense")
+    enc, tokens, counts = _forward_vs_oracle(dev, feats, masks, ann, 8, clips=(0,))
+    assert counts == [8] * 4 and enc.last_plan.max_len == 512
+
+
+def test_c2_full_shape_vs_oracle_every_clip(dev):
+    """BASELINE configs[1] at full size, fp32 masks as the reference contract has them: every clip against the
+    oracle (counts, pooled, merged bit-exact; projected tokens within 1e-2)."""
+    feats, masks, ann = synth.make_batch(8, 16, 4, "dense")
+    _, tokens, counts = _forward_vs_oracle(dev, feats, masks, ann, 8, clips=range(8), mask_dtype=torch.float32)
+    assert counts == [8] * 32 and tuple(tokens.shape) == (256, 3584)
 
 
 def test_c2_shape_properties_bf16(dev):

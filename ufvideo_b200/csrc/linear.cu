@@ -148,33 +148,37 @@ __device__ __forceinline__ void peer_store16(const ufv_peer_args& peer, bool mul
   }
 }
 
-// Closing protocol of the fused all-gather, called by every thread of every CTA after its remote stores are
-// fenced: the CTA that finishes last forwards the tail (reserved rows + token counts) and then raises this
-// rank's arrival flag in every destination: flag >= flag_value  =>  every byte of the call landed.
+// Closing protocol of the fused all-gather.  Called by every thread of every CTA behind a __syncthreads()
+// that follows the CTA's last remote store.  What sits between the last tile and the arrival flag is ONE
+// NVLink round trip: thread 0 alone executes a system-scope fence -- it is cumulative over the stores of the
+// CTA's other threads, which happen-before it through the barrier -- takes a ticket (local L2 atomic), and
+// whoever takes the last ticket raises this rank's flag in every destination with a release store:
+// flag >= flag_value  =>  every byte of the call has landed.  The tail (reserved rows + token counts, written
+// by the merge kernel long before) is forwarded by CTA 0 ahead of its own fence, so nobody waits for it.
+// (Round 1 fenced in all 320 threads, then let the last CTA forward the tail and fence again: three
+// dependent round trips, 16 us at 2 GPUs -- profiles/r02c_timeline_n2.txt.)
 __device__ __forceinline__ void peer_finish(const ufv_peer_args& peer, unsigned n_ctas) {
-  __shared__ int s_is_last;
-  if (threadIdx.x == 0) s_is_last = (atomicAdd(peer.ticket, 1u) == n_ctas - 1);
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  for (int wi = threadIdx.x; wi < peer.tail_words; wi += kGemmThreads) {
-    const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(peer.tail_src) + wi);
-    if (peer.multimem) {
-      st_multimem_u32(peer.tail_dst[0] + 4ull * wi, v);
-    } else {
-      for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint32_t*>(peer.tail_dst[d] + 4ull * wi) = v;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && peer.tail_words > 0) {
+    for (int wi = threadIdx.x; wi < peer.tail_words; wi += kGemmThreads) {
+      const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(peer.tail_src) + wi);
+      if (peer.multimem) {
+        st_multimem_u32(peer.tail_dst[0] + 4ull * wi, v);
+      } else {
+        for (int d = 0; d < peer.n_dst; ++d) *reinterpret_cast<uint32_t*>(peer.tail_dst[d] + 4ull * wi) = v;
+      }
     }
+    __syncthreads();
   }
+  if (threadIdx.x != 0) return;
   __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (peer.multimem) {
-      st_multimem_release_u32(peer.flag[0], uint32_t(peer.flag_value));
-    } else {
-      for (int d = 0; d < peer.n_dst; ++d) st_release_sys_u32(peer.flag[d], uint32_t(peer.flag_value));
-    }
-    *peer.ticket = 0u;                 // self-reset for the next call
+  if (atomicAdd(peer.ticket, 1u) != n_ctas - 1) return;
+  __threadfence();                     // acquire side of the ticket: the other CTAs' fenced stores precede the flag
+  if (peer.multimem) {
+    st_multimem_release_u32(peer.flag[0], uint32_t(peer.flag_value));
+  } else {
+    for (int d = 0; d < peer.n_dst; ++d) st_release_sys_u32(peer.flag[d], uint32_t(peer.flag_value));
   }
+  *peer.ticket = 0u;                   // self-reset for the next call
 }
 
 template <typename T, int BN, bool GELU, bool PEER>
@@ -357,7 +361,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) mbar_arrive(&acc_empty[acc]);   // this warp's share of the accumulator is in registers / stored
     }
   }
-  if (PEER) __threadfence_system();        // this thread's remote stores are ordered before the ticket below
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -573,7 +576,6 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       __syncwarp();                            // the loop top holds warp-collective tcgen05.ld
     }
   }
-  if (PEER) __threadfence_system();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -702,6 +704,14 @@ static int choose_bn(int m, int n) {
 // UFV_GEMM_SPLIT = 0 disables, = S forces S (with UFV_GEMM_SPLIT_BN = 64 | 128 | 256): developer sweeps.
 struct SplitChoice { int s; int bn; };
 
+// Measured on B200 (profiles/r02b_*): at M = 256 the split kernel's shorter main loop (0.67 instead of
+// 1.38 MB per SM) is eaten by its extra phases (partial stores, cluster barrier, partial loads: ~5 us), 19.0
+// against 17.6 us inside the step -- so it is opt-in (UFV_GEMM_SPLIT_DEFAULT=1) until that is fixed.
+static bool split_by_default() {
+  const char* e = getenv("UFV_GEMM_SPLIT_DEFAULT");
+  return e != nullptr && atoi(e) != 0;
+}
+
 static SplitChoice choose_split(int m, int n, int k) {
   const char* env_s = getenv("UFV_GEMM_SPLIT");          // read per call: tests and sweeps toggle it
   const char* env_bn = getenv("UFV_GEMM_SPLIT_BN");
@@ -713,7 +723,7 @@ static SplitChoice choose_split(int m, int n, int k) {
     c.s = atoi(env_s);
     if (env_bn != nullptr) c.bn = atoi(env_bn);
     if (c.bn != 64 && c.bn != 128 && c.bn != 256) c.bn = 256;
-  } else if (num_kb >= 32) {
+  } else if (split_by_default() && num_kb >= 32) {
     c.s = tiles_m <= 2 ? 4 : tiles_m <= 4 ? 2 : 1;
   }
   if (c.s < 2 || c.s > 8 || c.s > num_kb) return SplitChoice{1, c.bn};

@@ -21,6 +21,25 @@
 
 #include <cstdlib>
 
+// Developer build (-DUFV_TTM_TRACE): CTA 0 of the fused kernel stamps %globaltimer at its phase boundaries
+// into a device array that tools/ttm_trace.py reads back.  Not compiled into the shipped library.
+#ifdef UFV_TTM_TRACE
+__device__ unsigned long long g_ttm_trace[16];
+#define UFV_TRACE(i)                                                                  \
+  do {                                                                                \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                        \
+      unsigned long long t_;                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                          \
+      g_ttm_trace[i] = t_;                                                            \
+    }                                                                                 \
+  } while (0)
+extern "C" int ufv_debug_ttm_trace(unsigned long long* out_host) {
+  return int(cudaMemcpyFromSymbol(out_host, g_ttm_trace, sizeof(g_ttm_trace)));
+}
+#else
+#define UFV_TRACE(i) do { } while (0)
+#endif
+
 namespace ufv {
 
 constexpr int kSimWarps = 4;                 // adjacent pairs per CTA of the similarity kernel
@@ -320,6 +339,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   const int o = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // the object's extent is plan data (uploaded before kernel 1 ran): fetched while the pool kernel drains
+  UFV_TRACE(0);
   const int t_len = obj_len[o];
   const int slot = slot_off[o];
   const int start = obj_start[o];
@@ -328,7 +348,9 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
     mbar_fence_init();
   }
   __syncthreads();
+  UFV_TRACE(1);
   pdl_wait();                  // pooled rows come from kernel 2
+  UFV_TRACE(2);
   pdl_launch_dependents();
   if (dyn != nullptr) {        // graph replay: per-call values come through the device block
     epoch = dyn->epoch;
@@ -360,6 +382,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
     mbar_wait(&s_rows_bar, 0);
     x = s_rows;
   }
+  UFV_TRACE(3);
 
   // ---- 1. norms: one warp per token (kTtmBatch float4 loads in flight per lane) -----------------
   for (int t = warp; t < t_len; t += kTtmWarps) {
@@ -385,6 +408,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   }
   __syncthreads();
 
+  UFV_TRACE(4);
   // ---- 2. adjacent cosine similarities: one warp per pair ----------------------------------------
   const int n_sim = t_len - 1;
   for (int i = warp; i < n_sim; i += kTtmWarps) {
@@ -419,6 +443,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   }
   __syncthreads();
 
+  UFV_TRACE(5);
   // ---- 3. r-th largest by rank counting -------------------------------------------------------------
   const int r = t_len - k_keep;
   for (int i = tid; i < n_sim; i += kTtmThreads) {
@@ -475,6 +500,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
       cuts_out[size_t(o) * cut_pitch_words + w] = s_cutw[w];
   __syncthreads();
 
+  UFV_TRACE(6);
   // ---- 5. run means, ascending token order; unused slots are zero-filled -----------------------------------
   for (int u = tid; u < n_slots * c4; u += kTtmThreads) {
     const int g = u / c4, q = u - g * c4;
@@ -499,6 +525,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
     }
     store_token<T>(tokens_out, tokens_f32_out, size_t(slot + g) * c + q * 4, acc);
   }
+  UFV_TRACE(7);
 }
 
 
