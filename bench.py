@@ -463,13 +463,8 @@ def run_ours(a):
     # ---- roofline of the dominant kernel: segmented mask pool, timed alone ------------------------
     plan = packer.build_plan(masks_dev, ann, feats_dev.shape[0], k, dev)
     patches = layer.mask_to_patches(plan, dev)
-    union = 0
-    b = patches["bits"].cpu().numpy().view(np.uint32)
-    go, gm = plan.host["grp_off"], plan.host["grp_member"]
-    for g in range(plan.n_groups):
-        u = np.bitwise_or.reduce(b[gm[go[g]:go[g + 1]]], axis=0)
-        union += int(np.unpackbits(u.view(np.uint8)).sum())
-    pool_bytes = union * 1152 * 2 + q * 1152 * 4 + q * 96        # feature rows + pooled write + bitmasks
+    # each needed feature row once per FRAME (union over all its objects) + pooled write + bitmasks
+    pool_bytes = packer.algorithmic_pool_bytes(plan, patches["bits"].cpu().numpy(), 1152, 2)
     ms_pool = timed(lambda: layer.mask_pool(feats_dev, plan, patches), max(a.steps, 20), 3)
     peak, peak_src = peaks()
     achieved = pool_bytes / (ms_pool * 1e-3) / 1e9

@@ -45,8 +45,11 @@ enum {
 
 #define UFV_BITS_WORDS 24        /* uint32 words per patch bitmask row (729 bits -> 23, padded) */
 #define UFV_MAX_PATCH_SIDE 27    /* kernels are sized for up to 27 x 27 patches              */
-#define UFV_MAX_GROUP 8          /* object-frames pooled together from one staged frame tile */
+#define UFV_MAX_GROUP 64         /* object-frames pooled together from one staged frame tile */
 #define UFV_PLAN_PITCH 736       /* entries per group in the union-plan arrays (>= 729, % 16 == 0) */
+/* Members of a group are handled in sets of 8 (one pair of consumer warps of the pool kernel per set); a call
+ * whose largest group has `g` members carries this many member-mask planes per group (1, 2, 4 or 8): */
+#define UFV_OMASK_SETS(g) ((g) <= 8 ? 1 : (g) <= 16 ? 2 : (g) <= 32 ? 4 : 8)
 
 /* One object-frame's mask plane (32 bytes).  dtype UFV_RLE: a COCO run-length mask -- `addr` points to the
  * int32 cumulative run ends, `pitch` = number of runs, `aux` = image height; pixel p is on iff the first
@@ -104,24 +107,28 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  *   idx_out              optional (may be null): [n_masks * idx_pitch] uint16, ascending patch
  *                        indices of the on patches, first cnt entries valid
  *   group plan (all optional together; pass grp_ticket = null to skip): for group g with members
- *   grp_member[grp_off[g] .. grp_off[g+1]) the kernel writes grp_nu[g] = number of patches on in
- *   any member, grp_ulist[g*UFV_PLAN_PITCH ..] = those patches ascending, grp_omask[...] = per
- *   listed patch the bitmask of members that pool it (tail zero-filled).  grp_ticket[n_groups]
+ *   grp_member[grp_off[g] .. grp_off[g+1]) (at most UFV_MAX_GROUP) the kernel writes grp_nu[g] = number of
+ *   patches on in any member, grp_ulist[g*UFV_PLAN_PITCH ..] = those patches ascending, and the member
+ *   masks: with S = UFV_OMASK_SETS(max_group) planes per group,
+ *   grp_omask[(g*S + s)*UFV_PLAN_PITCH + i] = for listed patch i the bitmask of members 8s .. 8s+7 that
+ *   pool it (tails zero-filled).  max_group = the largest group size of the call.  grp_ticket[n_groups]
  *   must be zero on entry and is zero again on completion.
  * -------------------------------------------------------------------------------------------*/
 int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
                         int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
                         const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
-                        int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, void* stream);
+                        int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, int max_group, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 2: segmented mask pool.  Replaces the gather feats[ann_index], the layout permute,
  * the fp32 upcast (layer.py:98-104) and the masked mean (layer.py:145-147).
  *   feats [n_rows, n_patch, c] of feat_dtype (UFV_F32 / UFV_BF16 / UFV_F16), contiguous
  *   groups: group g pools object-frames grp_member[grp_off[g] .. grp_off[g+1]) (at most
- *           UFV_MAX_GROUP of them), all of which read feature row grp_row[g]; max_group = the
- *           largest group size in this call (selects the 4- or 8-object kernel variant);
- *           grp_nu / grp_ulist / grp_omask = the union plan written by ufv_mask_to_patches
+ *           UFV_MAX_GROUP of them), all of which read feature row grp_row[g] -- the row is streamed ONCE
+ *           for the whole group, each set of 8 members accumulated by its own pair of consumer warps;
+ *           max_group = the largest group size in this call (selects the kernel variant and the number
+ *           of member-mask planes); grp_nu / grp_ulist / grp_omask = the union plan written by
+ *           ufv_mask_to_patches with the same max_group
  *   cnt[n_masks] on-patch counts from ufv_mask_to_patches
  *   pooled_out fp32 [n_masks, c]:  sum over on patches in ascending patch order, divided by
  *           (float(cnt) + 1e-8f); an all-off mask gives an exact zero row.

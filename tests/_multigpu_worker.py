@@ -37,6 +37,8 @@ def encoder(dev):
 def shard(step, rank, world, n_clips_total, frames, objects, ragged):
     """This rank's contiguous block of the step's clips (sharding.clip_block), as device tensors."""
     block = sharding.clip_block(n_clips_total, rank, world)
+    if len(block) == 0:                           # more ranks than clips: an empty shard still takes part
+        return np.zeros((1, 729, 1152), np.float32), [], []
     feats, masks, ann = synth.make_batch(len(block), frames, objects, "blob", 96, 128, first_clip=1000 * step + block.start,
                                          ragged=ragged)
     return feats, masks, ann
@@ -55,7 +57,7 @@ def main():
     with torch.inference_mode():
         for step, (n_clips, frames, objects, ragged) in enumerate(cases * 3):          # 12 steps: the ring wraps
             feats, masks, ann = shard(step, rank, world, n_clips, frames, objects, ragged)
-            ft = torch.from_numpy(feats).to(dev).bfloat16() if len(masks) else torch.zeros((1, 729, 1152), device=dev).bfloat16()
+            ft = torch.from_numpy(feats).to(dev).bfloat16()
             md = [torch.from_numpy(m).to(dev) for m in masks]
             slots = packer.build_plan(md, ann, ft.shape[0], K, dev).slots
             # (1) fused gather

@@ -197,9 +197,11 @@ def check_group_plan(plan, patches):
         union = np.flatnonzero(on[members].any(0))
         assert nu[g] == union.size
         assert np.array_equal(ulist[g, :nu[g]], union)
-        want = sum((on[m, union].astype(np.uint8) << o) for o, m in enumerate(members))
-        assert np.array_equal(omask[g, :nu[g]], want)
-        assert not omask[g, nu[g]:].any() and not ulist[g, nu[g]:].any()
+        for st in range(omask.shape[1]):                      # one plane per set of 8 members
+            want = sum((on[m, union].astype(np.uint8) << o) for o, m in enumerate(members[8 * st:8 * st + 8]))
+            assert np.array_equal(omask[g, st, :nu[g]], want if members[8 * st:8 * st + 8].size else 0 * union)
+            assert not omask[g, st, nu[g]:].any()
+        assert not ulist[g, nu[g]:].any()
     assert not plan.ticket.cpu().numpy().any()
 
 
@@ -234,17 +236,24 @@ def test_mask_pooling_module_matches_reference_signature(dev, golden_dir):
     assert np.abs(out.cpu().numpy() - g["dense384"]).max() <= 1e-5
 
 
-def test_pool_many_objects_on_one_frame(dev):
-    """17 objects on one frame -> groups of 8, 8, 1 share the frame (PixRQA broadcast shape)."""
-    feats = synth.features(77, 1)
-    masks = synth.masks_blob(78, 17, 1, 100, 120)
-    plan = packer.build_plan([torch.from_numpy(masks).to(dev)], [[[0]]], 1, 4, dev)
-    assert plan.n_groups == 3 and plan.max_group == 8
+@pytest.mark.parametrize("n_obj,groups,sets", [(5, 1, 1), (9, 1, 2), (17, 1, 4), (33, 1, 8), (64, 1, 8), (70, 2, 8)])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_pool_many_objects_on_one_frame(dev, n_obj, groups, sets, dtype):
+    """Many objects on one frame (PixRQA broadcast shape): the frame is one group of up to 64 members, streamed
+    once, every set of 8 members pooled by its own pair of consumer warps; beyond 64 the frame is split.  Every
+    kernel variant (1 / 2 / 4 / 8 member sets), second frame with fewer members in the same call."""
+    feats = R.round_to(synth.features(77, 2), dtype)
+    masks = np.concatenate([synth.masks_blob(78, n_obj, 1, 100, 120), synth.masks_sparse(79, 3, 100, 120)])
+    rows = [0] * n_obj + [1] * 3
+    ann = [[[r] for r in rows]]
+    plan = packer.build_plan([torch.from_numpy(masks).to(dev)], ann, 2, 4, dev)
+    assert plan.n_groups == groups + 1 and plan.max_group == min(n_obj, 64)
     patches = layer.mask_to_patches(plan, dev)
+    assert patches["grp_omask"].shape[1] == sets
     check_group_plan(plan, patches)
-    pooled = layer.mask_pool(torch.from_numpy(feats).to(dev), plan, patches).cpu().numpy()
+    pooled = layer.mask_pool(torch.from_numpy(feats).to(dev).to(TORCH_DT[dtype]), plan, patches).cpu().numpy()
     on = np.stack([R.mask_to_patches(m) for m in masks])
-    assert np.array_equal(pooled, R.mask_pool(feats, [0] * 17, on))
+    assert np.array_equal(pooled, R.mask_pool(feats, rows, on))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -88,10 +88,10 @@ def test_plan_groups_objects_by_frame_and_reserves_token_slots():
 
 
 def test_plan_splits_frames_with_many_objects():
-    masks = [torch.zeros((19, 8, 8), dtype=torch.uint8)]
+    masks = [torch.zeros((150, 8, 8), dtype=torch.uint8)]
     plan = packer.build_plan(masks, [[[0]]], 1, 4, CPU)          # PixRQA broadcast: one feature row
-    assert plan.n_groups == 3 and plan.max_group == 8
-    assert np.diff(plan.host["grp_off"]).tolist() == [8, 8, 3]
+    assert plan.n_groups == 3 and plan.max_group == 64
+    assert np.diff(plan.host["grp_off"]).tolist() == [64, 64, 22]
     assert plan.host["obj_len"].tolist() == [1] and plan.m_pad == 1
 
 

@@ -116,17 +116,13 @@ def run(name, k=8, with_baselines=False):
     merged, counts, _ = layer.ttm(pooled, plan, k, dt)
     l0, l2 = enc.feat_linear[0], enc.feat_linear[2]
     hid = layer.linear(merged, l0.weight, l0.bias, True)
-    bits = patches["bits"].cpu().numpy().view(np.uint32)
-    go, gm = plan.host["grp_off"], plan.host["grp_member"]
-    union = 0
-    for g in range(plan.n_groups):
-        u = np.bitwise_or.reduce(bits[gm[go[g]:go[g + 1]]], axis=0)
-        union += int(np.unpackbits(u.view(np.uint8)).sum())
-    pool_bytes = union * 1152 * ft.element_size() + q * 1152 * 4
+    # SURVEY 8(d) bytes: union over ALL objects of a frame, however the packer grouped them
+    pool_bytes = packer.algorithmic_pool_bytes(plan, patches["bits"].cpu().numpy(), 1152, ft.element_size())
+    union = (pool_bytes - q * 1152 * 4 - q * 96) // (1152 * ft.element_size())
     res = {
         "config": name, "note": note, "object_frames": q, "frames": int(ft.shape[0]), "objects": plan.n_obj,
         "tokens": plan.m_pad, "groups": plan.n_groups, "max_len": plan.max_len,
-        "union_patch_frac": union / (plan.n_groups * 729.0),
+        "union_patch_frac": union / (len(set(plan.host["grp_row"].tolist())) * 729.0),
         "k1_us": timed(lambda: layer.mask_to_patches(plan, dev)),
         "k2_us": timed(lambda: layer.mask_pool(ft, plan, patches)),
         "k3_us": timed(lambda: layer.ttm(pooled, plan, k, dt)),
@@ -136,6 +132,9 @@ def run(name, k=8, with_baselines=False):
     }
     res["pool_gbs"] = pool_bytes / res["k2_us"] / 1e3
     res["pool_bytes"] = pool_bytes
+    peak_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    peak = json.load(open(peak_path))["hbm_gbs"] if os.path.isfile(peak_path) else 6650.0
+    res["pool_frac_of_measured_hbm"] = res["pool_gbs"] / peak
     res["proj_tflops"] = 33947648.0 * plan.m_pad / (res["k4a_us"] + res["k4b_us"]) / 1e6
     res["object_frames_per_s"] = q / res["forward_us"] * 1e6
     res.update(base)
@@ -154,11 +153,11 @@ def main():
         torch.cuda.empty_cache()
     print()
     print(f"{'config':10s} {'obj-fr':>7s} {'tokens':>6s} {'k1':>7s} {'k2':>8s} {'k3':>7s} {'k4a':>6s} {'k4b':>6s} "
-          f"{'fwd us':>8s} {'obj-fr/s':>10s} {'pool GB/s':>9s} {'proj TF':>7s}")
+          f"{'fwd us':>8s} {'obj-fr/s':>10s} {'pool GB/s':>9s} {'of HBM':>6s} {'proj TF':>7s}")
     for r in out:
         print(f"{r['config']:10s} {r['object_frames']:7d} {r['tokens']:6d} {r['k1_us']:7.1f} {r['k2_us']:8.1f} "
               f"{r['k3_us']:7.1f} {r['k4a_us']:6.1f} {r['k4b_us']:6.1f} {r['forward_us']:8.1f} "
-              f"{r['object_frames_per_s']:10.0f} {r['pool_gbs']:9.0f} {r['proj_tflops']:7.1f}"
+              f"{r['object_frames_per_s']:10.0f} {r['pool_gbs']:9.0f} {r['pool_frac_of_measured_hbm']:6.2f} {r['proj_tflops']:7.1f}"
               + (f"   eager-CUDA {r['eager_cuda_obj_frames_per_s']:9.0f}/s" if "eager_cuda_obj_frames_per_s" in r else "")
               + (f"   CPU({r.get('cpu_cores')}c) {r['cpu_obj_frames_per_s']:7.0f}/s" if "cpu_obj_frames_per_s" in r else ""))
 

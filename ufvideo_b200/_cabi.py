@@ -19,9 +19,15 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "ufv_b200.h")
 UFV_F32, UFV_BF16, UFV_F16, UFV_U8, UFV_RLE = 0, 1, 2, 3, 4
 BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
-MAX_GROUP = 8
+MAX_GROUP = 64
 PLAN_PITCH = 736
 ABI_VERSION = 8
+
+def omask_sets(max_group: int) -> int:
+    """UFV_OMASK_SETS of include/ufv_b200.h: member-mask planes per group for a call whose largest group has
+    ``max_group`` object-frames."""
+    return 1 if max_group <= 8 else 2 if max_group <= 16 else 4 if max_group <= 32 else 8
+
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -79,7 +85,7 @@ _SIGNATURES = {
     "ufv_device_address": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "ufv_tap_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p,
-                                      _p, _p, _p]),
+                                      _p, _p, C.c_int, _p]),
     "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_int,
                                 C.c_int, _p, _p]),
     "ufv_mask_pool_backward": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p]),

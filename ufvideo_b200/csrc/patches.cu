@@ -239,7 +239,7 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
                        uint16_t* __restrict__ idx_out, int idx_pitch,
                        const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member,
                        uint32_t* __restrict__ grp_ticket, int32_t* __restrict__ grp_nu,
-                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask,
+                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask, int omask_sets,
                        const uint32_t* __restrict__ dyn_src, uint32_t* __restrict__ dyn_dev) {
   __shared__ int32_t s_taps[4 * UFV_MAX_PATCH_SIDE];
   __shared__ uint32_t s_words[UFV_BITS_WORDS];
@@ -397,15 +397,14 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int i = tid; i < UFV_MAX_GROUP * UFV_BITS_WORDS; i += kPatchThreads) {
+  for (int i = tid; i < n_mem * UFV_BITS_WORDS; i += kPatchThreads) {
     const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
-    s_member_bits[o][w] = o < n_mem ? __ldcg(bits_out + size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w) : 0u;
+    s_member_bits[o][w] = __ldcg(bits_out + size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w);
   }
   __syncthreads();
   if (tid < UFV_BITS_WORDS) {
     uint32_t u = 0;
-#pragma unroll
-    for (int o = 0; o < UFV_MAX_GROUP; ++o) u |= s_member_bits[o][tid];
+    for (int o = 0; o < n_mem; ++o) u |= s_member_bits[o][tid];
     s_words[tid] = u;
   }
   __syncthreads();
@@ -413,22 +412,25 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   __syncthreads();
   const int n_u = s_prefix[UFV_BITS_WORDS];
   uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
-  uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
+  uint8_t* omask = grp_omask + size_t(g) * omask_sets * UFV_PLAN_PITCH;      // [set][UFV_PLAN_PITCH]
   for (int p = tid; p < UFV_PLAN_PITCH; p += kPatchThreads) {
     const int w = p >> 5;
     const uint32_t bit = 1u << (p & 31);
     const uint32_t u = w < UFV_BITS_WORDS ? s_words[w] : 0u;
     if (u & bit) {
       const int pos = s_prefix[w] + __popc(u & (bit - 1u));
-      uint32_t m = 0;
-#pragma unroll
-      for (int o = 0; o < UFV_MAX_GROUP; ++o) m |= ((s_member_bits[o][w] >> (p & 31)) & 1u) << o;
       ulist[pos] = static_cast<uint16_t>(p);
-      omask[pos] = static_cast<uint8_t>(m);
+      for (int st = 0; st < omask_sets; ++st) {          // members 8 st .. 8 st + 7
+        uint32_t m = 0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          if (st * 8 + o < n_mem) m |= ((s_member_bits[st * 8 + o][w] >> (p & 31)) & 1u) << o;
+        omask[size_t(st) * UFV_PLAN_PITCH + pos] = static_cast<uint8_t>(m);
+      }
     }
     if (p >= n_u) {                     // tail: no member pools these slots
       ulist[p] = 0;
-      omask[p] = 0;
+      for (int st = 0; st < omask_sets; ++st) omask[size_t(st) * UFV_PLAN_PITCH + p] = 0;
     }
   }
   if (tid == 0) {
@@ -463,24 +465,28 @@ namespace ufv {
 int launch_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out, int any_row_mode,
                            uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
                            const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
-                           int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, const ufv_dyn_args* dyn_src,
-                           ufv_dyn_args* dyn_dev, void* stream) {
+                           int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, int max_group,
+                           const ufv_dyn_args* dyn_src, ufv_dyn_args* dyn_dev, void* stream) {
   UFV_REQUIRE(n_masks >= 0 && n_out >= 1 && n_out <= UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
               "ufv_mask_to_patches: n_masks=%d n_out=%d out of range", n_masks, n_out);
   if (n_masks == 0) return 0;
   UFV_REQUIRE(desc && taps && bits_out && cnt_out, UFV_E_NULL, "ufv_mask_to_patches: null pointer");
   UFV_REQUIRE(idx_out == nullptr || idx_pitch >= n_out * n_out, UFV_E_SHAPE,
               "ufv_mask_to_patches: idx_pitch %d < %d", idx_pitch, n_out * n_out);
-  if (grp_ticket != nullptr)
+  if (grp_ticket != nullptr) {
     UFV_REQUIRE(grp_off && grp_member && grp_nu && grp_ulist && grp_omask, UFV_E_NULL,
                 "ufv_mask_to_patches: group plan requested but a plan pointer is null");
+    UFV_REQUIRE(max_group >= 1 && max_group <= UFV_MAX_GROUP, UFV_E_SHAPE,
+                "ufv_mask_to_patches: max_group=%d not in [1, %d]", max_group, UFV_MAX_GROUP);
+  }
+  const int omask_sets = UFV_OMASK_SETS(max_group);
   auto kernel = any_row_mode ? ufv::mask_to_patches_kernel<true> : ufv::mask_to_patches_kernel<false>;
   const int threads = any_row_mode ? ufv::PatchCfg<true>::kThreads : ufv::PatchCfg<false>::kThreads;
   return ufv::check_launch(
       "ufv_mask_to_patches",
       ufv::launch_kernel(kernel, dim3(n_masks), dim3(threads), 0, static_cast<cudaStream_t>(stream), desc,
                          taps, n_out, bits_out, cnt_out, idx_out, idx_pitch, grp_off, grp_member, grp_ticket,
-                         grp_nu, grp_ulist, grp_omask, reinterpret_cast<const uint32_t*>(dyn_src),
+                         grp_nu, grp_ulist, grp_omask, omask_sets, reinterpret_cast<const uint32_t*>(dyn_src),
                          reinterpret_cast<uint32_t*>(dyn_dev)));
 }
 }  // namespace ufv
@@ -489,8 +495,8 @@ extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* tap
                                    int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out,
                                    int idx_pitch, const int32_t* grp_off, const int32_t* grp_member,
                                    uint32_t* grp_ticket, int32_t* grp_nu, uint16_t* grp_ulist,
-                                   uint8_t* grp_omask, void* stream) {
+                                   uint8_t* grp_omask, int max_group, void* stream) {
   return ufv::launch_mask_to_patches(desc, taps, n_masks, n_out, any_row_mode, bits_out, cnt_out, idx_out, idx_pitch,
-                                     grp_off, grp_member, grp_ticket, grp_nu, grp_ulist, grp_omask, nullptr, nullptr,
-                                     stream);
+                                     grp_off, grp_member, grp_ticket, grp_nu, grp_ulist, grp_omask, max_group, nullptr,
+                                     nullptr, stream);
 }

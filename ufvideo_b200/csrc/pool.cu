@@ -6,17 +6,18 @@
 // [q, C, 27, 27] temporaries.  Here each needed feature row is read from HBM once per frame
 // and shared by every object on that frame.
 //
-// Work item = (group, 128-channel slice).  A group is one feature row (frame) plus up to OT
-// object-frames pooled from it; its plan (ascending union patch list + per-patch member mask)
-// was written by kernel 1.  Per CTA (96 threads):
-//   warp 2   producer: reads the plan and streams the slice of every listed patch row through a
+// Work item = (group, 128-channel slice).  A group is one feature row (frame) plus up to 64
+// object-frames pooled from it, handled as SETS sets of 8 members; its plan (ascending union patch list
+// + per-patch member mask of every set) was written by kernel 1.  Per CTA (32 * (2 * SETS + 1) threads):
+//   last warp  producer: reads the plan and streams the slice of every listed patch row through a
 //            ring of shared-memory stages with the TMA engine -- one 2-D tiled tensor-map load
 //            when the stage's rows are consecutive patches, otherwise one 1-D bulk copy per row
-//            (off patches are never fetched) -- plus the stage's member masks.
-//   warps 0,1  consumers: 64 channels each, 2 per lane.  Every staged row is added, in ascending
-//            patch order, into the fp32 accumulators of the members whose bit is set (the test
-//            is warp-uniform; adds are packed f32x2).  (A single consumer warp with 4 channels
-//            per lane needs fewer instructions but measured slower: 43.6 vs 41.3 us on c2,
+//            (off patches are never fetched) -- plus the stage's member masks.  The row is fetched
+//            ONCE however many objects pool from it (round 1 re-streamed it per 8 objects).
+//   warps 2s, 2s+1  consumers of member set s: 64 channels each, 2 per lane.  Every staged row is
+//            added, in ascending patch order, into the fp32 accumulators of the members whose bit is
+//            set (the test is warp-uniform; adds are packed f32x2).  (A single consumer warp with 4
+//            channels per lane needs fewer instructions but measured slower: 43.6 vs 41.3 us on c2,
 //            133 vs 89 us with 8 objects per frame -- two warps hide each other's latencies.)
 // Accumulation order per (object, channel) is the plain ascending-patch sequence, independent
 // of any blocking, which is what oracle/restatement.py::mask_pool restates bit-for-bit.
@@ -30,8 +31,6 @@
 namespace ufv {
 
 constexpr int kPoolCh = 128;          // channels per CTA slice
-constexpr int kPoolConsumers = 2;     // consumer warps, 64 channels each
-constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
 // 24.6 KB of ring per CTA (8 CTAs per SM) is the sweet spot; 32 rows x 3 stages measured 0-8 % faster than
 // 16 x 6 at the same footprint (tools/pool_variant_sweep.sh), more or fewer bytes per CTA are both slower.
 #ifndef UFV_POOL_ROWS
@@ -41,8 +40,15 @@ constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
 #define UFV_POOL_STAGES 3
 #endif
 constexpr int kPoolRows = UFV_POOL_ROWS;      // patch rows per stage (multiple of 16, <= 32)
-constexpr int kPoolStages = UFV_POOL_STAGES;
 static_assert(kPoolRows % 16 == 0 && kPoolRows <= 32, "stage rows: one producer lane per row, 16-byte mask copies");
+
+// Many member sets mean many consumer warps per CTA and therefore fewer CTAs per SM (thread limit): the ring
+// deepens so that the bytes in flight per SM stay at ~200 KB.
+template <int SETS> struct PoolCfg {
+  static constexpr int kConsumers = 2 * SETS;                 // consumer warps, 64 channels each
+  static constexpr int kThreads = 32 * (kConsumers + 1);
+  static constexpr int kStages = SETS <= 2 ? UFV_POOL_STAGES : 8;
+};
 
 __device__ __forceinline__ void add2(float2& acc, float2 v) {
   unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
@@ -66,19 +72,19 @@ template <> struct Pair<__half> {
   __device__ static float2 cvt(Raw r) { return __half22float2(*reinterpret_cast<const __half2*>(&r)); }
 };
 
-template <typename T, int OT>
-__global__ void __launch_bounds__(kPoolThreads)
+template <typename T, int OT, int SETS>
+__global__ void __launch_bounds__(PoolCfg<SETS>::kThreads)
 mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
                  int n_patch, int c, int n_slices, const int32_t* __restrict__ cnt,
                  const int32_t* __restrict__ grp_row, const int32_t* __restrict__ grp_off,
                  const int32_t* __restrict__ grp_member, const int32_t* __restrict__ grp_nu,
                  const uint16_t* __restrict__ grp_ulist, const uint8_t* __restrict__ grp_omask,
                  float* __restrict__ pooled) {
-  constexpr int S = kPoolStages, R = kPoolRows;
+  constexpr int S = PoolCfg<SETS>::kStages, R = kPoolRows, NC = PoolCfg<SETS>::kConsumers;
   using Raw = typename Pair<T>::Raw;
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
-  __shared__ __align__(16) uint8_t s_omask[S][R];                          // member masks of the staged rows
+  __shared__ __align__(16) uint8_t s_omask[S][SETS][R];                    // member masks of the staged rows
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t empty_bar[S];
 
@@ -93,7 +99,7 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kPoolConsumers);
+      mbar_init(&empty_bar[s], NC);
     }
     mbar_fence_init();
     if (use_tmap) tma_prefetch_desc(&tmap);
@@ -104,7 +110,7 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   // every plan word this CTA needs is requested at once: one L2 round trip, not a dependent chain
   const uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
   int my_patch = 0, row = 0;
-  if (warp == kPoolConsumers) {
+  if (warp == NC) {
     if (lane < R) my_patch = int(ulist[lane]);             // plan tail is zero-padded: always in bounds
     row = grp_row[g];
   }
@@ -112,9 +118,9 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   const int n_chunks = (n_u + R - 1) / R;
   const int slice_ch = min(kPoolCh, c - ch0);
 
-  if (warp == kPoolConsumers) {
+  if (warp == NC) {
     // ---------------- producer warp: plan -> TMA engine -> shared-memory ring ------------------
-    const uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
+    const uint8_t* omask = grp_omask + size_t(g) * SETS * UFV_PLAN_PITCH;
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
     for (int it = 0; it < n_chunks; ++it) {
@@ -130,8 +136,10 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (lane == 0) {
         const uint32_t data_bytes = tile ? uint32_t(R) * kPoolCh * sizeof(T) : uint32_t(rows) * slice_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], data_bytes + R);
-        bulk_g2s(&s_omask[s][0], omask + it * R, R, &full_bar[s]);
+        mbar_arrive_expect_tx(&full_bar[s], data_bytes + SETS * R);
+#pragma unroll
+        for (int st = 0; st < SETS; ++st)
+          bulk_g2s(&s_omask[s][st][0], omask + size_t(st) * UFV_PLAN_PITCH + it * R, R, &full_bar[s]);
         if (tile) tma_load_2d(dst, &tmap, ch0, int(row_base + first), &full_bar[s]);
       }
       if (!tile) {
@@ -143,14 +151,15 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     }
   } else {
     // ---------------- consumer warps: ascending-patch accumulation ---------------------------------
+    const int set = warp >> 1;                                           // member set of this warp pair
     float2 acc[OT];
 #pragma unroll
     for (int o = 0; o < OT; ++o) acc[o] = make_float2(0.f, 0.f);
-    const int my_ch = warp * (kPoolCh / kPoolConsumers) + lane * 2;      // within the slice
+    const int my_ch = (warp & 1) * (kPoolCh / 2) + lane * 2;             // within the slice
     const bool live = my_ch < slice_ch;
     // output rows and denominators: requested now, needed only after the last stage
-    const int m0 = grp_off[g];
-    const int n_mem = grp_off[g + 1] - m0;
+    const int m0 = grp_off[g] + set * 8;
+    const int n_mem = grp_off[g + 1] - m0;                               // <= 0 for a set this group does not have
     int out_row[OT];
     float denorm[OT];
 #pragma unroll
@@ -164,20 +173,44 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
       uint32_t mk[R / 4];
-      Raw v[R];
 #pragma unroll
-      for (int i = 0; i < R / 4; ++i) mk[i] = reinterpret_cast<const uint32_t*>(&s_omask[s][0])[i];
+      for (int i = 0; i < R / 4; ++i) mk[i] = reinterpret_cast<const uint32_t*>(&s_omask[s][set][0])[i];
+      if (SETS == 1) {
+        // few objects per frame: nearly every staged row is pooled by someone -- pull the whole stage into
+        // registers, hand it back to the producer early, then accumulate
+        Raw v[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);   // stage is in registers: hand it back early
+        for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;   // rows past n_u carry mask 0
-        const float2 f = Pair<T>::cvt(v[r]);
+        for (int r = 0; r < R; ++r) {
+          const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;   // rows past n_u carry mask 0
+          const float2 f = Pair<T>::cvt(v[r]);
 #pragma unroll
-        for (int o = 0; o < OT; ++o)
-          if (m & (1u << o)) add2(acc[o], f);
+          for (int o = 0; o < OT; ++o)
+            if (m & (1u << o)) add2(acc[o], f);
+        }
+      } else {
+        // many objects per frame: a set pools only part of the union -- rows none of its 8 members needs
+        // are skipped without touching shared memory (all tests are warp-uniform)
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 0; i < R / 4; ++i) any |= mk[i];
+        if (any != 0) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;
+            if (m != 0) {
+              const float2 f = Pair<T>::cvt(*reinterpret_cast<const Raw*>(src + r * kPoolCh));
+#pragma unroll
+              for (int o = 0; o < OT; ++o)
+                if (m & (1u << o)) add2(acc[o], f);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
     }
     if (live) {
@@ -265,11 +298,11 @@ struct PoolArgs {
   int n_groups; float* pooled;
 };
 
-template <typename T, int OT>
+template <typename T, int OT, int SETS>
 static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a, cudaStream_t stream) {
   const int n_slices = (a.c + kPoolCh - 1) / kPoolCh;
-  const size_t smem = size_t(kPoolStages) * kPoolRows * kPoolCh * sizeof(T);
-  auto kernel = mask_pool_kernel<T, OT>;
+  const size_t smem = size_t(PoolCfg<SETS>::kStages) * kPoolRows * kPoolCh * sizeof(T);
+  auto kernel = mask_pool_kernel<T, OT, SETS>;
   static bool configured = false;   // idempotent attribute; a benign race sets it twice
   if (!configured) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -277,7 +310,7 @@ static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
   }
   return check_launch(
       "ufv_mask_pool",
-      launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(kPoolThreads), smem, stream, tmap,
+      launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(PoolCfg<SETS>::kThreads), smem, stream, tmap,
                     use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.cnt, a.grp_row,
                     a.grp_off, a.grp_member, a.grp_nu, a.grp_ulist, a.grp_omask, a.pooled));
 }
@@ -285,8 +318,13 @@ static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
 template <typename T>
 static int dispatch_group(int max_group, const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
                           cudaStream_t stream) {
-  if (max_group <= 4) return launch_pool<T, 4>(tmap, use_tmap, a, stream);
-  return launch_pool<T, 8>(tmap, use_tmap, a, stream);
+  if (max_group <= 4) return launch_pool<T, 4, 1>(tmap, use_tmap, a, stream);
+  switch (UFV_OMASK_SETS(max_group)) {
+    case 1: return launch_pool<T, 8, 1>(tmap, use_tmap, a, stream);
+    case 2: return launch_pool<T, 8, 2>(tmap, use_tmap, a, stream);
+    case 4: return launch_pool<T, 8, 4>(tmap, use_tmap, a, stream);
+    default: return launch_pool<T, 8, 8>(tmap, use_tmap, a, stream);
+  }
 }
 
 // ---- adjoint of the mask pool (training) --------------------------------------------

@@ -58,7 +58,7 @@ def _plan_buffers(plan: packer.EncodePlan, device):
     g = max(plan.n_groups, 1)
     nu = torch.empty((g,), dtype=torch.int32, device=device)
     ulist = torch.empty((g, _cabi.PLAN_PITCH), dtype=torch.int16, device=device)
-    omask = torch.empty((g, _cabi.PLAN_PITCH), dtype=torch.uint8, device=device)
+    omask = torch.empty((g, _cabi.omask_sets(plan.max_group), _cabi.PLAN_PITCH), dtype=torch.uint8, device=device)
     return nu, ulist, omask
 
 
@@ -74,7 +74,7 @@ def mask_to_patches(plan: packer.EncodePlan, device, n_out: int = 27, want_idx: 
     _cabi.check(_cabi.lib().ufv_mask_to_patches(
         d["mask_desc"], d["taps"], q, n_out, plan.any_row_mode, bits.data_ptr(), cnt.data_ptr(),
         idx.data_ptr() if want_idx else None, 736, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
-        nu.data_ptr(), ulist.data_ptr(), omask.data_ptr(), _stream_ptr(device)))
+        nu.data_ptr(), ulist.data_ptr(), omask.data_ptr(), plan.max_group, _stream_ptr(device)))
     return {"bits": bits, "cnt": cnt, "idx": idx, "grp_nu": nu, "grp_ulist": ulist, "grp_omask": omask}
 
 
@@ -410,7 +410,8 @@ class MaskExtractor(nn.Module):
             _cabi.check(lib.ufv_mask_to_patches(d["mask_desc"], d["taps"], q, side, plan.any_row_mode,
                                                 ptr["bits"], ptr["cnt"],
                                                 None, 0, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
-                                                ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], stream))
+                                                ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], plan.max_group,
+                                                stream))
             _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, side * side, c, ptr["cnt"], d["grp_row"],
                                           d["grp_off"], d["grp_member"], ptr["grp_nu"], ptr["grp_ulist"],
                                           ptr["grp_omask"], plan.n_groups, plan.max_group, ptr["pooled"], stream))
@@ -442,7 +443,7 @@ class MaskExtractor(nn.Module):
         sizes = (("bits", q * _cabi.BITS_WORDS * 4), ("cnt", q * 4), ("pooled", q * c * 4), ("gemm_ws", gemm_ws),
                  ("merged", m_pad * c * es), ("hidden", m_pad * hid * es), ("counts", plan.n_obj * 4),
                  ("sims", plan.n_obj * max(plan.max_len, 1) * 4), ("dyn", 256),
-                 ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.PLAN_PITCH))
+                 ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.omask_sets(plan.max_group) * _cabi.PLAN_PITCH))
         off, total = {}, 0
         for name, nbytes in sizes:
             off[name] = total

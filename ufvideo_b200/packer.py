@@ -436,3 +436,18 @@ def _upload(plan: EncodePlan, device) -> None:
     p0 = plan.buffer.data_ptr()
     plan.dev = {name: p0 + off for name, off in offsets.items()}
     _evict(plan)
+
+
+def algorithmic_pool_bytes(plan: EncodePlan, bits: np.ndarray, c: int, feat_bytes: int) -> int:
+    """SURVEY.md section 8(d), pool term: every feature row a frame's objects need, ONCE per frame -- the union
+    of the on-patches over ALL object-frames that read that feature row, however the packer grouped them --
+    plus the fp32 pooled rows written and the patch bitmasks read.  ``bits`` = uint32 [q, 24] from kernel 1."""
+    bits = np.asarray(bits).view(np.uint32).reshape(plan.n_masks, -1)
+    go, gm, gr = plan.host["grp_off"], plan.host["grp_member"], plan.host["grp_row"]
+    per_row: dict = {}
+    for g in range(plan.n_groups):
+        u = np.bitwise_or.reduce(bits[gm[go[g]:go[g + 1]]], axis=0)
+        r = int(gr[g])
+        per_row[r] = u if r not in per_row else (per_row[r] | u)
+    union = sum(int(np.unpackbits(u.view(np.uint8)).sum()) for u in per_row.values())
+    return union * c * feat_bytes + plan.n_masks * c * 4 + plan.n_masks * bits.shape[1] * 4
