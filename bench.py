@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--objects", type=int, default=WORKLOAD["objects"])
     ap.add_argument("--family", default=WORKLOAD["family"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true",
+                    help="skip the clip-sharded configs[2] / configs[3] runs reported under 'sweep'")
     ap.add_argument("--timeline", default="", metavar="FILE",
                     help="developer knob: trace the steady-state device-resident step with CUPTI (torch.profiler) "
                          "and write the per-kernel timeline of a few steps to FILE instead of benchmarking")
@@ -304,6 +306,113 @@ def write_timeline(path, step, drain, barrier, rank, world, steps: int = 8):
 
 
 # ------------------------------------------------------------------------------------------------
+# clip-sharded configs[2] / configs[3] (strong scaling: the total number of clips is fixed, rank r owns a
+# contiguous block of them -- the reference's get_chunk sharding, eval/inference_PixRQA.py:186 -- and the
+# per-rank results are collected by the all-gather fused into the last Linear)
+# ------------------------------------------------------------------------------------------------
+SWEEP = {
+    # name: (clips in total, frames, objects, mask family, BASELINE.json entry)
+    "c3": (64, 32, 8, "sparse", "configs[2]: PixRQA-style batch, 64 clips x 32 frames x 8 objects, sparse/irregular masks"),
+    "c4": (32, 256, 16, "blob", "configs[3]: long video, 256 frames x 16 objects per clip (merge-heavy, r = 248); 32 clips"),
+}
+
+
+def run_sweep(enc, dev, rank, world, peak, steps=10, warmup=3):
+    """One entry per config: whole-job ms per step at this world size (CUDA events, max over ranks), the same
+    job on ONE GPU timed in the same run (rank 0, gives the scaling efficiency), and the pool kernel's fraction
+    of the measured HBM peak by SURVEY 8(d) bytes on this rank's shard.  Data: one clip's seeded synthetic masks
+    (uint8 384 x 384) reused for every clip, random bf16 features generated on the device (distinct per frame)."""
+    import torch
+    import torch.distributed as dist
+
+    from ufvideo_b200 import layer, packer, sharding, synth
+
+    k = WORKLOAD["k"]
+    out = []
+    for name, (n_clips, frames, objects, family, note) in SWEEP.items():
+        _, clip_masks, clip_ann = synth.make_clip(0, frames, objects, family, feats=False)
+        mask_dev = torch.from_numpy(clip_masks).to(dev)                                   # shared by all clips
+        q_clip = clip_masks.shape[0]
+
+        def build(clips):
+            n = len(clips)
+            g = torch.Generator(device=dev).manual_seed(4321 + clips.start)
+            feats = torch.randn((max(n, 1) * frames, 729, 1152), generator=g, device=dev, dtype=torch.bfloat16)
+            ann = [[[r + i * frames for r in obj] for obj in clip_ann] for i in range(n)]
+            return feats, [mask_dev] * n, ann
+
+        def time_steps(fn, sync_ranks):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            if sync_ranks and world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+            if sync_ranks and world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+
+        block = sharding.clip_block(n_clips, rank, world)
+        feats, masks, ann = build(block)
+        slots = packer.build_plan(masks, ann, feats.shape[0], k, dev).slots
+        pg = None
+        if world > 1:
+            pad_objs = -(-n_clips // world) * objects
+            pg = sharding.PeerGather(pad_objs * k, pad_objs, 3584, torch.bfloat16, dev)
+        last = [None]
+
+        def step():
+            if pg is None:
+                enc(feats, masks, None, ann, None)
+                return
+            peer, tok_view, cnt_view, s = pg.begin(slots)
+            enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
+            last[0] = s
+
+        def sharded():
+            step()
+
+        ms = time_steps(sharded, True)
+        if pg is not None:
+            pg.wait(last[0])
+            torch.cuda.synchronize()
+            pg.check()
+        # pool kernel of this rank's shard, alone
+        plan = packer.build_plan(masks, ann, feats.shape[0], k, dev)
+        patches = layer.mask_to_patches(plan, dev)
+        pool_bytes = packer.algorithmic_pool_bytes(plan, patches["bits"].cpu().numpy(), 1152, 2)
+        ms_pool = time_steps(lambda: layer.mask_pool(feats, plan, patches), False)
+        entry = {"config": name, "workload": note, "clips_total": n_clips, "clips_on_rank0": len(block),
+                 "object_frames_per_step": n_clips * q_clip, "n_gpus": world, "ms_per_step": ms,
+                 "object_frames_per_s": n_clips * q_clip / (ms * 1e-3),
+                 "pool": {"us_per_launch": ms_pool * 1e3, "algorithmic_bytes": pool_bytes,
+                          "achieved_gbs": pool_bytes / (ms_pool * 1e-3) / 1e9,
+                          "frac_of_measured_hbm": pool_bytes / (ms_pool * 1e-3) / 1e9 / peak,
+                          "objects_per_frame": objects}}
+        del feats, masks, ann, plan, patches, pg
+        torch.cuda.empty_cache()
+        if world > 1:
+            # the whole job on one GPU, same process, for the efficiency of this world size
+            ms1 = torch.zeros(1, device=dev)
+            if rank == 0:
+                f1, m1, a1 = build(range(n_clips))
+                ms1[0] = time_steps(lambda: enc(f1, m1, None, a1, None), False)
+                del f1, m1, a1
+                torch.cuda.empty_cache()
+            dist.broadcast(ms1, 0)
+            entry["ms_per_step_1gpu_same_run"] = float(ms1.item())
+            entry["scaling_efficiency"] = float(ms1.item()) / (world * ms)
+        out.append(entry)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(a):
@@ -475,6 +584,12 @@ def run_ours(a):
 
     if pg is not None:
         pg.check()
+    sweep = None
+    if not a.no_sweep:
+        pending.clear()
+        torch.cuda.empty_cache()
+        with torch.inference_mode():
+            sweep = run_sweep(enc, dev, rank, world, peak)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -527,6 +642,8 @@ def run_ours(a):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if sweep is not None:
+        line["sweep"] = sweep
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

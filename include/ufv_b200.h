@@ -47,9 +47,13 @@ enum {
 #define UFV_MAX_PATCH_SIDE 27    /* kernels are sized for up to 27 x 27 patches              */
 #define UFV_MAX_GROUP 64         /* object-frames pooled together from one staged frame tile */
 #define UFV_PLAN_PITCH 736       /* entries per group in the union-plan arrays (>= 729, % 16 == 0) */
-/* Members of a group are handled in sets of 8 (one pair of consumer warps of the pool kernel per set); a call
- * whose largest group has `g` members carries this many member-mask planes per group (1, 2, 4 or 8): */
-#define UFV_OMASK_SETS(g) ((g) <= 8 ? 1 : (g) <= 16 ? 2 : (g) <= 32 ? 4 : 8)
+/* Per-group member information in the union plan, chosen by the largest group of the call (max_group):
+ *   max_group <= 8   UFV_PLAN_PITCH bytes per group: per listed patch the bitmask of members that pool it
+ *   max_group  > 8   UFV_PLAN_MEMBERS(max_group) * UFV_BITS_WORDS uint32 per group: per member (padded to 16 /
+ *                    32 / 64 members) one bit per listed patch, bit i%32 of word i/32 = the member pools the
+ *                    i-th listed patch (so a consumer walks only the rows its member needs) */
+#define UFV_PLAN_MEMBERS(g) ((g) <= 8 ? 8 : (g) <= 16 ? 16 : (g) <= 32 ? 32 : 64)
+#define UFV_PLAN_MASK_BYTES(g) ((g) <= 8 ? UFV_PLAN_PITCH : UFV_PLAN_MEMBERS(g) * UFV_BITS_WORDS * 4)
 
 /* One object-frame's mask plane (32 bytes).  dtype UFV_RLE: a COCO run-length mask -- `addr` points to the
  * int32 cumulative run ends, `pitch` = number of runs, `aux` = image height; pixel p is on iff the first
@@ -109,9 +113,8 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  *   group plan (all optional together; pass grp_ticket = null to skip): for group g with members
  *   grp_member[grp_off[g] .. grp_off[g+1]) (at most UFV_MAX_GROUP) the kernel writes grp_nu[g] = number of
  *   patches on in any member, grp_ulist[g*UFV_PLAN_PITCH ..] = those patches ascending, and the member
- *   masks: with S = UFV_OMASK_SETS(max_group) planes per group,
- *   grp_omask[(g*S + s)*UFV_PLAN_PITCH + i] = for listed patch i the bitmask of members 8s .. 8s+7 that
- *   pool it (tails zero-filled).  max_group = the largest group size of the call.  grp_ticket[n_groups]
+ *   information at grp_omask + g * UFV_PLAN_MASK_BYTES(max_group) in the layout described at
+ *   UFV_PLAN_MASK_BYTES (tails zero-filled).  max_group = the largest group size of the call.  grp_ticket[n_groups]
  *   must be zero on entry and is zero again on completion.
  * -------------------------------------------------------------------------------------------*/
 int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
@@ -125,10 +128,12 @@ int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_ma
  *   feats [n_rows, n_patch, c] of feat_dtype (UFV_F32 / UFV_BF16 / UFV_F16), contiguous
  *   groups: group g pools object-frames grp_member[grp_off[g] .. grp_off[g+1]) (at most
  *           UFV_MAX_GROUP of them), all of which read feature row grp_row[g] -- the row is streamed ONCE
- *           for the whole group, each set of 8 members accumulated by its own pair of consumer warps;
- *           max_group = the largest group size in this call (selects the kernel variant and the number
- *           of member-mask planes); grp_nu / grp_ulist / grp_omask = the union plan written by
- *           ufv_mask_to_patches with the same max_group
+ *           for the whole group.  Up to 8 members: every staged row is added into the members whose mask bit
+ *           is set (warp-uniform predicates).  9 .. 64 members: each consumer warp owns a few members and
+ *           walks only the staged rows its members pool (bit iteration over the member words).
+ *           max_group = the largest group size in this call (selects the kernel variant and the plan
+ *           layout); grp_nu / grp_ulist / grp_omask = the union plan written by ufv_mask_to_patches with
+ *           the same max_group
  *   cnt[n_masks] on-patch counts from ufv_mask_to_patches
  *   pooled_out fp32 [n_masks, c]:  sum over on patches in ascending patch order, divided by
  *           (float(cnt) + 1e-8f); an all-off mask gives an exact zero row.

@@ -197,10 +197,18 @@ def check_group_plan(plan, patches):
         union = np.flatnonzero(on[members].any(0))
         assert nu[g] == union.size
         assert np.array_equal(ulist[g, :nu[g]], union)
-        for st in range(omask.shape[1]):                      # one plane per set of 8 members
-            want = sum((on[m, union].astype(np.uint8) << o) for o, m in enumerate(members[8 * st:8 * st + 8]))
-            assert np.array_equal(omask[g, st, :nu[g]], want if members[8 * st:8 * st + 8].size else 0 * union)
-            assert not omask[g, st, nu[g]:].any()
+        if plan.max_group <= 8:                               # a byte per listed patch: bitmask of the members
+            want = sum((on[m, union].astype(np.uint8) << o) for o, m in enumerate(members))
+            assert np.array_equal(omask[g, :nu[g]], want)
+            assert not omask[g, nu[g]:].any()
+        else:                                                 # a bit row per member: bit i = pools the i-th listed patch
+            words = omask[g].view(np.uint32).reshape(-1, 24)
+            assert words.shape[0] in (16, 32, 64) and words.shape[0] >= plan.max_group
+            for o in range(words.shape[0]):
+                want = np.zeros(24 * 32, dtype=bool)
+                if o < members.size:
+                    want[:nu[g]] = on[members[o], union]
+                assert np.array_equal(words[o], R.pack_bits(want)), (g, o)
         assert not ulist[g, nu[g]:].any()
     assert not plan.ticket.cpu().numpy().any()
 
@@ -236,12 +244,13 @@ def test_mask_pooling_module_matches_reference_signature(dev, golden_dir):
     assert np.abs(out.cpu().numpy() - g["dense384"]).max() <= 1e-5
 
 
-@pytest.mark.parametrize("n_obj,groups,sets", [(5, 1, 1), (9, 1, 2), (17, 1, 4), (33, 1, 8), (64, 1, 8), (70, 2, 8)])
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_pool_many_objects_on_one_frame(dev, n_obj, groups, sets, dtype):
+@pytest.mark.parametrize("n_obj,groups,plan_bytes", [(5, 1, 736), (9, 1, 1536), (17, 1, 3072), (33, 1, 6144),
+                                                     (64, 1, 6144), (70, 2, 6144)])
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+def test_pool_many_objects_on_one_frame(dev, n_obj, groups, plan_bytes, dtype):
     """Many objects on one frame (PixRQA broadcast shape): the frame is one group of up to 64 members, streamed
-    once, every set of 8 members pooled by its own pair of consumer warps; beyond 64 the frame is split.  Every
-    kernel variant (1 / 2 / 4 / 8 member sets), second frame with fewer members in the same call."""
+    once; beyond 8 members the bit-iterating consumers run (2 / 4 / 8 members per warp), beyond 64 the frame is
+    split.  A second frame with fewer members rides in the same call."""
     feats = R.round_to(synth.features(77, 2), dtype)
     masks = np.concatenate([synth.masks_blob(78, n_obj, 1, 100, 120), synth.masks_sparse(79, 3, 100, 120)])
     rows = [0] * n_obj + [1] * 3
@@ -249,7 +258,7 @@ def test_pool_many_objects_on_one_frame(dev, n_obj, groups, sets, dtype):
     plan = packer.build_plan([torch.from_numpy(masks).to(dev)], ann, 2, 4, dev)
     assert plan.n_groups == groups + 1 and plan.max_group == min(n_obj, 64)
     patches = layer.mask_to_patches(plan, dev)
-    assert patches["grp_omask"].shape[1] == sets
+    assert patches["grp_omask"].shape[1] == plan_bytes
     check_group_plan(plan, patches)
     pooled = layer.mask_pool(torch.from_numpy(feats).to(dev).to(TORCH_DT[dtype]), plan, patches).cpu().numpy()
     on = np.stack([R.mask_to_patches(m) for m in masks])

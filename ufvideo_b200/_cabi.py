@@ -23,10 +23,12 @@ MAX_GROUP = 64
 PLAN_PITCH = 736
 ABI_VERSION = 8
 
-def omask_sets(max_group: int) -> int:
-    """UFV_OMASK_SETS of include/ufv_b200.h: member-mask planes per group for a call whose largest group has
-    ``max_group`` object-frames."""
-    return 1 if max_group <= 8 else 2 if max_group <= 16 else 4 if max_group <= 32 else 8
+def plan_mask_bytes(max_group: int) -> int:
+    """UFV_PLAN_MASK_BYTES of include/ufv_b200.h: bytes of member information per group in the union plan."""
+    if max_group <= 8:
+        return PLAN_PITCH
+    members = 16 if max_group <= 16 else 32 if max_group <= 32 else 64
+    return members * BITS_WORDS * 4
 
 
 _p = C.c_void_p

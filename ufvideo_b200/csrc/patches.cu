@@ -239,12 +239,13 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
                        uint16_t* __restrict__ idx_out, int idx_pitch,
                        const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member,
                        uint32_t* __restrict__ grp_ticket, int32_t* __restrict__ grp_nu,
-                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask, int omask_sets,
+                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask, int plan_members,
                        const uint32_t* __restrict__ dyn_src, uint32_t* __restrict__ dyn_dev) {
   __shared__ int32_t s_taps[4 * UFV_MAX_PATCH_SIDE];
   __shared__ uint32_t s_words[UFV_BITS_WORDS];
   __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
   __shared__ uint32_t s_member_bits[UFV_MAX_GROUP][UFV_BITS_WORDS];
+  __shared__ uint16_t s_ulist[UFV_PLAN_PITCH];
   constexpr int kPatchThreads = PatchCfg<ROWS>::kThreads;
   __shared__ uint16_t s_flags[PatchCfg<ROWS>::kFlagRows][PatchCfg<ROWS>::kFlagCols];
   __shared__ int s_span[2];
@@ -397,9 +398,9 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int i = tid; i < n_mem * UFV_BITS_WORDS; i += kPatchThreads) {
+  for (int i = tid; i < max(n_mem, 8) * UFV_BITS_WORDS; i += kPatchThreads) {
     const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
-    s_member_bits[o][w] = __ldcg(bits_out + size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w);
+    s_member_bits[o][w] = o < n_mem ? __ldcg(bits_out + size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w) : 0u;
   }
   __syncthreads();
   if (tid < UFV_BITS_WORDS) {
@@ -412,7 +413,8 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
   __syncthreads();
   const int n_u = s_prefix[UFV_BITS_WORDS];
   uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
-  uint8_t* omask = grp_omask + size_t(g) * omask_sets * UFV_PLAN_PITCH;      // [set][UFV_PLAN_PITCH]
+  const bool member_words = plan_members > 8;      // many members: one bit row per member instead of a byte per patch
+  uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
   for (int p = tid; p < UFV_PLAN_PITCH; p += kPatchThreads) {
     const int w = p >> 5;
     const uint32_t bit = 1u << (p & 31);
@@ -420,17 +422,33 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
     if (u & bit) {
       const int pos = s_prefix[w] + __popc(u & (bit - 1u));
       ulist[pos] = static_cast<uint16_t>(p);
-      for (int st = 0; st < omask_sets; ++st) {          // members 8 st .. 8 st + 7
+      s_ulist[pos] = static_cast<uint16_t>(p);
+      if (!member_words) {
         uint32_t m = 0;
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
-          if (st * 8 + o < n_mem) m |= ((s_member_bits[st * 8 + o][w] >> (p & 31)) & 1u) << o;
-        omask[size_t(st) * UFV_PLAN_PITCH + pos] = static_cast<uint8_t>(m);
+        for (int o = 0; o < 8; ++o) m |= ((s_member_bits[o][w] >> (p & 31)) & 1u) << o;   // rows past n_mem are zero
+        omask[pos] = static_cast<uint8_t>(m);
       }
     }
     if (p >= n_u) {                     // tail: no member pools these slots
       ulist[p] = 0;
-      for (int st = 0; st < omask_sets; ++st) omask[size_t(st) * UFV_PLAN_PITCH + p] = 0;
+      if (!member_words) omask[p] = 0;
+    }
+  }
+  if (member_words) {
+    // word k of member o: bit b = member o pools the (32 k + b)-th listed patch.  One ballot per (chunk, member).
+    __syncthreads();
+    uint32_t* mwords = reinterpret_cast<uint32_t*>(grp_omask) + size_t(g) * plan_members * UFV_BITS_WORDS;
+    constexpr int kWarps = kPatchThreads / 32;
+    for (int k = warp; k < UFV_BITS_WORDS; k += kWarps) {
+      const int i = 32 * k + lane;
+      const bool valid = i < n_u;
+      const int patch = valid ? int(s_ulist[i]) : 0;
+      for (int o = 0; o < plan_members; ++o) {
+        const bool on = valid && o < n_mem && ((s_member_bits[o][patch >> 5] >> (patch & 31)) & 1u);
+        const uint32_t word = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) mwords[size_t(o) * UFV_BITS_WORDS + k] = word;
+      }
     }
   }
   if (tid == 0) {
@@ -479,14 +497,14 @@ int launch_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n
     UFV_REQUIRE(max_group >= 1 && max_group <= UFV_MAX_GROUP, UFV_E_SHAPE,
                 "ufv_mask_to_patches: max_group=%d not in [1, %d]", max_group, UFV_MAX_GROUP);
   }
-  const int omask_sets = UFV_OMASK_SETS(max_group);
+  const int plan_members = UFV_PLAN_MEMBERS(max_group);
   auto kernel = any_row_mode ? ufv::mask_to_patches_kernel<true> : ufv::mask_to_patches_kernel<false>;
   const int threads = any_row_mode ? ufv::PatchCfg<true>::kThreads : ufv::PatchCfg<false>::kThreads;
   return ufv::check_launch(
       "ufv_mask_to_patches",
       ufv::launch_kernel(kernel, dim3(n_masks), dim3(threads), 0, static_cast<cudaStream_t>(stream), desc,
                          taps, n_out, bits_out, cnt_out, idx_out, idx_pitch, grp_off, grp_member, grp_ticket,
-                         grp_nu, grp_ulist, grp_omask, omask_sets, reinterpret_cast<const uint32_t*>(dyn_src),
+                         grp_nu, grp_ulist, grp_omask, plan_members, reinterpret_cast<const uint32_t*>(dyn_src),
                          reinterpret_cast<uint32_t*>(dyn_dev)));
 }
 }  // namespace ufv

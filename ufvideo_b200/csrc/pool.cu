@@ -7,18 +7,21 @@
 // and shared by every object on that frame.
 //
 // Work item = (group, 128-channel slice).  A group is one feature row (frame) plus up to 64
-// object-frames pooled from it, handled as SETS sets of 8 members; its plan (ascending union patch list
-// + per-patch member mask of every set) was written by kernel 1.  Per CTA (32 * (2 * SETS + 1) threads):
-//   last warp  producer: reads the plan and streams the slice of every listed patch row through a
-//            ring of shared-memory stages with the TMA engine -- one 2-D tiled tensor-map load
-//            when the stage's rows are consecutive patches, otherwise one 1-D bulk copy per row
-//            (off patches are never fetched) -- plus the stage's member masks.  The row is fetched
-//            ONCE however many objects pool from it (round 1 re-streamed it per 8 objects).
-//   warps 2s, 2s+1  consumers of member set s: 64 channels each, 2 per lane.  Every staged row is
-//            added, in ascending patch order, into the fp32 accumulators of the members whose bit is
-//            set (the test is warp-uniform; adds are packed f32x2).  (A single consumer warp with 4
-//            channels per lane needs fewer instructions but measured slower: 43.6 vs 41.3 us on c2,
-//            133 vs 89 us with 8 objects per frame -- two warps hide each other's latencies.)
+// object-frames pooled from it; its plan (ascending union patch list + member information) was written
+// by kernel 1.  The producer warp reads the plan and streams the slice of every listed patch row through
+// a ring of shared-memory stages with the TMA engine -- one 2-D tiled tensor-map load when the stage's
+// rows are consecutive patches, otherwise one 1-D bulk copy per row (off patches are never fetched).  The
+// row is fetched ONCE however many objects pool from it.  Two consumer designs:
+//   mask_pool_kernel         (<= 8 members)  two consumer warps, 64 channels each, 2 per lane.  Every staged row
+//            is added, in ascending patch order, into the fp32 accumulators of the members whose bit is set
+//            (warp-uniform predicates, packed f32x2 adds).  Best when most members pool most rows.  (A single
+//            consumer warp with 4 channels per lane needs fewer instructions but measured slower: 43.6 vs
+//            41.3 us on c2, 133 vs 89 us with 8 objects per frame -- two warps hide each other's latencies.)
+//   mask_pool_sparse_kernel  (9 .. 64 members)  eight consumer warps, each owning a few members and all 128
+//            channels (4 per lane): a warp walks the set bits of its member's 32-row stage word and adds only
+//            those rows.  With 16 - 64 objects on a frame a row is pooled by a small fraction of them, and
+//            the predicated design spends its issue slots on adds that are switched off (measured on c4,
+//            16 blobs per frame: 306 us predicated in one pass, 263 us re-streaming the frame per 8 members).
 // Accumulation order per (object, channel) is the plain ascending-patch sequence, independent
 // of any blocking, which is what oracle/restatement.py::mask_pool restates bit-for-bit.
 //
@@ -42,13 +45,11 @@ constexpr int kPoolCh = 128;          // channels per CTA slice
 constexpr int kPoolRows = UFV_POOL_ROWS;      // patch rows per stage (multiple of 16, <= 32)
 static_assert(kPoolRows % 16 == 0 && kPoolRows <= 32, "stage rows: one producer lane per row, 16-byte mask copies");
 
-// Many member sets mean many consumer warps per CTA and therefore fewer CTAs per SM (thread limit): the ring
-// deepens so that the bytes in flight per SM stay at ~200 KB.
-template <int SETS> struct PoolCfg {
-  static constexpr int kConsumers = 2 * SETS;                 // consumer warps, 64 channels each
-  static constexpr int kThreads = 32 * (kConsumers + 1);
-  static constexpr int kStages = SETS <= 2 ? UFV_POOL_STAGES : 8;
-};
+constexpr int kPoolStages = UFV_POOL_STAGES;
+constexpr int kPoolConsumers = 2;             // dense kernel: consumer warps, 64 channels each
+constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
+constexpr int kSparseConsumers = 8;           // sparse kernel: consumer warps, 128 channels each, members interleaved
+constexpr int kSparseThreads = 32 * (kSparseConsumers + 1);
 
 __device__ __forceinline__ void add2(float2& acc, float2 v) {
   unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
@@ -72,19 +73,19 @@ template <> struct Pair<__half> {
   __device__ static float2 cvt(Raw r) { return __half22float2(*reinterpret_cast<const __half2*>(&r)); }
 };
 
-template <typename T, int OT, int SETS>
-__global__ void __launch_bounds__(PoolCfg<SETS>::kThreads)
+template <typename T, int OT>
+__global__ void __launch_bounds__(kPoolThreads)
 mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
                  int n_patch, int c, int n_slices, const int32_t* __restrict__ cnt,
                  const int32_t* __restrict__ grp_row, const int32_t* __restrict__ grp_off,
                  const int32_t* __restrict__ grp_member, const int32_t* __restrict__ grp_nu,
                  const uint16_t* __restrict__ grp_ulist, const uint8_t* __restrict__ grp_omask,
                  float* __restrict__ pooled) {
-  constexpr int S = PoolCfg<SETS>::kStages, R = kPoolRows, NC = PoolCfg<SETS>::kConsumers;
+  constexpr int S = kPoolStages, R = kPoolRows;
   using Raw = typename Pair<T>::Raw;
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
-  __shared__ __align__(16) uint8_t s_omask[S][SETS][R];                    // member masks of the staged rows
+  __shared__ __align__(16) uint8_t s_omask[S][R];                          // member masks of the staged rows
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t empty_bar[S];
 
@@ -99,7 +100,7 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], NC);
+      mbar_init(&empty_bar[s], kPoolConsumers);
     }
     mbar_fence_init();
     if (use_tmap) tma_prefetch_desc(&tmap);
@@ -110,7 +111,7 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   // every plan word this CTA needs is requested at once: one L2 round trip, not a dependent chain
   const uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
   int my_patch = 0, row = 0;
-  if (warp == NC) {
+  if (warp == kPoolConsumers) {
     if (lane < R) my_patch = int(ulist[lane]);             // plan tail is zero-padded: always in bounds
     row = grp_row[g];
   }
@@ -118,9 +119,9 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   const int n_chunks = (n_u + R - 1) / R;
   const int slice_ch = min(kPoolCh, c - ch0);
 
-  if (warp == NC) {
+  if (warp == kPoolConsumers) {
     // ---------------- producer warp: plan -> TMA engine -> shared-memory ring ------------------
-    const uint8_t* omask = grp_omask + size_t(g) * SETS * UFV_PLAN_PITCH;
+    const uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
     for (int it = 0; it < n_chunks; ++it) {
@@ -136,10 +137,8 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (lane == 0) {
         const uint32_t data_bytes = tile ? uint32_t(R) * kPoolCh * sizeof(T) : uint32_t(rows) * slice_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], data_bytes + SETS * R);
-#pragma unroll
-        for (int st = 0; st < SETS; ++st)
-          bulk_g2s(&s_omask[s][st][0], omask + size_t(st) * UFV_PLAN_PITCH + it * R, R, &full_bar[s]);
+        mbar_arrive_expect_tx(&full_bar[s], data_bytes + R);
+        bulk_g2s(&s_omask[s][0], omask + it * R, R, &full_bar[s]);
         if (tile) tma_load_2d(dst, &tmap, ch0, int(row_base + first), &full_bar[s]);
       }
       if (!tile) {
@@ -151,15 +150,14 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     }
   } else {
     // ---------------- consumer warps: ascending-patch accumulation ---------------------------------
-    const int set = warp >> 1;                                           // member set of this warp pair
     float2 acc[OT];
 #pragma unroll
     for (int o = 0; o < OT; ++o) acc[o] = make_float2(0.f, 0.f);
-    const int my_ch = (warp & 1) * (kPoolCh / 2) + lane * 2;             // within the slice
+    const int my_ch = warp * (kPoolCh / kPoolConsumers) + lane * 2;      // within the slice
     const bool live = my_ch < slice_ch;
     // output rows and denominators: requested now, needed only after the last stage
-    const int m0 = grp_off[g] + set * 8;
-    const int n_mem = grp_off[g + 1] - m0;                               // <= 0 for a set this group does not have
+    const int m0 = grp_off[g];
+    const int n_mem = grp_off[g + 1] - m0;
     int out_row[OT];
     float denorm[OT];
 #pragma unroll
@@ -173,44 +171,20 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
       uint32_t mk[R / 4];
+      Raw v[R];
 #pragma unroll
-      for (int i = 0; i < R / 4; ++i) mk[i] = reinterpret_cast<const uint32_t*>(&s_omask[s][set][0])[i];
-      if (SETS == 1) {
-        // few objects per frame: nearly every staged row is pooled by someone -- pull the whole stage into
-        // registers, hand it back to the producer early, then accumulate
-        Raw v[R];
+      for (int i = 0; i < R / 4; ++i) mk[i] = reinterpret_cast<const uint32_t*>(&s_omask[s][0])[i];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);   // stage is in registers: hand it back early
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;   // rows past n_u carry mask 0
-          const float2 f = Pair<T>::cvt(v[r]);
+      for (int r = 0; r < R; ++r) {
+        const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;   // rows past n_u carry mask 0
+        const float2 f = Pair<T>::cvt(v[r]);
 #pragma unroll
-          for (int o = 0; o < OT; ++o)
-            if (m & (1u << o)) add2(acc[o], f);
-        }
-      } else {
-        // many objects per frame: a set pools only part of the union -- rows none of its 8 members needs
-        // are skipped without touching shared memory (all tests are warp-uniform)
-        uint32_t any = 0;
-#pragma unroll
-        for (int i = 0; i < R / 4; ++i) any |= mk[i];
-        if (any != 0) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;
-            if (m != 0) {
-              const float2 f = Pair<T>::cvt(*reinterpret_cast<const Raw*>(src + r * kPoolCh));
-#pragma unroll
-              for (int o = 0; o < OT; ++o)
-                if (m & (1u << o)) add2(acc[o], f);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        for (int o = 0; o < OT; ++o)
+          if (m & (1u << o)) add2(acc[o], f);
       }
     }
     if (live) {
@@ -222,6 +196,155 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
           out.y = __fdiv_rn(acc[o].y, denorm[o]);
           *reinterpret_cast<float2*>(pooled + size_t(out_row[o]) * c + ch0 + my_ch) = out;
         }
+      }
+    }
+  }
+}
+
+// four adjacent channels of one staged row -> fp32 quad
+template <typename T> struct Quad;
+template <> struct Quad<float> {
+  __device__ static float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+};
+template <> struct Quad<__nv_bfloat16> {
+  __device__ static float4 load(const __nv_bfloat16* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+  }
+};
+template <> struct Quad<__half> {
+  __device__ static float4 load(const __half* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
+// ---- many objects on a frame: bit-iterating consumers ------------------------------------------------------
+// MPW = members per consumer warp (member j belongs to warp j % 8, its slot there is j / 8): 2 / 4 / 8 for groups of
+// up to 16 / 32 / 64 members.  A warp visits, per staged 32-row chunk and per member it owns, exactly the rows
+// that member pools (set bits of the member word, ascending) -- the accumulation order per (object, channel) is
+// the same ascending-patch sequence as in the dense kernel and in the oracle.
+template <typename T, int MPW>
+__global__ void __launch_bounds__(kSparseThreads)
+mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
+                        int n_patch, int c, int n_slices, const int32_t* __restrict__ cnt,
+                        const int32_t* __restrict__ grp_row, const int32_t* __restrict__ grp_off,
+                        const int32_t* __restrict__ grp_member, const int32_t* __restrict__ grp_nu,
+                        const uint16_t* __restrict__ grp_ulist, const uint32_t* __restrict__ grp_mwords,
+                        float* __restrict__ pooled) {
+  constexpr int S = kPoolStages, R = kPoolRows, NW = kSparseConsumers, PM = MPW * NW;
+  static_assert(R == 32, "one member word covers one stage");
+  extern __shared__ __align__(1024) uint8_t dyn_smem[];
+  T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
+  __shared__ uint32_t s_mw[PM][UFV_BITS_WORDS];                            // member words of this group
+  __shared__ __align__(8) uint64_t full_bar[S];
+  __shared__ __align__(8) uint64_t empty_bar[S];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int g = blockIdx.x / n_slices;
+  const int slice = blockIdx.x - g * n_slices;
+  const int ch0 = slice * kPoolCh;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NW);
+    }
+    mbar_fence_init();
+    if (use_tmap) tma_prefetch_desc(&tmap);
+  }
+  __syncthreads();
+  pdl_wait();                  // the union plan and counts come from kernel 1
+  pdl_launch_dependents();
+  const uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
+  int my_patch = 0, row = 0;
+  if (warp == NW) {
+    if (lane < R) my_patch = int(ulist[lane]);
+    row = grp_row[g];
+  }
+  const int n_u = grp_nu[g];
+  const int n_chunks = (n_u + R - 1) / R;
+  const int slice_ch = min(kPoolCh, c - ch0);
+  const int m0 = grp_off[g];
+  const int n_mem = grp_off[g + 1] - m0;
+  {
+    const uint32_t* src = grp_mwords + size_t(g) * PM * UFV_BITS_WORDS;
+    for (int i = tid; i < PM * UFV_BITS_WORDS; i += kSparseThreads)
+      (&s_mw[0][0])[i] = i / UFV_BITS_WORDS < n_mem ? src[i] : 0u;
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ---------------- producer warp (as in the dense kernel, without member masks) ----------------
+    const int64_t row_base = int64_t(row) * n_patch;
+    const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
+    for (int it = 0; it < n_chunks; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      const int patch = my_patch;
+      if (it + 1 < n_chunks && lane < R) my_patch = int(ulist[(it + 1) * R + lane]);
+      const int rows = min(R, n_u - it * R);
+      const int first = __shfl_sync(0xffffffffu, patch, 0);
+      const int last = __shfl_sync(0xffffffffu, patch, rows - 1);
+      const bool tile = use_tmap && rows == R && (last - first == R - 1);
+      T* dst = ring + size_t(s) * R * kPoolCh;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[s], tile ? uint32_t(R) * kPoolCh * sizeof(T) : uint32_t(rows) * slice_bytes);
+        if (tile) tma_load_2d(dst, &tmap, ch0, int(row_base + first), &full_bar[s]);
+      }
+      if (!tile) {
+        __syncwarp();
+        if (lane < rows)
+          bulk_g2s(dst + lane * kPoolCh, feats + (row_base + patch) * int64_t(c) + ch0, slice_bytes, &full_bar[s]);
+      }
+    }
+  } else {
+    // ---------------- consumer warps: members warp, warp + 8, ..., all 128 channels, 4 per lane -------------
+    float4 acc[MPW];
+#pragma unroll
+    for (int mi = 0; mi < MPW; ++mi) acc[mi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int my_ch = lane * 4;
+    const bool live = my_ch < slice_ch;
+    for (int it = 0; it < n_chunks; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(&full_bar[s], ph);
+      const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
+#pragma unroll
+      for (int mi = 0; mi < MPW; ++mi) {
+        uint32_t word = s_mw[mi * NW + warp][it];            // warp-uniform
+        while (word != 0u) {
+          const int r = __ffs(word) - 1;
+          word &= word - 1u;
+          const float4 f = Quad<T>::load(src + r * kPoolCh);
+          float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
+          add2(lo, make_float2(f.x, f.y));
+          add2(hi, make_float2(f.z, f.w));
+          acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < MPW; ++mi) {
+      const int j = mi * NW + warp;
+      if (j < n_mem && live) {
+        const int out_row = grp_member[m0 + j];
+        const float denorm = __fadd_rn(float(cnt[out_row]), 1e-8f);   // layer.py:145
+        float4 out;
+        out.x = __fdiv_rn(acc[mi].x, denorm);
+        out.y = __fdiv_rn(acc[mi].y, denorm);
+        out.z = __fdiv_rn(acc[mi].z, denorm);
+        out.w = __fdiv_rn(acc[mi].w, denorm);
+        *reinterpret_cast<float4*>(pooled + size_t(out_row) * c + ch0 + my_ch) = out;
       }
     }
   }
@@ -298,11 +421,11 @@ struct PoolArgs {
   int n_groups; float* pooled;
 };
 
-template <typename T, int OT, int SETS>
+template <typename T, int OT>
 static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a, cudaStream_t stream) {
   const int n_slices = (a.c + kPoolCh - 1) / kPoolCh;
-  const size_t smem = size_t(PoolCfg<SETS>::kStages) * kPoolRows * kPoolCh * sizeof(T);
-  auto kernel = mask_pool_kernel<T, OT, SETS>;
+  const size_t smem = size_t(kPoolStages) * kPoolRows * kPoolCh * sizeof(T);
+  auto kernel = mask_pool_kernel<T, OT>;
   static bool configured = false;   // idempotent attribute; a benign race sets it twice
   if (!configured) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -310,20 +433,38 @@ static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
   }
   return check_launch(
       "ufv_mask_pool",
-      launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(PoolCfg<SETS>::kThreads), smem, stream, tmap,
+      launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(kPoolThreads), smem, stream, tmap,
                     use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.cnt, a.grp_row,
                     a.grp_off, a.grp_member, a.grp_nu, a.grp_ulist, a.grp_omask, a.pooled));
+}
+
+template <typename T, int MPW>
+static int launch_pool_sparse(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a, cudaStream_t stream) {
+  const int n_slices = (a.c + kPoolCh - 1) / kPoolCh;
+  const size_t smem = size_t(kPoolStages) * kPoolRows * kPoolCh * sizeof(T);
+  auto kernel = mask_pool_sparse_kernel<T, MPW>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    configured = true;
+  }
+  return check_launch(
+      "ufv_mask_pool (many objects per frame)",
+      launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(kSparseThreads), smem, stream, tmap,
+                    use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.cnt, a.grp_row,
+                    a.grp_off, a.grp_member, a.grp_nu, a.grp_ulist, reinterpret_cast<const uint32_t*>(a.grp_omask),
+                    a.pooled));
 }
 
 template <typename T>
 static int dispatch_group(int max_group, const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
                           cudaStream_t stream) {
-  if (max_group <= 4) return launch_pool<T, 4, 1>(tmap, use_tmap, a, stream);
-  switch (UFV_OMASK_SETS(max_group)) {
-    case 1: return launch_pool<T, 8, 1>(tmap, use_tmap, a, stream);
-    case 2: return launch_pool<T, 8, 2>(tmap, use_tmap, a, stream);
-    case 4: return launch_pool<T, 8, 4>(tmap, use_tmap, a, stream);
-    default: return launch_pool<T, 8, 8>(tmap, use_tmap, a, stream);
+  if (max_group <= 4) return launch_pool<T, 4>(tmap, use_tmap, a, stream);
+  if (max_group <= 8) return launch_pool<T, 8>(tmap, use_tmap, a, stream);
+  switch (UFV_PLAN_MEMBERS(max_group)) {
+    case 16: return launch_pool_sparse<T, 2>(tmap, use_tmap, a, stream);
+    case 32: return launch_pool_sparse<T, 4>(tmap, use_tmap, a, stream);
+    default: return launch_pool_sparse<T, 8>(tmap, use_tmap, a, stream);
   }
 }
 

@@ -58,7 +58,7 @@ def _plan_buffers(plan: packer.EncodePlan, device):
     g = max(plan.n_groups, 1)
     nu = torch.empty((g,), dtype=torch.int32, device=device)
     ulist = torch.empty((g, _cabi.PLAN_PITCH), dtype=torch.int16, device=device)
-    omask = torch.empty((g, _cabi.omask_sets(plan.max_group), _cabi.PLAN_PITCH), dtype=torch.uint8, device=device)
+    omask = torch.empty((g, _cabi.plan_mask_bytes(plan.max_group)), dtype=torch.uint8, device=device)
     return nu, ulist, omask
 
 
@@ -443,7 +443,7 @@ class MaskExtractor(nn.Module):
         sizes = (("bits", q * _cabi.BITS_WORDS * 4), ("cnt", q * 4), ("pooled", q * c * 4), ("gemm_ws", gemm_ws),
                  ("merged", m_pad * c * es), ("hidden", m_pad * hid * es), ("counts", plan.n_obj * 4),
                  ("sims", plan.n_obj * max(plan.max_len, 1) * 4), ("dyn", 256),
-                 ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.omask_sets(plan.max_group) * _cabi.PLAN_PITCH))
+                 ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.plan_mask_bytes(plan.max_group)))
         off, total = {}, 0
         for name, nbytes in sizes:
             off[name] = total

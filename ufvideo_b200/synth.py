@@ -86,7 +86,7 @@ def make_masks(family: str, seed: int, n_obj: int, t: int, h: int, w: int) -> np
 
 def make_clip(clip_id: int, n_frames: int, n_obj: int, family: str = "dense", h: int = 384,
               w: int = 384, row0: int = 0, c: int = C_SIGLIP, n_patch: int = N_PATCH,
-              ragged: bool = False):
+              ragged: bool = False, feats: bool = True):
     """One clip: (feats [n_frames, n_patch, c] fp32, masks uint8 [q, h, w], ann_indices_of_clip).
 
     Every object is annotated on every frame unless ``ragged``, where object o keeps a random
@@ -94,7 +94,7 @@ def make_clip(clip_id: int, n_frames: int, n_obj: int, family: str = "dense", h:
     feature row (the collator's cumulative offset, train.py:689-692).
     """
     seed = CLIP_SEED0 + clip_id
-    feats = features(seed, n_frames, n_patch, c)
+    feats = features(seed, n_frames, n_patch, c) if feats else None     # feats=False: masks and indices only
     g = rng_for(seed * 7919 + 1)
     if ragged:
         frames = [np.sort(g.choice(n_frames, int(g.integers(1, n_frames + 1)), replace=False))
