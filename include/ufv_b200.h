@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UFV_ABI_VERSION 8
+#define UFV_ABI_VERSION 9
 
 /* element types */
 enum { UFV_F32 = 0, UFV_BF16 = 1, UFV_F16 = 2, UFV_U8 = 3, UFV_RLE = 4 /* masks only */ };
@@ -46,14 +46,6 @@ enum {
 #define UFV_BITS_WORDS 24        /* uint32 words per patch bitmask row (729 bits -> 23, padded) */
 #define UFV_MAX_PATCH_SIDE 27    /* kernels are sized for up to 27 x 27 patches              */
 #define UFV_MAX_GROUP 64         /* object-frames pooled together from one staged frame tile */
-#define UFV_PLAN_PITCH 736       /* entries per group in the union-plan arrays (>= 729, % 16 == 0) */
-/* Per-group member information in the union plan, chosen by the largest group of the call (max_group):
- *   max_group <= 8   UFV_PLAN_PITCH bytes per group: per listed patch the bitmask of members that pool it
- *   max_group  > 8   UFV_PLAN_MEMBERS(max_group) * UFV_BITS_WORDS uint32 per group: per member (padded to 16 /
- *                    32 / 64 members) one bit per listed patch, bit i%32 of word i/32 = the member pools the
- *                    i-th listed patch (so a consumer walks only the rows its member needs) */
-#define UFV_PLAN_MEMBERS(g) ((g) <= 8 ? 8 : (g) <= 16 ? 16 : (g) <= 32 ? 32 : 64)
-#define UFV_PLAN_MASK_BYTES(g) ((g) <= 8 ? UFV_PLAN_PITCH : UFV_PLAN_MEMBERS(g) * UFV_BITS_WORDS * 4)
 
 /* One object-frame's mask plane (32 bytes).  dtype UFV_RLE: a COCO run-length mask -- `addr` points to the
  * int32 cumulative run ends, `pitch` = number of runs, `aux` = image height; pixel p is on iff the first
@@ -65,7 +57,7 @@ typedef struct ufv_mask_desc {
   int32_t pitch;      /* row pitch in elements                                                  */
   int32_t dtype;      /* UFV_U8 (also bool) / UFV_F32 / UFV_BF16 / UFV_F16                      */
   int32_t tap_off;    /* offset of the plane's tap table inside `taps`, in int32 units          */
-  int32_t group;      /* pool group this object-frame belongs to (index into grp_off)           */
+  int32_t group;      /* pool group this object-frame belongs to (informational; kernels do not read it) */
   int32_t flags;      /* bit 0: read in row mode when the tap span fits (see ufv_mask_to_patches) */
   int32_t aux;        /* UFV_RLE: image height h (pixels are numbered column-major, p = x * h + y)  */
 } ufv_mask_desc;
@@ -93,8 +85,7 @@ int ufv_device_address(const void* host_ptr, uint64_t* dev_addr_host);
 int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
 
 /* ---------------------------------------------------------------------------------------------
- * Kernel 1: mask resize + binarise -> patch bitmask, count and index list per object-frame,
- * plus the union plan of every pool group.
+ * Kernel 1: mask resize + binarise -> patch bitmask, count and index list per object-frame.
  * Replaces F.interpolate + (mask > 0) + mask.sum at layer.py:139,143,145.  Bit-exact.
  * Per object-frame the kernel reads in tap mode (every tap gathered individually: lowest latency
  * for masks in HBM) or, when desc.flags bit 0 is set and the tap columns of a row span <= 4 KB,
@@ -110,39 +101,30 @@ int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* taps_host);
  *   cnt_out[n_masks]     number of on patches
  *   idx_out              optional (may be null): [n_masks * idx_pitch] uint16, ascending patch
  *                        indices of the on patches, first cnt entries valid
- *   group plan (all optional together; pass grp_ticket = null to skip): for group g with members
- *   grp_member[grp_off[g] .. grp_off[g+1]) (at most UFV_MAX_GROUP) the kernel writes grp_nu[g] = number of
- *   patches on in any member, grp_ulist[g*UFV_PLAN_PITCH ..] = those patches ascending, and the member
- *   information at grp_omask + g * UFV_PLAN_MASK_BYTES(max_group) in the layout described at
- *   UFV_PLAN_MASK_BYTES (tails zero-filled).  max_group = the largest group size of the call.  grp_ticket[n_groups]
- *   must be zero on entry and is zero again on completion.
  * -------------------------------------------------------------------------------------------*/
 int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
                         int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
-                        const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
-                        int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, int max_group, void* stream);
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 2: segmented mask pool.  Replaces the gather feats[ann_index], the layout permute,
  * the fp32 upcast (layer.py:98-104) and the masked mean (layer.py:145-147).
  *   feats [n_rows, n_patch, c] of feat_dtype (UFV_F32 / UFV_BF16 / UFV_F16), contiguous
+ *   bits / cnt: patch bitmasks and on-counts of all object-frames, from ufv_mask_to_patches
  *   groups: group g pools object-frames grp_member[grp_off[g] .. grp_off[g+1]) (at most
  *           UFV_MAX_GROUP of them), all of which read feature row grp_row[g] -- the row is streamed ONCE
- *           for the whole group.  Up to 8 members: every staged row is added into the members whose mask bit
- *           is set (warp-uniform predicates).  9 .. 64 members: each consumer warp owns a few members and
- *           walks only the staged rows its members pool (bit iteration over the member words).
- *           max_group = the largest group size in this call (selects the kernel variant and the plan
- *           layout); grp_nu / grp_ulist / grp_omask = the union plan written by ufv_mask_to_patches with
- *           the same max_group
- *   cnt[n_masks] on-patch counts from ufv_mask_to_patches
+ *           for the whole group, in windows of 32 consecutive patches: the kernel ORs the members'
+ *           bitmasks, skips windows nobody needs, fetches mostly-needed windows as one 2-D tile and
+ *           sparse ones row by row.  Up to 8 members: every staged row is added into the members whose
+ *           bit is set (warp-uniform predicates).  9 .. 64 members: each consumer warp owns a few members
+ *           and walks only the rows its members pool.
+ *           max_group = the largest group size in this call (selects the kernel variant)
  *   pooled_out fp32 [n_masks, c]:  sum over on patches in ascending patch order, divided by
  *           (float(cnt) + 1e-8f); an all-off mask gives an exact zero row.
  * -------------------------------------------------------------------------------------------*/
 int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, int n_patch, int c,
-                  const int32_t* cnt, const int32_t* grp_row, const int32_t* grp_off,
-                  const int32_t* grp_member, const int32_t* grp_nu, const uint16_t* grp_ulist,
-                  const uint8_t* grp_omask, int n_groups, int max_group, float* pooled_out,
-                  void* stream);
+                  const uint32_t* bits, const int32_t* cnt, const int32_t* grp_row, const int32_t* grp_off,
+                  const int32_t* grp_member, int n_groups, int max_group, float* pooled_out, void* stream);
 
 /* Adjoint of ufv_mask_pool w.r.t. the features (training; the reference gets it from autograd through
  * layer.py:98-104,145-147).  w fp32 [n_masks, c] = d_pooled / (cnt + 1e-8); the object-frames that pool
@@ -253,7 +235,6 @@ typedef struct ufv_encode_args {
   const ufv_mask_desc* mask_desc; const int32_t* taps; int32_t n_masks; int32_t idx_pitch;
   int32_t any_row_mode; int32_t reserved1;
   uint32_t* bits; int32_t* cnt; uint16_t* idx;            /* idx optional */
-  uint32_t* grp_ticket; int32_t* grp_nu; uint16_t* grp_ulist; uint8_t* grp_omask;
   /* pool */
   const int32_t* grp_row; const int32_t* grp_off; const int32_t* grp_member; int32_t n_groups;
   int32_t max_group;

@@ -20,16 +20,7 @@ UFV_F32, UFV_BF16, UFV_F16, UFV_U8, UFV_RLE = 0, 1, 2, 3, 4
 BITS_WORDS = 24
 MAX_PATCH_SIDE = 27
 MAX_GROUP = 64
-PLAN_PITCH = 736
-ABI_VERSION = 8
-
-def plan_mask_bytes(max_group: int) -> int:
-    """UFV_PLAN_MASK_BYTES of include/ufv_b200.h: bytes of member information per group in the union plan."""
-    if max_group <= 8:
-        return PLAN_PITCH
-    members = 16 if max_group <= 16 else 32 if max_group <= 32 else 64
-    return members * BITS_WORDS * 4
-
+ABI_VERSION = 9
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -56,7 +47,6 @@ class EncodeArgs(C.Structure):
         ("mask_desc", _p), ("taps", _p), ("n_masks", _i32), ("idx_pitch", _i32),
         ("any_row_mode", _i32), ("reserved1", _i32),
         ("bits", _p), ("cnt", _p), ("idx", _p),
-        ("grp_ticket", _p), ("grp_nu", _p), ("grp_ulist", _p), ("grp_omask", _p),
         ("grp_row", _p), ("grp_off", _p), ("grp_member", _p), ("n_groups", _i32),
         ("max_group", _i32),
         ("pooled", _p),
@@ -86,10 +76,8 @@ _SIGNATURES = {
     "ufv_struct_size": (C.c_int, [C.c_char_p]),
     "ufv_device_address": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "ufv_tap_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
-    "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p,
-                                      _p, _p, C.c_int, _p]),
-    "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_int,
-                                C.c_int, _p, _p]),
+    "ufv_mask_to_patches": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p]),
+    "ufv_mask_pool": (C.c_int, [_p, C.c_int, _i64, C.c_int, C.c_int, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]),
     "ufv_mask_pool_backward": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p]),
     "ufv_ttm": (C.c_int, [_p, C.c_int, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p,
                           _p, C.c_int, _p, C.c_int, _p, _i32, _p]),

@@ -10,8 +10,6 @@ namespace ufv {
 
 int launch_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out, int any_row_mode,
                            uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
-                           const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
-                           int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, int max_group,
                            const ufv_dyn_args* dyn_src, ufv_dyn_args* dyn_dev, void* stream);
 int ttm_dispatch(const float* pooled, int c, const int32_t* obj_start, const int32_t* obj_len,
                  const int32_t* slot_off, int n_obj, int max_len, int k_keep, void* tokens_out,
@@ -239,13 +237,11 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
     UFV_REQUIRE(a->n_masks > 0 && a->n_obj > 0 && a->m_pad > 0, UFV_E_SHAPE,
                 "ufv_encode: graph-replay mode needs a non-empty batch");
   int rc = launch_mask_to_patches(a->mask_desc, a->taps, a->n_masks, side, a->any_row_mode, a->bits, a->cnt, a->idx,
-                                  a->idx_pitch, a->grp_off, a->grp_member, a->grp_ticket, a->grp_nu, a->grp_ulist,
-                                  a->grp_omask, a->max_group, dyn_mode ? a->dyn_src : nullptr,
-                                  dyn_mode ? a->dyn_dev : nullptr, stream);
+                                  a->idx_pitch, dyn_mode ? a->dyn_src : nullptr, dyn_mode ? a->dyn_dev : nullptr,
+                                  stream);
   if (rc != 0) return rc;
-  rc = ufv_mask_pool(a->feats, a->feat_dtype, a->n_rows, side * side, a->c, a->cnt, a->grp_row, a->grp_off,
-                     a->grp_member, a->grp_nu, a->grp_ulist, a->grp_omask, a->n_groups, a->max_group,
-                     a->pooled, stream);
+  rc = ufv_mask_pool(a->feats, a->feat_dtype, a->n_rows, side * side, a->c, a->bits, a->cnt, a->grp_row, a->grp_off,
+                     a->grp_member, a->n_groups, a->max_group, a->pooled, stream);
   if (rc != 0) return rc;
   rc = ttm_dispatch(a->pooled, a->c, a->obj_start, a->obj_len, a->slot_off, a->n_obj, a->max_len, a->k_keep,
                     a->merged, a->feat_dtype, nullptr, a->counts, nullptr, 0, a->sims, a->sims_pitch,

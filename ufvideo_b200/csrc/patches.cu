@@ -7,9 +7,8 @@
 // "interp > 0" is the OR of the (at most four) taps whose weight is non-zero: integer-exact,
 // and only 4 * n_out^2 mask elements are read instead of H * W.
 //
-// One CTA per object-frame.  The CTA that finishes a group last (atomic ticket) also builds the
-// group's plan: the ascending list of patches that are on in ANY member mask (only those feature
-// rows are ever fetched by kernel 2) and, per listed patch, the bitmask of members that pool it.
+// One CTA per object-frame.  (Round 1 also built a per-frame "union plan" here, by whichever CTA of a frame
+// finished last; the pool kernel now derives what it needs from the bitmasks itself, per 32-patch window.)
 #include "common.cuh"
 
 #include <cmath>
@@ -237,19 +236,13 @@ __global__ void __launch_bounds__(PatchCfg<ROWS>::kThreads, PatchCfg<ROWS>::kMin
 mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __restrict__ taps, int n_out,
                        uint32_t* __restrict__ bits_out, int32_t* __restrict__ cnt_out,
                        uint16_t* __restrict__ idx_out, int idx_pitch,
-                       const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member,
-                       uint32_t* __restrict__ grp_ticket, int32_t* __restrict__ grp_nu,
-                       uint16_t* __restrict__ grp_ulist, uint8_t* __restrict__ grp_omask, int plan_members,
                        const uint32_t* __restrict__ dyn_src, uint32_t* __restrict__ dyn_dev) {
   __shared__ int32_t s_taps[4 * UFV_MAX_PATCH_SIDE];
   __shared__ uint32_t s_words[UFV_BITS_WORDS];
   __shared__ int32_t s_prefix[UFV_BITS_WORDS + 1];
-  __shared__ uint32_t s_member_bits[UFV_MAX_GROUP][UFV_BITS_WORDS];
-  __shared__ uint16_t s_ulist[UFV_PLAN_PITCH];
   constexpr int kPatchThreads = PatchCfg<ROWS>::kThreads;
   __shared__ uint16_t s_flags[PatchCfg<ROWS>::kFlagRows][PatchCfg<ROWS>::kFlagCols];
   __shared__ int s_span[2];
-  __shared__ int s_last;
 
   const int j = blockIdx.x;
   const int tid = threadIdx.x;
@@ -386,75 +379,6 @@ mask_to_patches_kernel(const ufv_mask_desc* __restrict__ desc, const int32_t* __
     }
   }
   if (dyn_copy) dyn_dev[tid] = dyn_word;
-  if (grp_ticket == nullptr) return;
-
-  // ---- group plan, built by whichever member CTA arrives last ---------------------------------------
-  const int g = d.group;
-  const int m0 = grp_off[g];
-  const int n_mem = grp_off[g + 1] - m0;
-  __threadfence();                      // publish this CTA's bits before taking a ticket
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&grp_ticket[g], 1u) == uint32_t(n_mem - 1));
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = tid; i < max(n_mem, 8) * UFV_BITS_WORDS; i += kPatchThreads) {
-    const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
-    s_member_bits[o][w] = o < n_mem ? __ldcg(bits_out + size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w) : 0u;
-  }
-  __syncthreads();
-  if (tid < UFV_BITS_WORDS) {
-    uint32_t u = 0;
-    for (int o = 0; o < n_mem; ++o) u |= s_member_bits[o][tid];
-    s_words[tid] = u;
-  }
-  __syncthreads();
-  word_prefix(s_words, s_prefix, tid);
-  __syncthreads();
-  const int n_u = s_prefix[UFV_BITS_WORDS];
-  uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
-  const bool member_words = plan_members > 8;      // many members: one bit row per member instead of a byte per patch
-  uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
-  for (int p = tid; p < UFV_PLAN_PITCH; p += kPatchThreads) {
-    const int w = p >> 5;
-    const uint32_t bit = 1u << (p & 31);
-    const uint32_t u = w < UFV_BITS_WORDS ? s_words[w] : 0u;
-    if (u & bit) {
-      const int pos = s_prefix[w] + __popc(u & (bit - 1u));
-      ulist[pos] = static_cast<uint16_t>(p);
-      s_ulist[pos] = static_cast<uint16_t>(p);
-      if (!member_words) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) m |= ((s_member_bits[o][w] >> (p & 31)) & 1u) << o;   // rows past n_mem are zero
-        omask[pos] = static_cast<uint8_t>(m);
-      }
-    }
-    if (p >= n_u) {                     // tail: no member pools these slots
-      ulist[p] = 0;
-      if (!member_words) omask[p] = 0;
-    }
-  }
-  if (member_words) {
-    // word k of member o: bit b = member o pools the (32 k + b)-th listed patch.  One ballot per (chunk, member).
-    __syncthreads();
-    uint32_t* mwords = reinterpret_cast<uint32_t*>(grp_omask) + size_t(g) * plan_members * UFV_BITS_WORDS;
-    constexpr int kWarps = kPatchThreads / 32;
-    for (int k = warp; k < UFV_BITS_WORDS; k += kWarps) {
-      const int i = 32 * k + lane;
-      const bool valid = i < n_u;
-      const int patch = valid ? int(s_ulist[i]) : 0;
-      for (int o = 0; o < plan_members; ++o) {
-        const bool on = valid && o < n_mem && ((s_member_bits[o][patch >> 5] >> (patch & 31)) & 1u);
-        const uint32_t word = __ballot_sync(0xffffffffu, on);
-        if (lane == 0) mwords[size_t(o) * UFV_BITS_WORDS + k] = word;
-      }
-    }
-  }
-  if (tid == 0) {
-    grp_nu[g] = n_u;
-    grp_ticket[g] = 0u;                 // self-reset: the ticket buffer is reusable by the next call
-  }
 }
 
 }  // namespace ufv
@@ -482,8 +406,6 @@ extern "C" int ufv_tap_table(int h, int w, int n_out, int pad_square, int32_t* t
 namespace ufv {
 int launch_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out, int any_row_mode,
                            uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out, int idx_pitch,
-                           const int32_t* grp_off, const int32_t* grp_member, uint32_t* grp_ticket,
-                           int32_t* grp_nu, uint16_t* grp_ulist, uint8_t* grp_omask, int max_group,
                            const ufv_dyn_args* dyn_src, ufv_dyn_args* dyn_dev, void* stream) {
   UFV_REQUIRE(n_masks >= 0 && n_out >= 1 && n_out <= UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
               "ufv_mask_to_patches: n_masks=%d n_out=%d out of range", n_masks, n_out);
@@ -491,30 +413,19 @@ int launch_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n
   UFV_REQUIRE(desc && taps && bits_out && cnt_out, UFV_E_NULL, "ufv_mask_to_patches: null pointer");
   UFV_REQUIRE(idx_out == nullptr || idx_pitch >= n_out * n_out, UFV_E_SHAPE,
               "ufv_mask_to_patches: idx_pitch %d < %d", idx_pitch, n_out * n_out);
-  if (grp_ticket != nullptr) {
-    UFV_REQUIRE(grp_off && grp_member && grp_nu && grp_ulist && grp_omask, UFV_E_NULL,
-                "ufv_mask_to_patches: group plan requested but a plan pointer is null");
-    UFV_REQUIRE(max_group >= 1 && max_group <= UFV_MAX_GROUP, UFV_E_SHAPE,
-                "ufv_mask_to_patches: max_group=%d not in [1, %d]", max_group, UFV_MAX_GROUP);
-  }
-  const int plan_members = UFV_PLAN_MEMBERS(max_group);
   auto kernel = any_row_mode ? ufv::mask_to_patches_kernel<true> : ufv::mask_to_patches_kernel<false>;
   const int threads = any_row_mode ? ufv::PatchCfg<true>::kThreads : ufv::PatchCfg<false>::kThreads;
   return ufv::check_launch(
       "ufv_mask_to_patches",
       ufv::launch_kernel(kernel, dim3(n_masks), dim3(threads), 0, static_cast<cudaStream_t>(stream), desc,
-                         taps, n_out, bits_out, cnt_out, idx_out, idx_pitch, grp_off, grp_member, grp_ticket,
-                         grp_nu, grp_ulist, grp_omask, plan_members, reinterpret_cast<const uint32_t*>(dyn_src),
-                         reinterpret_cast<uint32_t*>(dyn_dev)));
+                         taps, n_out, bits_out, cnt_out, idx_out, idx_pitch,
+                         reinterpret_cast<const uint32_t*>(dyn_src), reinterpret_cast<uint32_t*>(dyn_dev)));
 }
 }  // namespace ufv
 
 extern "C" int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_masks, int n_out,
                                    int any_row_mode, uint32_t* bits_out, int32_t* cnt_out, uint16_t* idx_out,
-                                   int idx_pitch, const int32_t* grp_off, const int32_t* grp_member,
-                                   uint32_t* grp_ticket, int32_t* grp_nu, uint16_t* grp_ulist,
-                                   uint8_t* grp_omask, int max_group, void* stream) {
+                                   int idx_pitch, void* stream) {
   return ufv::launch_mask_to_patches(desc, taps, n_masks, n_out, any_row_mode, bits_out, cnt_out, idx_out, idx_pitch,
-                                     grp_off, grp_member, grp_ticket, grp_nu, grp_ulist, grp_omask, max_group, nullptr,
-                                     nullptr, stream);
+                                     nullptr, nullptr, stream);
 }

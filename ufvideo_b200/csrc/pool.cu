@@ -7,18 +7,21 @@
 // and shared by every object on that frame.
 //
 // Work item = (group, 128-channel slice).  A group is one feature row (frame) plus up to 64
-// object-frames pooled from it; its plan (ascending union patch list + member information) was written
-// by kernel 1.  The producer warp reads the plan and streams the slice of every listed patch row through
-// a ring of shared-memory stages with the TMA engine -- one 2-D tiled tensor-map load when the stage's
-// rows are consecutive patches, otherwise one 1-D bulk copy per row (off patches are never fetched).  The
-// row is fetched ONCE however many objects pool from it.  Two consumer designs:
+// object-frames pooled from it.  The frame's 729 patch rows are walked in WINDOWS of 32 consecutive
+// patches.  Every CTA first ORs its members' patch bitmasks (kernel 1's output, 96 bytes each) into the
+// frame's union; then the producer warp moves, per non-empty window, the slice of the needed rows into a
+// ring of shared-memory stages with the TMA engine: ONE 2-D tiled tensor-map load of all 32 rows when most
+// of the window is needed (a single request; the few unneeded rows ride along), otherwise one 1-D bulk
+// copy per needed row (measured: 256-byte row copies stream at ~3.4 TB/s, 32-row tiles at ~5.4 TB/s).
+// Windows no member needs are skipped entirely.  The row is fetched ONCE however many objects pool from it.
+// Two consumer designs:
 //   mask_pool_kernel         (<= 8 members)  two consumer warps, 64 channels each, 2 per lane.  Every staged row
 //            is added, in ascending patch order, into the fp32 accumulators of the members whose bit is set
 //            (warp-uniform predicates, packed f32x2 adds).  Best when most members pool most rows.  (A single
 //            consumer warp with 4 channels per lane needs fewer instructions but measured slower: 43.6 vs
 //            41.3 us on c2, 133 vs 89 us with 8 objects per frame -- two warps hide each other's latencies.)
 //   mask_pool_sparse_kernel  (9 .. 64 members)  eight consumer warps, each owning a few members and all 128
-//            channels (4 per lane): a warp walks the set bits of its member's 32-row stage word and adds only
+//            channels (4 per lane): a warp walks the set bits of its member's window word and adds only
 //            those rows.  With 16 - 64 objects on a frame a row is pooled by a small fraction of them, and
 //            the predicated design spends its issue slots on adds that are switched off (measured on c4,
 //            16 blobs per frame: 306 us predicated in one pass, 263 us re-streaming the frame per 8 members).
@@ -26,6 +29,7 @@
 // of any blocking, which is what oracle/restatement.py::mask_pool restates bit-for-bit.
 //
 // Roofline: HBM.  Algorithmic bytes per group = n_union_patches * C * sizeof(feat).
+// kTileMin: a full window whose union has at least this many rows is fetched as one tile.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -50,6 +54,27 @@ constexpr int kPoolConsumers = 2;             // dense kernel: consumer warps, 6
 constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
 constexpr int kSparseConsumers = 8;           // sparse kernel: consumer warps, 128 channels each, members interleaved
 constexpr int kSparseThreads = 32 * (kSparseConsumers + 1);
+static_assert(kPoolRows == 32, "a window is one 32-bit word of the patch bitmasks");
+
+// Per non-empty window: the producer warp's part, shared by both kernels.  `u` = union word of the window
+// (bit r = patch 32 * win + r is needed by some member).  Returns after the copies have been issued.
+template <typename T>
+__device__ __forceinline__ void produce_window(const CUtensorMap* tmap, int use_tmap, const T* __restrict__ feats,
+                                               int64_t row_base, int c, int ch0, uint32_t slice_bytes, int win,
+                                               int n_patch, uint32_t u, int tile_min, T* dst, uint64_t* full_bar,
+                                               int lane) {
+  const bool full = 32 * win + 32 <= n_patch;
+  const bool tile = use_tmap && full && __popc(u) >= tile_min;
+  if (lane == 0) {
+    mbar_arrive_expect_tx(full_bar, tile ? uint32_t(kPoolRows) * kPoolCh * sizeof(T) : uint32_t(__popc(u)) * slice_bytes);
+    if (tile) tma_load_2d(dst, tmap, ch0, int(row_base + 32 * win), full_bar);
+  }
+  if (!tile) {
+    __syncwarp();
+    if ((u >> lane) & 1u)
+      bulk_g2s(dst + lane * kPoolCh, feats + (row_base + 32 * win + lane) * int64_t(c) + ch0, slice_bytes, full_bar);
+  }
+}
 
 __device__ __forceinline__ void add2(float2& acc, float2 v) {
   unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
@@ -76,15 +101,16 @@ template <> struct Pair<__half> {
 template <typename T, int OT>
 __global__ void __launch_bounds__(kPoolThreads)
 mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
-                 int n_patch, int c, int n_slices, const int32_t* __restrict__ cnt,
-                 const int32_t* __restrict__ grp_row, const int32_t* __restrict__ grp_off,
-                 const int32_t* __restrict__ grp_member, const int32_t* __restrict__ grp_nu,
-                 const uint16_t* __restrict__ grp_ulist, const uint8_t* __restrict__ grp_omask,
+                 int n_patch, int c, int n_slices, const uint32_t* __restrict__ bits,
+                 const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,
+                 const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member, int tile_min,
                  float* __restrict__ pooled) {
   constexpr int S = kPoolStages, R = kPoolRows;
   using Raw = typename Pair<T>::Raw;
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
+  __shared__ uint32_t s_bits[8][UFV_BITS_WORDS];                           // members' patch bitmasks
+  __shared__ uint32_t s_union[UFV_BITS_WORDS];
   __shared__ __align__(16) uint8_t s_omask[S][R];                          // member masks of the staged rows
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t empty_bar[S];
@@ -105,48 +131,47 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     mbar_fence_init();
     if (use_tmap) tma_prefetch_desc(&tmap);
   }
+  // the group's extent is plan data (uploaded before kernel 1 ran): fetched while kernel 1 drains
+  const int m0 = grp_off[g];
+  const int n_mem = grp_off[g + 1] - m0;
+  const int row = grp_row[g];
   __syncthreads();
-  pdl_wait();                  // the union plan and counts come from kernel 1
+  pdl_wait();                  // patch bitmasks and counts come from kernel 1
   pdl_launch_dependents();
-  // every plan word this CTA needs is requested at once: one L2 round trip, not a dependent chain
-  const uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
-  int my_patch = 0, row = 0;
-  if (warp == kPoolConsumers) {
-    if (lane < R) my_patch = int(ulist[lane]);             // plan tail is zero-padded: always in bounds
-    row = grp_row[g];
+  for (int i = tid; i < 8 * UFV_BITS_WORDS; i += kPoolThreads) {
+    const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
+    s_bits[o][w] = o < n_mem ? bits[size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w] : 0u;
   }
-  const int n_u = grp_nu[g];
-  const int n_chunks = (n_u + R - 1) / R;
+  __syncthreads();
+  if (tid < UFV_BITS_WORDS) {
+    uint32_t u = 0;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) u |= s_bits[o][tid];
+    s_union[tid] = u;
+  }
+  __syncthreads();
+  const int n_win = (n_patch + R - 1) / R;
   const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == kPoolConsumers) {
-    // ---------------- producer warp: plan -> TMA engine -> shared-memory ring ------------------
-    const uint8_t* omask = grp_omask + size_t(g) * UFV_PLAN_PITCH;
+    // ---------------- producer warp: windows -> TMA engine -> shared-memory ring ------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    for (int it = 0; it < n_chunks; ++it) {
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
-      const int patch = my_patch;
-      if (it + 1 < n_chunks && lane < R) my_patch = int(ulist[(it + 1) * R + lane]);   // prefetch
-      const int rows = min(R, n_u - it * R);
-      const int first = __shfl_sync(0xffffffffu, patch, 0);
-      const int last = __shfl_sync(0xffffffffu, patch, rows - 1);
-      const bool tile = use_tmap && rows == R && (last - first == R - 1);
-      T* dst = ring + size_t(s) * R * kPoolCh;
+    int k = 0;                                                 // stages used so far (non-empty windows)
+    for (int win = 0; win < n_win; ++win) {
+      const uint32_t u = s_union[win];
+      if (u == 0u) continue;                                   // no member needs any row of this window
+      const int s = k % S;
+      const uint32_t ph = (k / S) & 1;
+      ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      if (lane == 0) {
-        const uint32_t data_bytes = tile ? uint32_t(R) * kPoolCh * sizeof(T) : uint32_t(rows) * slice_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], data_bytes + R);
-        bulk_g2s(&s_omask[s][0], omask + it * R, R, &full_bar[s]);
-        if (tile) tma_load_2d(dst, &tmap, ch0, int(row_base + first), &full_bar[s]);
-      }
-      if (!tile) {
-        __syncwarp();
-        if (lane < rows)
-          bulk_g2s(dst + lane * kPoolCh, feats + (row_base + patch) * int64_t(c) + ch0, slice_bytes,
-                   &full_bar[s]);
-      }
+      uint32_t m = 0;                                          // lane r: which members pool patch 32 win + r
+#pragma unroll
+      for (int o = 0; o < 8; ++o) m |= ((s_bits[o][win] >> lane) & 1u) << o;
+      s_omask[s][lane] = static_cast<uint8_t>(m);
+      __syncwarp();                                            // the masks precede lane 0's (releasing) arrive
+      produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
+                        ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
     }
   } else {
     // ---------------- consumer warps: ascending-patch accumulation ---------------------------------
@@ -156,8 +181,6 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     const int my_ch = warp * (kPoolCh / kPoolConsumers) + lane * 2;      // within the slice
     const bool live = my_ch < slice_ch;
     // output rows and denominators: requested now, needed only after the last stage
-    const int m0 = grp_off[g];
-    const int n_mem = grp_off[g + 1] - m0;
     int out_row[OT];
     float denorm[OT];
 #pragma unroll
@@ -165,9 +188,12 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       out_row[o] = o < n_mem ? grp_member[m0 + o] : -1;
       denorm[o] = out_row[o] >= 0 ? __fadd_rn(float(cnt[out_row[o]]), 1e-8f) : 1.0f;   // layer.py:145
     }
-    for (int it = 0; it < n_chunks; ++it) {
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
+    int k = 0;
+    for (int win = 0; win < n_win; ++win) {
+      if (s_union[win] == 0u) continue;
+      const int s = k % S;
+      const uint32_t ph = (k / S) & 1;
+      ++k;
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
       uint32_t mk[R / 4];
@@ -175,12 +201,12 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
 #pragma unroll
       for (int i = 0; i < R / 4; ++i) mk[i] = reinterpret_cast<const uint32_t*>(&s_omask[s][0])[i];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);
+      for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);   // unneeded rows: stale bytes, mask 0
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);   // stage is in registers: hand it back early
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;   // rows past n_u carry mask 0
+        const uint32_t m = (mk[r >> 2] >> (8 * (r & 3))) & 0xffu;
         const float2 f = Pair<T>::cvt(v[r]);
 #pragma unroll
         for (int o = 0; o < OT; ++o)
@@ -230,16 +256,15 @@ template <> struct Quad<__half> {
 template <typename T, int MPW>
 __global__ void __launch_bounds__(kSparseThreads)
 mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
-                        int n_patch, int c, int n_slices, const int32_t* __restrict__ cnt,
-                        const int32_t* __restrict__ grp_row, const int32_t* __restrict__ grp_off,
-                        const int32_t* __restrict__ grp_member, const int32_t* __restrict__ grp_nu,
-                        const uint16_t* __restrict__ grp_ulist, const uint32_t* __restrict__ grp_mwords,
+                        int n_patch, int c, int n_slices, const uint32_t* __restrict__ bits,
+                        const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,
+                        const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member, int tile_min,
                         float* __restrict__ pooled) {
   constexpr int S = kPoolStages, R = kPoolRows, NW = kSparseConsumers, PM = MPW * NW;
-  static_assert(R == 32, "one member word covers one stage");
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
-  __shared__ uint32_t s_mw[PM][UFV_BITS_WORDS];                            // member words of this group
+  __shared__ uint32_t s_bits[PM][UFV_BITS_WORDS];                          // members' patch bitmasks
+  __shared__ uint32_t s_union[UFV_BITS_WORDS];
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t empty_bar[S];
 
@@ -259,51 +284,40 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     mbar_fence_init();
     if (use_tmap) tma_prefetch_desc(&tmap);
   }
-  __syncthreads();
-  pdl_wait();                  // the union plan and counts come from kernel 1
-  pdl_launch_dependents();
-  const uint16_t* ulist = grp_ulist + size_t(g) * UFV_PLAN_PITCH;
-  int my_patch = 0, row = 0;
-  if (warp == NW) {
-    if (lane < R) my_patch = int(ulist[lane]);
-    row = grp_row[g];
-  }
-  const int n_u = grp_nu[g];
-  const int n_chunks = (n_u + R - 1) / R;
-  const int slice_ch = min(kPoolCh, c - ch0);
   const int m0 = grp_off[g];
   const int n_mem = grp_off[g + 1] - m0;
-  {
-    const uint32_t* src = grp_mwords + size_t(g) * PM * UFV_BITS_WORDS;
-    for (int i = tid; i < PM * UFV_BITS_WORDS; i += kSparseThreads)
-      (&s_mw[0][0])[i] = i / UFV_BITS_WORDS < n_mem ? src[i] : 0u;
+  const int row = grp_row[g];
+  __syncthreads();
+  pdl_wait();                  // patch bitmasks and counts come from kernel 1
+  pdl_launch_dependents();
+  for (int i = tid; i < PM * UFV_BITS_WORDS; i += kSparseThreads) {
+    const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
+    s_bits[o][w] = o < n_mem ? bits[size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w] : 0u;
   }
   __syncthreads();
+  if (tid < UFV_BITS_WORDS) {
+    uint32_t u = 0;
+    for (int o = 0; o < PM; ++o) u |= s_bits[o][tid];
+    s_union[tid] = u;
+  }
+  __syncthreads();
+  const int n_win = (n_patch + R - 1) / R;
+  const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == NW) {
-    // ---------------- producer warp (as in the dense kernel, without member masks) ----------------
+    // ---------------- producer warp ---------------------------------------------------------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    for (int it = 0; it < n_chunks; ++it) {
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
-      const int patch = my_patch;
-      if (it + 1 < n_chunks && lane < R) my_patch = int(ulist[(it + 1) * R + lane]);
-      const int rows = min(R, n_u - it * R);
-      const int first = __shfl_sync(0xffffffffu, patch, 0);
-      const int last = __shfl_sync(0xffffffffu, patch, rows - 1);
-      const bool tile = use_tmap && rows == R && (last - first == R - 1);
-      T* dst = ring + size_t(s) * R * kPoolCh;
+    int k = 0;
+    for (int win = 0; win < n_win; ++win) {
+      const uint32_t u = s_union[win];
+      if (u == 0u) continue;
+      const int s = k % S;
+      const uint32_t ph = (k / S) & 1;
+      ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&full_bar[s], tile ? uint32_t(R) * kPoolCh * sizeof(T) : uint32_t(rows) * slice_bytes);
-        if (tile) tma_load_2d(dst, &tmap, ch0, int(row_base + first), &full_bar[s]);
-      }
-      if (!tile) {
-        __syncwarp();
-        if (lane < rows)
-          bulk_g2s(dst + lane * kPoolCh, feats + (row_base + patch) * int64_t(c) + ch0, slice_bytes, &full_bar[s]);
-      }
+      produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
+                        ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
     }
   } else {
     // ---------------- consumer warps: members warp, warp + 8, ..., all 128 channels, 4 per lane -------------
@@ -312,14 +326,17 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     for (int mi = 0; mi < MPW; ++mi) acc[mi] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int my_ch = lane * 4;
     const bool live = my_ch < slice_ch;
-    for (int it = 0; it < n_chunks; ++it) {
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
+    int k = 0;
+    for (int win = 0; win < n_win; ++win) {
+      if (s_union[win] == 0u) continue;
+      const int s = k % S;
+      const uint32_t ph = (k / S) & 1;
+      ++k;
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
 #pragma unroll
       for (int mi = 0; mi < MPW; ++mi) {
-        uint32_t word = s_mw[mi * NW + warp][it];            // warp-uniform
+        uint32_t word = s_bits[mi * NW + warp][win];         // warp-uniform: the rows of this window the member pools
         while (word != 0u) {
           const int r = __ffs(word) - 1;
           word &= word - 1u;
@@ -416,9 +433,8 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t r
 }
 
 struct PoolArgs {
-  const void* feats; int n_patch; int c; const int32_t* cnt; const int32_t* grp_row; const int32_t* grp_off;
-  const int32_t* grp_member; const int32_t* grp_nu; const uint16_t* grp_ulist; const uint8_t* grp_omask;
-  int n_groups; float* pooled;
+  const void* feats; int n_patch; int c; const uint32_t* bits; const int32_t* cnt; const int32_t* grp_row;
+  const int32_t* grp_off; const int32_t* grp_member; int n_groups; int tile_min; float* pooled;
 };
 
 template <typename T, int OT>
@@ -434,8 +450,8 @@ static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
   return check_launch(
       "ufv_mask_pool",
       launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(kPoolThreads), smem, stream, tmap,
-                    use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.cnt, a.grp_row,
-                    a.grp_off, a.grp_member, a.grp_nu, a.grp_ulist, a.grp_omask, a.pooled));
+                    use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.bits, a.cnt, a.grp_row,
+                    a.grp_off, a.grp_member, a.tile_min, a.pooled));
 }
 
 template <typename T, int MPW>
@@ -451,9 +467,8 @@ static int launch_pool_sparse(const CUtensorMap& tmap, int use_tmap, const PoolA
   return check_launch(
       "ufv_mask_pool (many objects per frame)",
       launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(kSparseThreads), smem, stream, tmap,
-                    use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.cnt, a.grp_row,
-                    a.grp_off, a.grp_member, a.grp_nu, a.grp_ulist, reinterpret_cast<const uint32_t*>(a.grp_omask),
-                    a.pooled));
+                    use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.bits, a.cnt, a.grp_row,
+                    a.grp_off, a.grp_member, a.tile_min, a.pooled));
 }
 
 template <typename T>
@@ -461,11 +476,9 @@ static int dispatch_group(int max_group, const CUtensorMap& tmap, int use_tmap, 
                           cudaStream_t stream) {
   if (max_group <= 4) return launch_pool<T, 4>(tmap, use_tmap, a, stream);
   if (max_group <= 8) return launch_pool<T, 8>(tmap, use_tmap, a, stream);
-  switch (UFV_PLAN_MEMBERS(max_group)) {
-    case 16: return launch_pool_sparse<T, 2>(tmap, use_tmap, a, stream);
-    case 32: return launch_pool_sparse<T, 4>(tmap, use_tmap, a, stream);
-    default: return launch_pool_sparse<T, 8>(tmap, use_tmap, a, stream);
-  }
+  if (max_group <= 16) return launch_pool_sparse<T, 2>(tmap, use_tmap, a, stream);
+  if (max_group <= 32) return launch_pool_sparse<T, 4>(tmap, use_tmap, a, stream);
+  return launch_pool_sparse<T, 8>(tmap, use_tmap, a, stream);
 }
 
 // ---- adjoint of the mask pool (training) --------------------------------------------
@@ -592,15 +605,14 @@ extern "C" int ufv_mask_pool_backward(const float* w, const uint32_t* bits, cons
 }
 
 extern "C" int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, int n_patch, int c,
-                             const int32_t* cnt, const int32_t* grp_row, const int32_t* grp_off,
-                             const int32_t* grp_member, const int32_t* grp_nu, const uint16_t* grp_ulist,
-                             const uint8_t* grp_omask, int n_groups, int max_group, float* pooled_out,
-                             void* stream) {
+                             const uint32_t* bits, const int32_t* cnt, const int32_t* grp_row,
+                             const int32_t* grp_off, const int32_t* grp_member, int n_groups, int max_group,
+                             float* pooled_out, void* stream) {
   using namespace ufv;
   UFV_REQUIRE(n_groups >= 0 && n_rows >= 0, UFV_E_SHAPE, "ufv_mask_pool: negative size");
   if (n_groups == 0) return 0;
-  UFV_REQUIRE(feats && cnt && grp_row && grp_off && grp_member && grp_nu && grp_ulist && grp_omask &&
-                  pooled_out, UFV_E_NULL, "ufv_mask_pool: null pointer");
+  UFV_REQUIRE(feats && bits && cnt && grp_row && grp_off && grp_member && pooled_out, UFV_E_NULL,
+              "ufv_mask_pool: null pointer");
   UFV_REQUIRE(n_patch >= 1 && n_patch <= UFV_MAX_PATCH_SIDE * UFV_MAX_PATCH_SIDE, UFV_E_SHAPE,
               "ufv_mask_pool: n_patch=%d out of range", n_patch);
   UFV_REQUIRE(max_group >= 1 && max_group <= UFV_MAX_GROUP, UFV_E_SHAPE,
@@ -608,8 +620,8 @@ extern "C" int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, 
   UFV_REQUIRE(feat_dtype == UFV_F32 || feat_dtype == UFV_BF16 || feat_dtype == UFV_F16, UFV_E_DTYPE,
               "ufv_mask_pool: unsupported feature dtype %d", feat_dtype);
   UFV_REQUIRE(c >= 8 && c % 8 == 0, UFV_E_SHAPE, "ufv_mask_pool: c=%d must be a multiple of 8", c);
-  UFV_REQUIRE(aligned16(feats) && aligned16(pooled_out) && aligned16(grp_omask) && aligned16(grp_ulist),
-              UFV_E_ALIGN, "ufv_mask_pool: feats / pooled_out / plan buffers must be 16-byte aligned");
+  UFV_REQUIRE(aligned16(feats) && aligned16(pooled_out), UFV_E_ALIGN,
+              "ufv_mask_pool: feats / pooled_out must be 16-byte aligned");
   UFV_REQUIRE(n_rows * n_patch < (int64_t(1) << 31), UFV_E_SHAPE,
               "ufv_mask_pool: n_rows * n_patch exceeds 2^31");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -617,9 +629,13 @@ extern "C" int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, 
   int rc = make_tensor_map_2d(&tmap, feats, feat_dtype, uint64_t(n_rows) * n_patch, uint64_t(c), kPoolRows,
                               kPoolCh, 0);
   if (rc != 0) return rc;
-  static const int use_tile = getenv("UFV_POOL_NO_TILE") == nullptr;   // developer knob (sweeps)
-  const PoolArgs a{feats, n_patch, c, cnt, grp_row, grp_off, grp_member, grp_nu, grp_ulist, grp_omask,
-                   n_groups, pooled_out};
+  static const int use_tile = getenv("UFV_POOL_NO_TILE") == nullptr;   // developer knobs (sweeps)
+  static const int tile_min = [] {
+    const char* e = getenv("UFV_POOL_TILE_MIN");
+    const int v = e ? atoi(e) : 20;
+    return v < 1 ? 1 : v > 33 ? 33 : v;
+  }();
+  const PoolArgs a{feats, n_patch, c, bits, cnt, grp_row, grp_off, grp_member, n_groups, tile_min, pooled_out};
   switch (feat_dtype) {
     case UFV_F32:
       return dispatch_group<float>(max_group, tmap, use_tile, a, st);

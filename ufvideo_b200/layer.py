@@ -53,29 +53,17 @@ def _feat_dtype(t: torch.Tensor) -> int:
 # ------------------------------------------------------------------------------------------------
 # stage-level operators (each one C-ABI call); the parity tests drive these directly
 # ------------------------------------------------------------------------------------------------
-def _plan_buffers(plan: packer.EncodePlan, device):
-    """Device buffers of the per-group union plan written by kernel 1 and read by kernel 2."""
-    g = max(plan.n_groups, 1)
-    nu = torch.empty((g,), dtype=torch.int32, device=device)
-    ulist = torch.empty((g, _cabi.PLAN_PITCH), dtype=torch.int16, device=device)
-    omask = torch.empty((g, _cabi.plan_mask_bytes(plan.max_group)), dtype=torch.uint8, device=device)
-    return nu, ulist, omask
-
-
 def mask_to_patches(plan: packer.EncodePlan, device, n_out: int = 27, want_idx: bool = False):
-    """Kernel 1.  Returns a dict: bits int32 [q, 24], cnt int32 [q], idx int16 [q, 736] | None and
-    the group plan (grp_nu, grp_ulist, grp_omask)."""
+    """Kernel 1.  Returns a dict: bits int32 [q, 24], cnt int32 [q], idx int16 [q, 736] | None."""
     q = plan.n_masks
     bits = torch.empty((q, _cabi.BITS_WORDS), dtype=torch.int32, device=device)
     cnt = torch.empty((q,), dtype=torch.int32, device=device)
     idx = torch.zeros((q, 736), dtype=torch.int16, device=device) if want_idx else None
-    nu, ulist, omask = _plan_buffers(plan, device)
     d = plan.dev
     _cabi.check(_cabi.lib().ufv_mask_to_patches(
         d["mask_desc"], d["taps"], q, n_out, plan.any_row_mode, bits.data_ptr(), cnt.data_ptr(),
-        idx.data_ptr() if want_idx else None, 736, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
-        nu.data_ptr(), ulist.data_ptr(), omask.data_ptr(), plan.max_group, _stream_ptr(device)))
-    return {"bits": bits, "cnt": cnt, "idx": idx, "grp_nu": nu, "grp_ulist": ulist, "grp_omask": omask}
+        idx.data_ptr() if want_idx else None, 736, _stream_ptr(device)))
+    return {"bits": bits, "cnt": cnt, "idx": idx}
 
 
 def mask_pool(feats: torch.Tensor, plan: packer.EncodePlan, patches: dict):
@@ -85,9 +73,8 @@ def mask_pool(feats: torch.Tensor, plan: packer.EncodePlan, patches: dict):
     pooled = torch.empty((plan.n_masks, c), dtype=torch.float32, device=feats.device)
     d = plan.dev
     _cabi.check(_cabi.lib().ufv_mask_pool(
-        feats.data_ptr(), _feat_dtype(feats), f, n_patch, c, patches["cnt"].data_ptr(),
-        d["grp_row"], d["grp_off"], d["grp_member"], patches["grp_nu"].data_ptr(),
-        patches["grp_ulist"].data_ptr(), patches["grp_omask"].data_ptr(), plan.n_groups, plan.max_group,
+        feats.data_ptr(), _feat_dtype(feats), f, n_patch, c, patches["bits"].data_ptr(), patches["cnt"].data_ptr(),
+        d["grp_row"], d["grp_off"], d["grp_member"], plan.n_groups, plan.max_group,
         pooled.data_ptr(), _stream_ptr(feats.device)))
     return pooled
 
@@ -408,13 +395,10 @@ class MaskExtractor(nn.Module):
                 _cabi.check(lib.ufv_encode(run["args_ref"], stream))
         else:                                     # other depths: the same kernels, staged
             _cabi.check(lib.ufv_mask_to_patches(d["mask_desc"], d["taps"], q, side, plan.any_row_mode,
-                                                ptr["bits"], ptr["cnt"],
-                                                None, 0, d["grp_off"], d["grp_member"], plan.ticket.data_ptr(),
-                                                ptr["grp_nu"], ptr["grp_ulist"], ptr["grp_omask"], plan.max_group,
-                                                stream))
-            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, side * side, c, ptr["cnt"], d["grp_row"],
-                                          d["grp_off"], d["grp_member"], ptr["grp_nu"], ptr["grp_ulist"],
-                                          ptr["grp_omask"], plan.n_groups, plan.max_group, ptr["pooled"], stream))
+                                                ptr["bits"], ptr["cnt"], None, 0, stream))
+            _cabi.check(lib.ufv_mask_pool(feats.data_ptr(), dt, f, side * side, c, ptr["bits"], ptr["cnt"], d["grp_row"],
+                                          d["grp_off"], d["grp_member"], plan.n_groups, plan.max_group,
+                                          ptr["pooled"], stream))
             _cabi.check(lib.ufv_ttm(ptr["pooled"], c, d["obj_start"], d["obj_len"], d["slot_off"],
                                     plan.n_obj, plan.max_len, k_keep, ptr["merged"], dt, None,
                                     ptr["counts"], None, 0, ptr["sims"], max(plan.max_len, 1), None, 0, stream))
@@ -434,7 +418,7 @@ class MaskExtractor(nn.Module):
     def _prepare_run(self, plan, sig, feats, linears, side, k_keep, device):
         """Workspace + argument struct of one (plan, pointers, stream) combination."""
         _, dt, f, c, hid, stream, two, _ = sig
-        q, m_pad, g = plan.n_masks, plan.m_pad, max(plan.n_groups, 1)
+        q, m_pad = plan.n_masks, plan.m_pad
         es = feats.element_size()
         # one workspace allocation, carved into 256-byte aligned pieces
         lib = _cabi.lib()
@@ -442,8 +426,7 @@ class MaskExtractor(nn.Module):
             if two and m_pad else 0
         sizes = (("bits", q * _cabi.BITS_WORDS * 4), ("cnt", q * 4), ("pooled", q * c * 4), ("gemm_ws", gemm_ws),
                  ("merged", m_pad * c * es), ("hidden", m_pad * hid * es), ("counts", plan.n_obj * 4),
-                 ("sims", plan.n_obj * max(plan.max_len, 1) * 4), ("dyn", 256),
-                 ("grp_nu", g * 4), ("grp_ulist", g * _cabi.PLAN_PITCH * 2), ("grp_omask", g * _cabi.plan_mask_bytes(plan.max_group)))
+                 ("sims", plan.n_obj * max(plan.max_len, 1) * 4), ("dyn", 256))
         off, total = {}, 0
         for name, nbytes in sizes:
             off[name] = total
@@ -469,8 +452,7 @@ class MaskExtractor(nn.Module):
                 feats=feats.data_ptr(), feat_dtype=dt, n_patch_side=side, n_rows=f, c=c, hid=hid,
                 mask_desc=d["mask_desc"], taps=d["taps"], n_masks=q, idx_pitch=0,
                 any_row_mode=plan.any_row_mode, bits=ptr["bits"],
-                cnt=ptr["cnt"], idx=None, grp_ticket=plan.ticket.data_ptr(), grp_nu=ptr["grp_nu"],
-                grp_ulist=ptr["grp_ulist"], grp_omask=ptr["grp_omask"], grp_row=d["grp_row"],
+                cnt=ptr["cnt"], idx=None, grp_row=d["grp_row"],
                 grp_off=d["grp_off"], grp_member=d["grp_member"], n_groups=plan.n_groups,
                 max_group=plan.max_group, pooled=ptr["pooled"], obj_start=d["obj_start"],
                 obj_len=d["obj_len"], slot_off=d["slot_off"], n_obj=plan.n_obj, max_len=plan.max_len,

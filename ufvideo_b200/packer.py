@@ -86,7 +86,6 @@ class EncodePlan:
     host: dict = field(default_factory=dict)      # name -> numpy array
     dev: dict = field(default_factory=dict)       # name -> device pointer (int)
     buffer: torch.Tensor | None = None            # owns the device memory behind ``dev``
-    ticket: torch.Tensor | None = None            # zeroed per-group arrival counters (self-resetting)
     sample_of: np.ndarray | None = None           # int32 [q] sample each object-frame came from
     plane_off: np.ndarray | None = None           # int64 [q] byte offset of its plane in that sample
     base_ptrs: tuple = ()                         # mask tensor base addresses baked into ``buffer``
@@ -395,7 +394,6 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
                       sample_of=cat(sample_of, np.int32), plane_off=cat(plane_off, np.int64),
                       expect_counts=[int(s) for s in slots], slots_bytes=slots.tobytes(),
                       any_row_mode=any_row_mode, rle_rows=rle_rows)
-    plan.ticket = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)   # self-resetting
     _fill_addresses(plan, ptrs)
     _upload(plan, device)
     return plan
