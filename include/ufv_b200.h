@@ -172,6 +172,12 @@ int ufv_ttm(const float* pooled, int c, const int32_t* obj_start, const int32_t*
 int64_t ufv_linear_ws_bytes(int m, int n, int k, int dtype);
 int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
                int dtype, int gelu, void* ws, int64_t ws_bytes, void* stream);
+/* Same, with a scatter epilogue: output row r is stored as row row_map[r] of y (row pitch n elements), or
+ * dropped when row_map[r] < 0.  row_map int32 [m] on the device; null = identity.  This is how the last Linear
+ * of the projector writes the object tokens straight into the caller's inputs_embeds at their <region>
+ * positions (videorefer_arch.py:300-311), with no tokens tensor and no copy in between. */
+int ufv_linear_scatter(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+                       int dtype, int gelu, const int32_t* row_map, void* ws, int64_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 4 fused with the result-collection all-gather (multi-GPU, clips sharded over ranks).
@@ -253,6 +259,9 @@ typedef struct ufv_encode_args {
   void* hidden; void* tokens_out;
   /* scratch of the split-K Linears (ufv_linear): max over the two layers of ufv_linear_ws_bytes; may be null */
   void* gemm_ws; int64_t gemm_ws_bytes;
+  /* optional scatter epilogue of the last Linear (ufv_linear_scatter): int32 [m_pad] on the device, row r of
+   * the padded tokens is stored as row tokens_row_map[r] of tokens_out (< 0: dropped).  Ignored with `peer`. */
+  const int32_t* tokens_row_map;
   /* optional: fuse the result-collection all-gather into the last Linear (ufv_linear_gather);
    * tokens_out is then unused */
   const ufv_peer_args* peer;
@@ -295,6 +304,16 @@ int ufv_compact_rows(const void* in, const int32_t* slot_off, const int32_t* cou
 int ufv_splice_rows(const void* text, int n_text, const int32_t* region_pos, const void* tokens,
                     const int32_t* slot_off, const int32_t* counts, int n_obj, int m_pad, void* out,
                     int32_t* out_len, int32_t* row_src, int row_bytes, void* stream);
+
+/* <region> splice with batch padding and labels for a layout known on the host (the reference's
+ * prepare_inputs_labels_for_multimodal, videorefer_arch.py:291-368, for the batch [B, L_max] flattened to
+ * n_out_rows = B * L_max rows).  src_map[i] >= 0: output row i is text row src_map[i] (embedding copied, label
+ * labels_in[src_map[i]], attention 1); -1: padding (zero embedding, label ignore_index, attention 0); -2: a
+ * region-token row -- its embedding is written by ufv_linear_scatter / ufv_encode (tokens_row_map), here it
+ * only gets label ignore_index and attention 1.  labels_in / labels_out / attn_out are optional (null). */
+int ufv_splice_static(const void* text, const int64_t* labels_in, const int32_t* src_map, void* out,
+                      int64_t* labels_out, uint8_t* attn_out, int n_out_rows, int row_bytes,
+                      int64_t ignore_index, void* stream);
 
 /* Gather rows: out[i, :] = in[row_map[i], :], `row_bytes` per row (multiple of 16). */
 int ufv_gather_rows(const void* in, const int32_t* row_map, void* out, int n_out_rows,

@@ -665,6 +665,78 @@ def test_region_splice_matches_the_reference_consumer_loop(dev):
     assert (src[:2] == [0, 1]).all() and src[2] == -1 and src[-1] == n_text - 1
 
 
+def reference_consumer(text, labels, seq_lens, region_pos, tokens, nums, ignore=-100):
+    """The region part of the reference's prepare_inputs_labels_for_multimodal restated with torch cats
+    (videorefer_arch.py:291-368): per sample, text pieces and object tokens concatenated at the <region>
+    placeholders (a sample without one still advances the object cursor, :263-264), IGNORE labels on token rows,
+    then zero / IGNORE / False padding to the longest sample."""
+    embeds, labs, off, row, obj = [], [], 0, 0, 0
+    for n, pos in zip(seq_lens, region_pos):
+        if not pos:
+            embeds.append(text[off:off + n])
+            labs.append(labels[off:off + n])
+            row += nums[obj]
+            obj += 1
+        else:
+            e, l, last = [], [], 0
+            for p_ in pos:
+                e += [text[off + last:off + p_], tokens[row:row + nums[obj]]]
+                l += [labels[off + last:off + p_], torch.full((nums[obj],), ignore, dtype=labels.dtype, device=labels.device)]
+                row += nums[obj]
+                obj += 1
+                last = p_ + 1
+            e.append(text[off + last:off + n])
+            l.append(labels[off + last:off + n])
+            embeds.append(torch.cat(e))
+            labs.append(torch.cat(l))
+        off += n
+    l_max = max(x.shape[0] for x in embeds)
+    out = torch.zeros((len(embeds), l_max, text.shape[1]), dtype=text.dtype, device=text.device)
+    lab = torch.full((len(embeds), l_max), ignore, dtype=labels.dtype, device=labels.device)
+    att = torch.zeros((len(embeds), l_max), dtype=torch.bool, device=text.device)
+    for i, (e, l) in enumerate(zip(embeds, labs)):
+        out[i, :e.shape[0]], lab[i, :l.shape[0]], att[i, :e.shape[0]] = e, l, True
+    return out, lab, att
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("case", ["ragged", "equal", "ties"])
+def test_forward_into_builds_the_padded_batch_like_the_reference_consumer(dev, dtype, case):
+    """forward_into (scatter epilogue of the last Linear + ufv_splice_static) against the reference's consumer
+    loop: embeddings, labels and attention mask of the padded batch, including a sample without a placeholder,
+    adjacent placeholders, a placeholder at position 0, repeated calls with new text (graph replay) and an object
+    that ties down to fewer tokens than reserved (slow path)."""
+    k = 4
+    f0, m0, a0 = synth.make_clip(40, 6, 2, "blob", 64, 64, row0=0)
+    f1, m1, a1 = synth.make_clip(41, 1, 1, "blob", 64, 64, row0=6)          # the dummy object of a region-less sample
+    f2, m2, a2 = synth.make_clip(42, 7, 3, "dense", 64, 64, row0=7, ragged=case != "equal")
+    feats = np.concatenate([f0, f1, f2])
+    if case == "ties":
+        feats[0:6] = feats[0]                                                # clip 0: identical frames -> one token per object
+    masks, ann = [m0, m1, m2], [a0, a1, a2]
+    if case == "equal":
+        seq_lens, region_pos = [11, 17, 8], [[1, 4], [], [0, 3, 7]]
+    else:
+        seq_lens, region_pos = [9, 5, 12], [[3, 4], [], [0, 5, 11]]
+    enc = make_encoder(dev, dtype, k)
+    ft = torch.from_numpy(feats).to(dev).to(TORCH_DT[dtype])
+    md = [torch.from_numpy(m).to(dev) for m in masks]
+    tokens, nums = enc(ft, md, None, ann, None)
+    if case == "ties":
+        assert nums[:2] == [1, 1]
+    for rep in range(3):                                                     # from the 2nd call on: replayed graph
+        g = torch.Generator(device="cpu").manual_seed(rep)
+        text = torch.randn((sum(seq_lens), 3584), generator=g).to(dev).to(TORCH_DT[dtype])
+        labels = torch.randint(0, 1000, (sum(seq_lens),), generator=g).to(dev)
+        out, lab, att, got_nums = enc.forward_into(ft, md, ann, text, seq_lens, region_pos, labels=labels)
+        want_out, want_lab, want_att = reference_consumer(text, labels, seq_lens, region_pos, tokens, nums)
+        assert got_nums == nums
+        assert out.shape == want_out.shape and torch.equal(att, want_att) and torch.equal(lab, want_lab)
+        assert torch.equal(out, want_out), (case, rep)
+    if case == "equal":
+        assert att.all()                                                     # same lengths: no padding row anywhere
+
+
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 def test_pool_adjoint_kernel_against_dense_torch(dev, dtype):
     """ufv_mask_pool_backward: rows with <= 8 object-frames (register path), a row with 17 (L1 path) and a

@@ -55,7 +55,7 @@ class EncodeArgs(C.Structure):
         ("merged", _p), ("counts", _p), ("sims", _p), ("sims_pitch", _i32), ("reserved0", _i32),
         ("counts_host", _p), ("epoch", _i32), ("reserved", _i32),
         ("w1", _p), ("b1", _p), ("w2", _p), ("b2", _p),
-        ("hidden", _p), ("tokens_out", _p), ("gemm_ws", _p), ("gemm_ws_bytes", _i64),
+        ("hidden", _p), ("tokens_out", _p), ("gemm_ws", _p), ("gemm_ws_bytes", _i64), ("tokens_row_map", _p),
         ("peer", C.POINTER(PeerArgs)),
         ("dyn_src", _p), ("dyn_dev", _p),
     ]
@@ -83,6 +83,8 @@ _SIGNATURES = {
                           _p, C.c_int, _p, C.c_int, _p, _i32, _p]),
     "ufv_linear_ws_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _i64, _p]),
+    "ufv_linear_scatter": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _i64, _p]),
+    "ufv_splice_static": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _i64, _p]),
     "ufv_linear_gather": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PeerArgs), _p, _i64,
                                     _p]),
     "ufv_wait_flags": (C.c_int, [_p, C.c_int, _i32, C.c_int, _p, _p]),

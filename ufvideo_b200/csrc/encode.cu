@@ -17,7 +17,8 @@ int ttm_dispatch(const float* pooled, int c, const int32_t* obj_start, const int
                  int cut_pitch_words, float* sims_out, int sims_pitch, int32_t* counts_host,
                  int32_t epoch, const ufv_dyn_args* dyn, void* stream);
 int last_linear_dyn(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
-                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes, void* stream);
+                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes,
+                    const int32_t* row_map, void* stream);
 
 static_assert(sizeof(ufv_dyn_args) == 256, "ufv_dyn_args must stay 256 bytes (kernel 1 copies 64 words)");
 
@@ -153,7 +154,50 @@ __global__ void splice_rows_kernel(const uint4* __restrict__ text, int n_text, c
   if (threadIdx.x == 0 && row_src != nullptr) row_src[dst] = tag;
 }
 
+// ---- static <region> splice with batch padding and labels (videorefer_arch.py:291-368) ---------------------
+// The batch's final [B, L_max] layout is known on the host whenever no object ties below its reserved token
+// count (the normal case): src_map[i] says what output row i is -- a text row (>= 0: its index), padding
+// (-1: zero embedding, IGNORE label, attention 0) or a region-token row (-2: the projector's scatter epilogue
+// writes the embedding; label IGNORE, attention 1).  One CTA per output row.
+__global__ void splice_static_kernel(const uint4* __restrict__ text, const int64_t* __restrict__ labels_in,
+                                     const int32_t* __restrict__ src_map, uint4* __restrict__ out,
+                                     int64_t* __restrict__ labels_out, uint8_t* __restrict__ attn_out,
+                                     int vec_per_row, int64_t ignore_index) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int i = blockIdx.x;
+  const int s = src_map[i];
+  if (threadIdx.x == 0) {
+    if (labels_out != nullptr) labels_out[i] = (s >= 0 && labels_in != nullptr) ? labels_in[s] : ignore_index;
+    if (attn_out != nullptr) attn_out[i] = s == -1 ? 0 : 1;
+  }
+  if (s == -2) return;
+  uint4* d = out + size_t(i) * vec_per_row;
+  if (s >= 0) {
+    const uint4* src = text + size_t(s) * vec_per_row;
+    for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) d[v] = src[v];
+  } else {
+    for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) d[v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 }  // namespace ufv
+
+extern "C" int ufv_splice_static(const void* text, const int64_t* labels_in, const int32_t* src_map, void* out,
+                                 int64_t* labels_out, uint8_t* attn_out, int n_out_rows, int row_bytes,
+                                 int64_t ignore_index, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(n_out_rows >= 0 && row_bytes > 0 && row_bytes % 16 == 0, UFV_E_SHAPE,
+              "ufv_splice_static: n_out_rows=%d row_bytes=%d", n_out_rows, row_bytes);
+  if (n_out_rows == 0) return 0;
+  UFV_REQUIRE(src_map && out, UFV_E_NULL, "ufv_splice_static: null pointer");
+  UFV_REQUIRE(aligned16(text) && aligned16(out), UFV_E_ALIGN, "ufv_splice_static: unaligned buffer");
+  return check_launch("ufv_splice_static",
+                      launch_kernel(splice_static_kernel, dim3(n_out_rows), dim3(128), 0,
+                                    static_cast<cudaStream_t>(stream), static_cast<const uint4*>(text), labels_in,
+                                    src_map, static_cast<uint4*>(out), labels_out, attn_out, row_bytes / 16,
+                                    ignore_index));
+}
 
 extern "C" int ufv_abi_version(void) { return UFV_ABI_VERSION; }
 
@@ -256,12 +300,12 @@ extern "C" int ufv_encode(const ufv_encode_args* a, void* stream) {
   if (rc != 0) return rc;
   if (dyn_mode)             // output pointer / all-gather destinations are read from the device block
     return last_linear_dyn(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, dyn,
-                           a->gemm_ws, a->gemm_ws_bytes, stream);
+                           a->gemm_ws, a->gemm_ws_bytes, a->tokens_row_map, stream);
   if (a->peer != nullptr)   // last Linear fused with the all-gather: tiles go straight to every rank
     return ufv_linear_gather(a->hidden, a->w2, a->b2, a->m_pad, a->hid, a->hid, a->feat_dtype, a->peer, a->gemm_ws,
                              a->gemm_ws_bytes, stream);
-  return ufv_linear(a->hidden, a->w2, a->b2, a->tokens_out, a->m_pad, a->hid, a->hid, a->feat_dtype, 0,
-                    a->gemm_ws, a->gemm_ws_bytes, stream);
+  return ufv_linear_scatter(a->hidden, a->w2, a->b2, a->tokens_out, a->m_pad, a->hid, a->hid, a->feat_dtype, 0,
+                            a->tokens_row_map, a->gemm_ws, a->gemm_ws_bytes, stream);
 }
 
 // ---- graph replay ---------------------------------------------------------------------------------------

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k, int tiles_m,
                  int n_tiles, const __grid_constant__ ufv_peer_args peer_param,
-                 const ufv_dyn_args* __restrict__ dyn) {
+                 const ufv_dyn_args* __restrict__ dyn, const int32_t* __restrict__ row_map) {
   using Cfg = GemmCfg<BN, PEER>;
   // fused all-gather: a warp's 32 x 32 sub-tile is turned around in shared memory so that its remote
   // stores are contiguous 64-byte row segments (4 lanes x 16 B) instead of 32 scattered 16-byte
@@ -294,13 +294,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       mbar_wait(&acc_full[acc], aph);
       tc_fence_after_sync();
       const int row = m0 + quarter * 32 + lane;
+      // scatter epilogue (the <region> splice): output row `row` lands in row row_map[row] of y, or nowhere (-1)
+      const int dst_row = (!PEER && row_map != nullptr) ? (row < m ? __ldg(row_map + row) : -1) : row;
 #pragma unroll 1
       for (int col0 = half * 32; col0 < BN; col0 += 64) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * uint32_t(BN) + uint32_t(col0), v);
         tmem_ld_wait();
         const int gcol = n0 + col0;
-        if ((PEER || row < m) && gcol < n) {
+        if ((PEER || (row < m && dst_row >= 0)) && gcol < n) {
           uint32_t packed[16];
           if (gcol + 32 <= n) {
             const uint4* bsrc = reinterpret_cast<const uint4*>(bias + gcol);   // warp-uniform: broadcast
@@ -337,14 +339,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               }
               __syncwarp();
             } else {
-              T* dst = y + size_t(row) * n + gcol;
+              T* dst = y + size_t(dst_row) * n + gcol;
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 reinterpret_cast<uint4*>(dst)[i] =
                     make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
             }
           } else if (!PEER) {            // ragged right edge (n % 32 != 0); the gather variant requires n % 32 == 0
-            T* dst = y + size_t(row) * n + gcol;
+            T* dst = y + size_t(dst_row) * n + gcol;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (gcol + i < n) {
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k,
                      float* __restrict__ slab, const __grid_constant__ ufv_peer_args peer_param,
-                     const ufv_dyn_args* __restrict__ dyn) {
+                     const ufv_dyn_args* __restrict__ dyn, const int32_t* __restrict__ row_map) {
   using Cfg = SplitCfg<BN>;
   __shared__ uint4 s_stage[PEER ? kEpiWarps : 1][PEER ? 32 : 1][5];
   extern __shared__ uint8_t dyn_smem_raw[];
@@ -509,6 +511,7 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   if (n_split > 1) cluster_sync_all();      // every thread of every CTA: partial stores released, then acquired
   if (warp >= 2) {
     const int row = m0 + quarter * 32 + lane;
+    const int dst_row = (!PEER && row_map != nullptr) ? (row < m ? __ldg(row_map + row) : -1) : row;
 #pragma unroll 1
     for (int c = half; c < Cfg::kChunks; c += 2) {
       const int gcol = n0 + c * 32;
@@ -533,7 +536,7 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = s == 0 ? __uint_as_float(v[i]) : __fadd_rn(acc[i], __uint_as_float(v[i]));
       }
-      const bool live_row = PEER || row < m;   // rows past m: nothing to store, but the lane stays in the loop
+      const bool live_row = PEER || (row < m && dst_row >= 0);   // nothing to store: the lane still stays in the loop
       uint32_t packed[16];
       const uint4* bsrc = reinterpret_cast<const uint4*>(bias + gcol);          // n % 32 == 0 on this path
 #pragma unroll
@@ -568,7 +571,7 @@ linear_splitk_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
         __syncwarp();
       } else if (live_row) {
-        T* dst = y + size_t(row) * n + gcol;
+        T* dst = y + size_t(dst_row) * n + gcol;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           reinterpret_cast<uint4*>(dst)[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
@@ -643,7 +646,8 @@ static int sm_count() {
 
 template <typename T, int BN>
 static int launch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                     int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, cudaStream_t stream) {
+                     int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, const int32_t* row_map,
+                     cudaStream_t stream) {
   const int smem_bytes = peer != nullptr ? GemmCfg<BN, true>::kSmem : GemmCfg<BN, false>::kSmem;
   CUtensorMap tx, tw;
   int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
@@ -666,7 +670,7 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
   return check_launch("ufv_linear (tcgen05)",
                       launch_kernel(kernel, grid, dim3(kGemmThreads), smem_bytes, stream, tx, tw,
                                     static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles,
-                                    peer != nullptr ? *peer : no_peer, dyn));
+                                    peer != nullptr ? *peer : no_peer, dyn, row_map));
 }
 
 // N-tile choice.  A launch costs (waves over the SMs) x (time of one tile).  Tile times per 64-deep
@@ -741,7 +745,7 @@ static size_t split_ws_bytes(int m, int n, int k) {
 template <typename T, int BN>
 static int launch_splitk(const void* x, const void* w, const void* bias, void* y, int m, int n, int k, int gelu,
                          int n_split, float* slab, const ufv_peer_args* peer, const ufv_dyn_args* dyn,
-                         cudaStream_t stream) {
+                         const int32_t* row_map, cudaStream_t stream) {
   CUtensorMap tx, tw;
   int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
   if (rc != 0) return rc;
@@ -761,27 +765,28 @@ static int launch_splitk(const void* x, const void* w, const void* bias, void* y
   return check_launch("ufv_linear (tcgen05, split-K cluster)",
                       launch_kernel_cluster(kernel, grid, dim3(kGemmThreads), SplitCfg<BN>::kSmem, stream,
                                             unsigned(n_split), tx, tw, static_cast<const T*>(bias),
-                                            static_cast<T*>(y), m, n, k, slab, peer != nullptr ? *peer : no_peer, dyn));
+                                            static_cast<T*>(y), m, n, k, slab, peer != nullptr ? *peer : no_peer, dyn,
+                                            row_map));
 }
 
 template <typename T>
 static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
                        int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes,
-                       cudaStream_t stream) {
+                       const int32_t* row_map, cudaStream_t stream) {
   const SplitChoice sc = choose_split(m, n, k);
   if (sc.s > 1 && ws != nullptr && size_t(ws_bytes) >= split_ws_bytes(m, n, k)) {
     float* slab = static_cast<float*>(ws);
     switch (sc.bn) {
-      case 256: return launch_splitk<T, 256>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, stream);
-      case 128: return launch_splitk<T, 128>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, stream);
-      default: return launch_splitk<T, 64>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, stream);
+      case 256: return launch_splitk<T, 256>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, row_map, stream);
+      case 128: return launch_splitk<T, 128>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, row_map, stream);
+      default: return launch_splitk<T, 64>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, row_map, stream);
     }
   }
   switch (choose_bn(m, n)) {
-    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
-    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
-    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
-    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, peer, dyn, stream);
+    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
+    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
+    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
+    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
   }
 }
 
@@ -791,7 +796,8 @@ constexpr int kSBM = 32, kSBN = 64, kSBK = 32, kSimtThreads = 256;
 template <bool GELU>
 __global__ void __launch_bounds__(kSimtThreads)
 linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                  const float* __restrict__ bias, float* __restrict__ y, int m, int n, int k) {
+                  const float* __restrict__ bias, float* __restrict__ y, int m, int n, int k,
+                  const int32_t* __restrict__ row_map) {
   __shared__ float sx[kSBK][kSBM + 1];
   __shared__ float sw[kSBK][kSBN + 1];
   const int tid = threadIdx.x;
@@ -828,13 +834,15 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
   for (int i = 0; i < 2; ++i) {
     const int row = m0 + tr * 2 + i;
     if (row >= m) continue;
+    const int dst_row = row_map != nullptr ? row_map[row] : row;      // scatter epilogue (-1: drop the row)
+    if (dst_row < 0) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + tc * 4 + j;
       if (col >= n) continue;
       float v = acc[i][j] + bias[col];
       if (GELU) v = gelu_erf(v);
-      y[size_t(row) * n + col] = v;
+      y[size_t(dst_row) * n + col] = v;
     }
   }
 }
@@ -847,7 +855,8 @@ constexpr int kSkinnyM = 16, kSkinnyCols = 2, kSkinnyWarps = 8;
 template <bool GELU>
 __global__ void __launch_bounds__(32 * kSkinnyWarps)
 linear_f32_skinny_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                         const float* __restrict__ bias, float* __restrict__ y, int m, int n, int k) {
+                         const float* __restrict__ bias, float* __restrict__ y, int m, int n, int k,
+                         const int32_t* __restrict__ row_map) {
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
@@ -881,10 +890,11 @@ linear_f32_skinny_kernel(const float* __restrict__ x, const float* __restrict__ 
         float v = acc[r][c];
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0 && (c == 0 || has2)) {
+        const int dst_row = row_map != nullptr ? row_map[r] : r;
+        if (lane == 0 && (c == 0 || has2) && dst_row >= 0) {
           v += bias[col0 + c];
           if (GELU) v = gelu_erf(v);
-          y[size_t(r) * n + col0 + c] = v;
+          y[size_t(dst_row) * n + col0 + c] = v;
         }
       }
     }
@@ -898,8 +908,9 @@ extern "C" int64_t ufv_linear_ws_bytes(int m, int n, int k, int dtype) {
   return int64_t(ufv::split_ws_bytes(m, n, k));
 }
 
-extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                          int dtype, int gelu, void* ws, int64_t ws_bytes, void* stream) {
+extern "C" int ufv_linear_scatter(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+                                  int dtype, int gelu, const int32_t* row_map, void* ws, int64_t ws_bytes,
+                                  void* stream) {
   using namespace ufv;
   UFV_REQUIRE(ws == nullptr || aligned16(ws), UFV_E_ALIGN, "ufv_linear: ws must be 16-byte aligned");
   UFV_REQUIRE(m >= 0 && n >= 1 && k >= 1, UFV_E_SHAPE, "ufv_linear: m=%d n=%d k=%d", m, n, k);
@@ -914,7 +925,7 @@ extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* 
     return check_launch("ufv_linear (fp32, skinny)",
                         launch_kernel(kernel, dim3((n + cols_per_cta - 1) / cols_per_cta), dim3(32 * kSkinnyWarps), 0,
                                       st, static_cast<const float*>(x), static_cast<const float*>(w),
-                                      static_cast<const float*>(bias), static_cast<float*>(y), m, n, k));
+                                      static_cast<const float*>(bias), static_cast<float*>(y), m, n, k, row_map));
   }
   if (dtype == UFV_F32) {
     const dim3 grid((n + kSBN - 1) / kSBN, (m + kSBM - 1) / kSBM);
@@ -922,25 +933,33 @@ extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* 
     return check_launch("ufv_linear (fp32)",
                         launch_kernel(kernel, grid, dim3(kSimtThreads), 0, st, static_cast<const float*>(x),
                                       static_cast<const float*>(w), static_cast<const float*>(bias),
-                                      static_cast<float*>(y), m, n, k));
+                                      static_cast<float*>(y), m, n, k, row_map));
   }
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "ufv_linear: unsupported dtype %d", dtype);
   UFV_REQUIRE(k % 8 == 0 && n % 8 == 0, UFV_E_SHAPE, "ufv_linear: k=%d and n=%d must be multiples of 8", k, n);
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, ws, ws_bytes, st);
-  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, ws, ws_bytes, st);
+  if (dtype == UFV_BF16)
+    return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, ws, ws_bytes, row_map, st);
+  return dispatch_tc<__half>(x, w, bias, y, m, n, k, gelu, nullptr, nullptr, ws, ws_bytes, row_map, st);
+}
+
+extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
+                          int dtype, int gelu, void* ws, int64_t ws_bytes, void* stream) {
+  return ufv_linear_scatter(x, w, bias, y, m, n, k, dtype, gelu, nullptr, ws, ws_bytes, stream);
 }
 
 namespace ufv {
 // last Linear of the chained path in graph-replay mode (tensor-core dtypes only): the output pointer and,
 // with `peer`, the all-gather destinations are read from the device block `dyn` at run time
 int last_linear_dyn(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
-                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes, void* stream) {
+                    const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes,
+                    const int32_t* row_map, void* stream) {
   UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "graph replay: bf16 / fp16 only (dtype %d)", dtype);
   UFV_REQUIRE(m >= 1 && k % 8 == 0 && n % 32 == 0, UFV_E_SHAPE, "graph replay: m=%d n=%d k=%d", m, n, k);
   UFV_REQUIRE(x && w && bias && dyn && aligned16(x) && aligned16(w), UFV_E_NULL, "graph replay: bad pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, ws, ws_bytes, st);
-  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, ws, ws_bytes, st);
+  if (dtype == UFV_BF16)
+    return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, ws, ws_bytes, row_map, st);
+  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, dyn, ws, ws_bytes, row_map, st);
 }
 }  // namespace ufv
 
@@ -966,8 +985,9 @@ extern "C" int ufv_linear_gather(const void* x, const void* w, const void* bias,
     return check_launch("ufv_linear_gather (empty shard)",
                         launch_kernel(peer_tail_only_kernel, dim3(1), dim3(256), 0, st, *peer));
   UFV_REQUIRE(aligned16(x) && aligned16(w), UFV_E_ALIGN, "ufv_linear_gather: x / w must be 16-byte aligned");
-  if (dtype == UFV_BF16) return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, st);
-  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, st);
+  if (dtype == UFV_BF16)
+    return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, nullptr, st);
+  return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, nullptr, st);
 }
 
 extern "C" int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,

@@ -56,23 +56,68 @@ constexpr int kSparseConsumers = 8;           // sparse kernel: consumer warps, 
 constexpr int kSparseThreads = 32 * (kSparseConsumers + 1);
 static_assert(kPoolRows == 32, "a window is one 32-bit word of the patch bitmasks");
 
-// Per non-empty window: the producer warp's part, shared by both kernels.  `u` = union word of the window
-// (bit r = patch 32 * win + r is needed by some member).  Returns after the copies have been issued.
-template <typename T>
-__device__ __forceinline__ void produce_window(const CUtensorMap* tmap, int use_tmap, const T* __restrict__ feats,
-                                               int64_t row_base, int c, int ch0, uint32_t slice_bytes, int win,
-                                               int n_patch, uint32_t u, int tile_min, T* dst, uint64_t* full_bar,
-                                               int lane) {
-  const bool full = 32 * win + 32 <= n_patch;
-  const bool tile = use_tmap && full && __popc(u) >= tile_min;
-  if (lane == 0) {
-    mbar_arrive_expect_tx(full_bar, tile ? uint32_t(kPoolRows) * kPoolCh * sizeof(T) : uint32_t(__popc(u)) * slice_bytes);
-    if (tile) tma_load_2d(dst, tmap, ch0, int(row_base + 32 * win), full_bar);
+// One ring stage holds a CHUNK of the frame: either one full window that is mostly needed, fetched as a 2-D tile
+// (row r of the window sits in slot r), or a run of consecutive windows whose needed rows -- at most 32 in
+// total -- are copied one by one and packed into slots 0, 1, 2, ... in ascending patch order (a sparse frame
+// of 80 needed rows is 3 stages, not 23).  Producer and consumers derive the same chunks from the union words.
+struct PoolChunk {
+  int w0, w1;      // windows [w0, w1)
+  int rows;        // needed rows in the chunk
+  bool tile;
+};
+
+__device__ __forceinline__ bool window_is_tile(int win, uint32_t u, int n_patch, int use_tmap, int tile_min) {
+  return use_tmap && 32 * win + 32 <= n_patch && __popc(u) >= tile_min;
+}
+
+// advances `win` past the chunk; false when the frame is exhausted
+__device__ __forceinline__ bool next_chunk(const uint32_t* s_union, int n_win, int n_patch, int use_tmap, int tile_min,
+                                           int& win, PoolChunk& ch) {
+  while (win < n_win && s_union[win] == 0u) ++win;
+  if (win >= n_win) return false;
+  const uint32_t u = s_union[win];
+  ch.w0 = win;
+  ch.rows = __popc(u);
+  ch.tile = window_is_tile(win, u, n_patch, use_tmap, tile_min);
+  int e = win + 1;
+  if (!ch.tile) {
+    while (e < n_win) {
+      const uint32_t u2 = s_union[e];
+      if (u2 != 0u) {
+        if (window_is_tile(e, u2, n_patch, use_tmap, tile_min) || ch.rows + __popc(u2) > kPoolRows) break;
+        ch.rows += __popc(u2);
+      }
+      ++e;
+    }
   }
-  if (!tile) {
+  ch.w1 = e;
+  win = e;
+  return true;
+}
+
+// slot of patch (win, r) inside a packed chunk whose earlier windows hold `base` rows
+__device__ __forceinline__ int packed_slot(int base, uint32_t u, int r) { return base + __popc(u & ((1u << r) - 1u)); }
+
+// The producer warp's part for one chunk (the caller has waited for the stage to be empty and, in the dense
+// kernel, written the stage's member masks).  Issues the expect-tx arrive, then the copies.
+template <typename T>
+__device__ __forceinline__ void produce_chunk(const CUtensorMap* tmap, const T* __restrict__ feats, int64_t row_base,
+                                              int c, int ch0, uint32_t slice_bytes, const PoolChunk& ch,
+                                              const uint32_t* s_union, T* dst, uint64_t* full_bar, int lane) {
+  if (lane == 0) {
+    mbar_arrive_expect_tx(full_bar, ch.tile ? uint32_t(kPoolRows) * kPoolCh * sizeof(T) : uint32_t(ch.rows) * slice_bytes);
+    if (ch.tile) tma_load_2d(dst, tmap, ch0, int(row_base + 32 * ch.w0), full_bar);
+  }
+  if (!ch.tile) {
     __syncwarp();
-    if ((u >> lane) & 1u)
-      bulk_g2s(dst + lane * kPoolCh, feats + (row_base + 32 * win + lane) * int64_t(c) + ch0, slice_bytes, full_bar);
+    int base = 0;
+    for (int w = ch.w0; w < ch.w1; ++w) {
+      const uint32_t u = s_union[w];
+      if ((u >> lane) & 1u)
+        bulk_g2s(dst + packed_slot(base, u, lane) * kPoolCh, feats + (row_base + 32 * w + lane) * int64_t(c) + ch0,
+                 slice_bytes, full_bar);
+      base += __popc(u);
+    }
   }
 }
 
@@ -157,21 +202,37 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     // ---------------- producer warp: windows -> TMA engine -> shared-memory ring ------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    int k = 0;                                                 // stages used so far (non-empty windows)
-    for (int win = 0; win < n_win; ++win) {
-      const uint32_t u = s_union[win];
-      if (u == 0u) continue;                                   // no member needs any row of this window
+    int k = 0, win = 0;                                        // stages used so far, next window
+    PoolChunk ch;
+    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
       ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      uint32_t m = 0;                                          // lane r: which members pool patch 32 win + r
+      // member masks of the stage's slots: which of the <= 8 members pool the patch sitting in slot i
+      if (ch.tile) {
+        uint32_t m = 0;
 #pragma unroll
-      for (int o = 0; o < 8; ++o) m |= ((s_bits[o][win] >> lane) & 1u) << o;
-      s_omask[s][lane] = static_cast<uint8_t>(m);
+        for (int o = 0; o < 8; ++o) m |= ((s_bits[o][ch.w0] >> lane) & 1u) << o;
+        s_omask[s][lane] = static_cast<uint8_t>(m);
+      } else {
+        s_omask[s][lane] = 0;
+        __syncwarp();
+        int base = 0;
+        for (int w = ch.w0; w < ch.w1; ++w) {
+          const uint32_t u = s_union[w];
+          if ((u >> lane) & 1u) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) m |= ((s_bits[o][w] >> lane) & 1u) << o;
+            s_omask[s][packed_slot(base, u, lane)] = static_cast<uint8_t>(m);
+          }
+          base += __popc(u);
+        }
+      }
       __syncwarp();                                            // the masks precede lane 0's (releasing) arrive
-      produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
-                        ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
+      produce_chunk<T>(&tmap, feats, row_base, c, ch0, slice_bytes, ch, s_union, ring + size_t(s) * R * kPoolCh,
+                       &full_bar[s], lane);
     }
   } else {
     // ---------------- consumer warps: ascending-patch accumulation ---------------------------------
@@ -188,9 +249,9 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       out_row[o] = o < n_mem ? grp_member[m0 + o] : -1;
       denorm[o] = out_row[o] >= 0 ? __fadd_rn(float(cnt[out_row[o]]), 1e-8f) : 1.0f;   // layer.py:145
     }
-    int k = 0;
-    for (int win = 0; win < n_win; ++win) {
-      if (s_union[win] == 0u) continue;
+    int k = 0, win = 0;
+    PoolChunk ch;
+    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
       ++k;
@@ -201,7 +262,7 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
 #pragma unroll
       for (int i = 0; i < R / 4; ++i) mk[i] = reinterpret_cast<const uint32_t*>(&s_omask[s][0])[i];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);   // unneeded rows: stale bytes, mask 0
+      for (int r = 0; r < R; ++r) v[r] = *reinterpret_cast<const Raw*>(src + r * kPoolCh);   // unused slots: stale bytes, mask 0
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);   // stage is in registers: hand it back early
 #pragma unroll
@@ -308,16 +369,15 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     // ---------------- producer warp ---------------------------------------------------------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    int k = 0;
-    for (int win = 0; win < n_win; ++win) {
-      const uint32_t u = s_union[win];
-      if (u == 0u) continue;
+    int k = 0, win = 0;
+    PoolChunk ch;
+    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
       ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
-                        ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
+      produce_chunk<T>(&tmap, feats, row_base, c, ch0, slice_bytes, ch, s_union, ring + size_t(s) * R * kPoolCh,
+                       &full_bar[s], lane);
     }
   } else {
     // ---------------- consumer warps: members warp, warp + 8, ..., all 128 channels, 4 per lane -------------
@@ -326,26 +386,33 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     for (int mi = 0; mi < MPW; ++mi) acc[mi] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int my_ch = lane * 4;
     const bool live = my_ch < slice_ch;
-    int k = 0;
-    for (int win = 0; win < n_win; ++win) {
-      if (s_union[win] == 0u) continue;
+    int k = 0, win = 0;
+    PoolChunk ch;
+    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
       ++k;
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
+      int base = 0;
+      for (int w = ch.w0; w < ch.w1; ++w) {
+        const uint32_t u = s_union[w];
+        if (u == 0u) continue;
 #pragma unroll
-      for (int mi = 0; mi < MPW; ++mi) {
-        uint32_t word = s_bits[mi * NW + warp][win];         // warp-uniform: the rows of this window the member pools
-        while (word != 0u) {
-          const int r = __ffs(word) - 1;
-          word &= word - 1u;
-          const float4 f = Quad<T>::load(src + r * kPoolCh);
-          float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
-          add2(lo, make_float2(f.x, f.y));
-          add2(hi, make_float2(f.z, f.w));
-          acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        for (int mi = 0; mi < MPW; ++mi) {
+          uint32_t word = s_bits[mi * NW + warp][w];         // warp-uniform: the rows of this window the member pools
+          while (word != 0u) {
+            const int r = __ffs(word) - 1;
+            word &= word - 1u;
+            const int slot = ch.tile ? r : packed_slot(base, u, r);
+            const float4 f = Quad<T>::load(src + slot * kPoolCh);
+            float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
+            add2(lo, make_float2(f.x, f.y));
+            add2(hi, make_float2(f.z, f.w));
+            acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
         }
+        base += __popc(u);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);

@@ -179,6 +179,65 @@ def splice_regions(text_embeds: torch.Tensor, region_pos: torch.Tensor, tokens: 
     return out, out_len, row_src
 
 
+class RegionLayout:
+    """Where every row of the reference's ``new_input_embeds`` comes from (videorefer_arch.py:291-368), for a
+    batch whose objects keep their reserved token counts (``slots`` = min(T_o, K): true unless the merge ties).
+
+    seq_lens[i]    rows of sample i's embedded sequence (mm tokens already expanded by the caller)
+    region_pos[i]  ascending local positions of its ``<region>`` placeholders; objects are consumed in order
+                   over the batch.  A sample WITHOUT a placeholder still consumes one object whose tokens are
+                   dropped -- the reference advances its region cursor by one there (videorefer_arch.py:263-264,
+                   :300-305; that object is the dummy mask the collator adds).
+    Built on the host with numpy: new_lens, l_max, src_map int32 [B * l_max] (text row index, -1 padding,
+    -2 region token) and token_row_map int32 [m_pad] (destination row of every padded token row, -1 dropped)."""
+
+    def __init__(self, seq_lens, region_pos, slots):
+        seq_lens = [int(n) for n in seq_lens]
+        slots = np.asarray(slots, dtype=np.int64)
+        slot_off = np.concatenate([[0], np.cumsum(slots)])
+        b = len(seq_lens)
+        if len(region_pos) != b:
+            raise ValueError("region_pos and seq_lens disagree on the number of samples")
+        text_off = np.concatenate([[0], np.cumsum(seq_lens)])
+        rows, obj = [], 0
+        for i in range(b):
+            pos = [int(p) for p in region_pos[i]]
+            if any(p < 0 or p >= seq_lens[i] for p in pos) or pos != sorted(set(pos)):
+                raise ValueError(f"sample {i}: region positions must be ascending indices into its sequence")
+            if not pos:                                   # no placeholder: one object consumed, nothing inserted
+                if obj >= slots.size:
+                    raise ValueError("fewer objects than the samples consume")
+                rows.append((np.arange(seq_lens[i]) + text_off[i], [], [obj]))
+                obj += 1
+                continue
+            if obj + len(pos) > slots.size:
+                raise ValueError("fewer objects than <region> placeholders")
+            seq, ins = [], []
+            last = 0
+            for p in pos:
+                seq.append(np.arange(last, p) + text_off[i])
+                seq.append(np.full(int(slots[obj]), -2, dtype=np.int64))
+                ins.append((obj, sum(len(x) for x in seq) - int(slots[obj])))      # (object, local start of its tokens)
+                obj += 1
+                last = p + 1
+            seq.append(np.arange(last, seq_lens[i]) + text_off[i])
+            rows.append((np.concatenate(seq), ins, []))
+        if obj != slots.size:
+            raise ValueError(f"{slots.size} objects but the samples consume {obj}")
+        self.new_lens = [int(r[0].size) for r in rows]
+        self.l_max = max(self.new_lens) if rows else 0
+        self.batch = b
+        src = np.full((b, self.l_max), -1, dtype=np.int32)
+        tok = np.full(int(slot_off[-1]), -1, dtype=np.int32)
+        for i, (seq, ins, _dropped) in enumerate(rows):
+            src[i, :seq.size] = seq
+            for o, start in ins:
+                tok[slot_off[o]:slot_off[o + 1]] = i * self.l_max + start + np.arange(int(slots[o]))
+        self.src_map = src.reshape(-1)
+        self.token_row_map = tok
+        self.n_text = int(text_off[-1])
+
+
 # ------------------------------------------------------------------------------------------------
 # reference-named API
 # ------------------------------------------------------------------------------------------------
@@ -251,7 +310,8 @@ class MaskExtractor(nn.Module):
             self.__dict__["_lin_cache"] = cached
         return cached[2]
 
-    def encode_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None, _awaited=False):
+    def encode_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None, _awaited=False,
+                      scatter=None):
         """Kernels 1-4 without the host read-back: returns (tokens [m_pad, hid], counts int32
         [n_obj] on the device, plan).  Row r of an object is valid iff r < counts[object].
         ``out`` / ``counts_out`` let the projector and the merge kernel write straight into caller
@@ -333,7 +393,13 @@ class MaskExtractor(nn.Module):
         plan.run = self._last_run = run
         if peer is not None and not two:
             raise ValueError("peer gather needs the depth-2 projector path")
-        if out is None:
+        if scatter is not None:
+            # scatter epilogue: the last Linear stores token row r as row row_map[r] of the caller's buffer
+            # (``scatter`` = (buffer [rows, hid], int32 row map [m_pad] on the device)); validated by the caller
+            if not two or peer is not None or out is not None:
+                raise ValueError("scatter needs the depth-2 projector path and excludes out= / peer=")
+            tokens = scatter[0]
+        elif out is None:
             tokens = run.pop("spare_out", None)   # allocated while the previous call waited for its counts
             if tokens is None or tokens.dtype != feats.dtype:
                 tokens = torch.empty((m_pad, hid), dtype=feats.dtype, device=device)
@@ -362,14 +428,16 @@ class MaskExtractor(nn.Module):
         if two:                                   # the reference's depth=2 projector: one chained call
             epoch = run["epoch"] = run["epoch"] % 32767 + 1        # 1 .. 32767, the tag of this call's counts
             graph = None
+            row_map_ptr = scatter[1].data_ptr() if scatter is not None else None
             if _awaited and USE_CUDA_GRAPH and dt != _cabi.UFV_F32 and q > 0 and plan.n_obj > 0 and m_pad > 0:
                 # A caller that waits for the counts before its next call (forward, forward_padded) lets
                 # the launch sequence be replayed as a CUDA graph: the per-call values travel through the
                 # pinned block (kernel 1 forwards it to the device), everything else is constant.
                 run["awaited_calls"] += 1
-                graph = run["graphs"].get(peer is not None)
+                gkey = (peer is not None, row_map_ptr)           # the row map is a kernel parameter of the capture
+                graph = run["graphs"].get(gkey)
                 if graph is None and run["awaited_calls"] >= 2:
-                    graph = self._capture_graph(run, peer)
+                    graph = self._capture_graph(run, peer, row_map_ptr)
             if graph is not None:
                 dyn = run["dyn"]
                 dyn.tokens_out = tokens.data_ptr()
@@ -383,6 +451,7 @@ class MaskExtractor(nn.Module):
             else:
                 a = run["args"]
                 a.tokens_out = tokens.data_ptr()
+                a.tokens_row_map = row_map_ptr
                 a.counts = ptr["counts"] if counts_out is None else counts_out.data_ptr()
                 if peer is None:
                     a.peer = None
@@ -473,17 +542,20 @@ class MaskExtractor(nn.Module):
             run["dyn_src_addr"] = packer._device_address(pinned)
         return run
 
-    def _capture_graph(self, run, peer):
+    def _capture_graph(self, run, peer, row_map_ptr=None):
         """Capture the launch sequence of this run once (include/ufv_b200.h: ufv_encode_graph_create)."""
         a = run["args"]
         g = _cabi.EncodeArgs.from_buffer_copy(a)
         g.dyn_src, g.dyn_dev = run["dyn_src_addr"], run["ptr"]["dyn"]
         g.counts = run["ptr"]["counts"]
         g.tokens_out = None
+        g.tokens_row_map = row_map_ptr
         g.peer = ctypes.pointer(peer) if peer is not None else None    # selects the kernel variant only
         handle = ctypes.c_void_p()
         _cabi.check(_cabi.lib().ufv_encode_graph_create(ctypes.byref(g), ctypes.byref(handle)))
-        run["graphs"][peer is not None] = handle
+        if len(run["graphs"]) >= 8:                                    # bounded: the oldest capture goes
+            _cabi.lib().ufv_encode_graph_destroy(run["graphs"].pop(next(iter(run["graphs"]))))
+        run["graphs"][(peer is not None, row_map_ptr)] = handle
         run.setdefault("graph_args", []).append(g)
         return handle
 
@@ -505,6 +577,88 @@ class MaskExtractor(nn.Module):
             if run.get("args") is not None and plan.n_obj > 0:
                 return tokens, _await_counts(plan, run, tokens.device), plan
             return tokens, counts.cpu().numpy(), plan
+
+    def forward_into(self, feats, masks, ann_indices, text_embeds, seq_lens, region_pos, labels=None,
+                     ignore_index: int = -100):
+        """The path plus its consumer: builds the reference's ``new_input_embeds`` /
+        ``new_labels`` / attention mask of ``prepare_inputs_labels_for_multimodal`` (videorefer_arch.py:291-368)
+        for the region part in one go.  The last Linear of the projector stores every object token straight at its
+        ``<region>`` position inside the padded [B, L_max, hidden] batch (scatter epilogue); text rows, padding,
+        labels and the attention mask are laid down by one small kernel.  No tokens tensor, no per-sample cat.
+
+        text_embeds [sum(seq_lens), hidden]  the samples' embedded sequences back to back (model dtype, device)
+        seq_lens, region_pos                 see ``RegionLayout``
+        labels (optional) int64 [sum(seq_lens)] -> new labels [B, L_max] with ``ignore_index`` on region and
+        padding rows.  Returns (inputs_embeds [B, L_max, hidden], labels or None, attention_mask bool [B, L_max],
+        region_token_nums list[int]).  If the merge ties (an object keeps fewer tokens than reserved) the layout is
+        rebuilt from the real counts on the slow path, as the reference's python loop would produce it."""
+        with self._on_module_device():
+            linears = self._linears()
+            device = linears[0]._parameters["weight"].device
+            _require_cuda(text_embeds, "text_embeds")
+            if not torch.is_tensor(feats) or feats.dim() != 3:
+                raise ValueError("feats must be a tensor [F, n_patch, C]")
+            side = int(round(feats.shape[1] ** 0.5))
+            k_keep = int(self.region_token_num)
+            plan = packer.build_plan(masks, ann_indices, feats.shape[0], k_keep, device,
+                                     self.image_aspect_ratio == "pad", side)
+            hid = linears[-1].weight.shape[0]
+            if text_embeds.dim() != 2 or text_embeds.shape[1] != hid or text_embeds.dtype != linears[0].weight.dtype:
+                raise ValueError(f"text_embeds must be [rows, {hid}] of the projector dtype")
+            text_embeds = text_embeds.contiguous()
+            lkey = (tuple(int(n) for n in seq_lens), tuple(tuple(int(p) for p in r) for r in region_pos))
+            layouts = plan.__dict__.setdefault("_layouts", {})
+            hit = layouts.get(lkey)
+            if hit is None:
+                lay = RegionLayout(seq_lens, region_pos, plan.slots)
+                if lay.n_text != text_embeds.shape[0]:
+                    raise ValueError("text_embeds rows != sum(seq_lens)")
+                maps = torch.from_numpy(np.concatenate([lay.src_map, lay.token_row_map])).to(device)
+                if len(layouts) > 32:
+                    layouts.clear()
+                hit = layouts[lkey] = (lay, maps[:lay.src_map.size], maps[lay.src_map.size:])
+            lay, src_map, row_map = hit
+            n_rows = lay.batch * lay.l_max
+            out = torch.empty((n_rows, hid), dtype=text_embeds.dtype, device=device)
+            new_labels = torch.empty((n_rows,), dtype=torch.int64, device=device) if labels is not None else None
+            attn = torch.empty((n_rows,), dtype=torch.uint8, device=device)
+            if labels is not None:
+                labels = labels.to(device=device, dtype=torch.int64).contiguous()
+            _cabi.check(_cabi.lib().ufv_splice_static(
+                text_embeds.data_ptr(), labels.data_ptr() if labels is not None else None, src_map.data_ptr(),
+                out.data_ptr(), new_labels.data_ptr() if labels is not None else None, attn.data_ptr(), n_rows,
+                hid * text_embeds.element_size(), int(ignore_index), _stream_ptr(device)))
+            two = len(linears) == 2
+            if two and plan.m_pad > 0:
+                _, counts, plan = self.encode_padded(feats, masks, ann_indices, _awaited=True, scatter=(out, row_map))
+                run = self._last_run
+                nums = _await_counts(plan, run, device) if plan.n_obj > 0 else np.zeros(0, np.int32)
+            else:                                             # other projector depths: no scatter epilogue
+                tokens, nums_list = self._forward_impl(feats, masks, ann_indices)
+                nums = np.asarray(nums_list, dtype=np.int32)
+                if nums.tobytes() == plan.slots_bytes:
+                    live = row_map >= 0
+                    out.index_copy_(0, row_map[live].long(), tokens[live])
+            if nums.tobytes() != plan.slots_bytes:
+                # ties: some object kept fewer tokens than reserved -> every later row moves; rebuild from the counts
+                tokens, nums_list = self._forward_impl(feats, masks, ann_indices)
+                lay = RegionLayout(seq_lens, region_pos, nums_list)
+                n_rows = lay.batch * lay.l_max
+                src_map = torch.from_numpy(lay.src_map).to(device)
+                out = torch.empty((n_rows, hid), dtype=text_embeds.dtype, device=device)
+                new_labels = torch.empty((n_rows,), dtype=torch.int64, device=device) if labels is not None else None
+                attn = torch.empty((n_rows,), dtype=torch.uint8, device=device)
+                _cabi.check(_cabi.lib().ufv_splice_static(
+                    text_embeds.data_ptr(), labels.data_ptr() if labels is not None else None, src_map.data_ptr(),
+                    out.data_ptr(), new_labels.data_ptr() if labels is not None else None, attn.data_ptr(), n_rows,
+                    hid * text_embeds.element_size(), int(ignore_index), _stream_ptr(device)))
+                dest = torch.from_numpy(lay.token_row_map).to(device)
+                live = dest >= 0
+                out.index_copy_(0, dest[live].long(), tokens[live])
+                nums = np.asarray(nums_list, dtype=np.int32)
+            shape = (lay.batch, lay.l_max)
+            return (out.view(*shape, hid), new_labels.view(shape) if new_labels is not None else None,
+                    attn.view(shape).bool(), [int(n) for n in nums])
 
     def _forward_with_grad(self, feats, masks, ann_indices):
         """Training path (the region encoder is trainable in the reference, videorefer_arch.py:94-96):
