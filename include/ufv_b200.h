@@ -180,6 +180,27 @@ int ufv_linear_scatter(const void* x, const void* w, const void* bias, void* y, 
                        int dtype, int gelu, const int32_t* row_map, void* ws, int64_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Backward pass of the projector (the region encoder is trainable in the reference,
+ * videorefer_arch.py:94-96, train.py:887-890; there it is torch autograd over cuBLAS).  Every product runs
+ * on the same tcgen05 kernel as the forward pass:
+ *   ufv_linear_ex   y = epilogue(x . w^T + bias), bf16 / fp16, bias may be null.  epilogue:
+ *                   0  none
+ *                   1  GELU of the rounded sum; aux (optional, [m, n]) also receives the rounded
+ *                      pre-activation -- what the training forward keeps for the backward pass
+ *                   2  multiply by GELU'(aux[m, n]): the dgrad through Linear-2 and the GELU in one pass,
+ *                      dZ1 = (dY . W2) * GELU'(Z1), with w = W2^T
+ *   ufv_transpose16 out[c, r] = in[r, c] for 2-byte elements, output rows padded with zeros to out_pitch
+ *                   (>= rows, a multiple of 8): turns W, dY, H, X into the K-major operands the kernel takes:
+ *                   dgrad  dX = dZ . W      -> x = dZ,       w = W^T
+ *                   wgrad  dW = dZ^T . X    -> x = dZ^T,     w = X^T   (contraction over the tokens)
+ *   ufv_colsum      out[c] = sum_r x[r, c] (fp32 accumulation): the bias gradients
+ * -------------------------------------------------------------------------------------------*/
+int ufv_linear_ex(const void* x, const void* w, const void* bias, void* y, int m, int n, int k, int dtype,
+                  int epilogue, void* aux, void* stream);
+int ufv_transpose16(const void* in, void* out, int rows, int cols, int out_pitch, void* stream);
+int ufv_colsum(const void* x, void* out, int m, int n, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Kernel 4 fused with the result-collection all-gather (multi-GPU, clips sharded over ranks).
  * The reference collects per-rank results through files (eval/inference_PixRQA.py:214); here the
  * epilogue of the last Linear stores every output tile straight into the gathered buffer of

@@ -712,7 +712,8 @@ def test_forward_into_builds_the_padded_batch_like_the_reference_consumer(dev, d
     f2, m2, a2 = synth.make_clip(42, 7, 3, "dense", 64, 64, row0=7, ragged=case != "equal")
     feats = np.concatenate([f0, f1, f2])
     if case == "ties":
-        feats[0:6] = feats[0]                                                # clip 0: identical frames -> one token per object
+        feats[0:6] = feats[0]                                                # clip 0: identical frames and masks ->
+        m0 = np.repeat(m0[:1], m0.shape[0], axis=0)                          # every similarity ties: one token per object
     masks, ann = [m0, m1, m2], [a0, a1, a2]
     if case == "equal":
         seq_lens, region_pos = [11, 17, 8], [[1, 4], [], [0, 3, 7]]
@@ -796,6 +797,58 @@ def test_training_path_gradients_match_the_reference_ops(dev):
     with torch.no_grad():                                   # and the inference path still agrees
         t2, n2 = enc(feats.detach(), masks, None, ann, None)
     assert n2 == nums and (t2 - tokens.detach()).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("m", [48, 256, 300])
+def test_projector_backward_on_the_tensor_core_kernel(dev, dtype, m):
+    """_Projector (forward and backward of feat_linear on the tcgen05 kernel: GELU epilogue that keeps the
+    pre-activation, dgrad with the GELU-backward epilogue, wgrad over transposed operands, bias column sums)
+    against torch autograd over the same 16-bit modules."""
+    dt = TORCH_DT[dtype]
+    w1, b1, w2, b2 = [torch.from_numpy(a).to(dev).to(dt) for a in synth.make_weights(5)]
+    g = torch.Generator(device="cpu").manual_seed(m)
+    x0 = (torch.randn((m, 1152), generator=g) * 0.05).to(dev).to(dt)
+    probe = (torch.randn((m, 3584), generator=g) * 0.1).to(dev).to(dt)
+    ours = [t.detach().clone().requires_grad_(True) for t in (x0, w1, b1, w2, b2)]
+    ref = [t.detach().clone().requires_grad_(True) for t in (x0, w1, b1, w2, b2)]
+    y = layer._Projector.apply(*ours)
+    y_ref = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(ref[0], ref[1], ref[2])),
+                                       ref[3], ref[4])
+    assert (y.float() - y_ref.float()).abs().max().item() <= 1e-2
+    (y.float() * probe.float()).sum().backward()
+    (y_ref.float() * probe.float()).sum().backward()
+    for name, a, b in zip(("dx", "dw1", "db1", "dw2", "db2"), ours, ref):
+        ga, gb = a.grad.float(), b.grad.float()
+        assert ga.shape == gb.shape and torch.isfinite(ga).all(), name
+        scale = gb.abs().max().item()
+        # 16-bit gradients of sums over up to 3584 terms: compare against the magnitude of the gradient tensor
+        assert (ga - gb).abs().max().item() <= 2e-2 * max(scale, 1e-3), (name, (ga - gb).abs().max().item(), scale)
+
+
+def test_training_path_in_bf16_uses_the_tensor_core_backward(dev):
+    """forward() under autograd in bf16: gradients w.r.t. features and projector parameters agree with the
+    same computation when the projector runs under torch autograd / cuBLAS (UFV_TORCH_PROJECTOR_BACKWARD=1)."""
+    feats_np, masks_np, ann = synth.make_batch(2, 6, 2, "blob", h=96, w=96, first_clip=910, ragged=True)
+    masks = [torch.from_numpy(m).to(dev) for m in masks_np]
+    grads = {}
+    for mode in ("tcgen05", "torch"):
+        if mode == "torch":
+            os.environ["UFV_TORCH_PROJECTOR_BACKWARD"] = "1"
+        try:
+            enc = make_encoder(dev, "bf16", 3)
+            enc.requires_grad_(True)
+            feats = torch.from_numpy(feats_np).to(dev).bfloat16().requires_grad_(True)
+            tokens, nums = enc(feats, masks, None, ann, None)
+            probe = torch.linspace(-1, 1, tokens.numel(), device=dev).reshape(tokens.shape)
+            (tokens.float() * probe).sum().backward()
+            grads[mode] = (feats.grad.float(), enc.feat_linear[0].weight.grad.float(), enc.feat_linear[2].weight.grad.float(),
+                           enc.feat_linear[2].bias.grad.float(), nums)
+        finally:
+            os.environ.pop("UFV_TORCH_PROJECTOR_BACKWARD", None)
+    assert grads["tcgen05"][4] == grads["torch"][4]
+    for a, b in zip(grads["tcgen05"][:4], grads["torch"][:4]):
+        assert (a - b).abs().max().item() <= 3e-2 * max(b.abs().max().item(), 1e-3)
 
 
 def test_long_objects_spread_over_many_ctas(dev):

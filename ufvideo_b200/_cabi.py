@@ -83,6 +83,9 @@ _SIGNATURES = {
                           _p, C.c_int, _p, C.c_int, _p, _i32, _p]),
     "ufv_linear_ws_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ufv_linear": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _i64, _p]),
+    "ufv_linear_ex": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "ufv_transpose16": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "ufv_colsum": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p]),
     "ufv_linear_scatter": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _i64, _p]),
     "ufv_splice_static": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _i64, _p]),
     "ufv_linear_gather": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PeerArgs), _p, _i64,

@@ -45,6 +45,27 @@ __device__ __forceinline__ float gelu_erf_16bit(float v) {
   return v * (v > 0.0f ? 1.0f - q : q);
 }
 
+// d/dv GELU(v) = Phi(v) + v * phi(v) for the backward epilogue (same erfc form; phi = exp(-v^2 / 2) / sqrt(2 pi)).
+__device__ __forceinline__ float gelu_erf_grad_16bit(float v) {
+  const float av = fabsf(v);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(av, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * (v * -0.72134752044448170368f)));   // exp(-v^2 / 2)
+  float p = 0.5f * 1.061405429f;
+  p = fmaf(p, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float q = p * t * e;                      // Phi(-|v|)
+  const float cdf = v > 0.0f ? 1.0f - q : q;
+  return fmaf(v * 0.39894228040143267794f, e, cdf);
+}
+
+// epilogue modes of the tensor-core kernel
+constexpr int kEpiNone = 0;      // y = acc + bias
+constexpr int kEpiGelu = 1;      // y = GELU(round(acc + bias)); aux (optional): the rounded pre-activation is stored there too
+constexpr int kEpiGeluBwd = 2;   // y = (acc + bias) * GELU'(aux): aux = the forward's pre-activation (dgrad through GELU)
+
 // ================================= tcgen05 path ===================================================
 constexpr int kBM = 128;
 constexpr int kBK = 64;             // 64 x 2 B = one 128-byte swizzle row
@@ -181,12 +202,13 @@ __device__ __forceinline__ void peer_finish(const ufv_peer_args& peer, unsigned 
   *peer.ticket = 0u;                   // self-reset for the next call
 }
 
-template <typename T, int BN, bool GELU, bool PEER>
+template <typename T, int BN, int EPI, bool PEER>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const T* __restrict__ bias, T* __restrict__ y, int m, int n, int k, int tiles_m,
                  int n_tiles, const __grid_constant__ ufv_peer_args peer_param,
-                 const ufv_dyn_args* __restrict__ dyn, const int32_t* __restrict__ row_map) {
+                 const ufv_dyn_args* __restrict__ dyn, const int32_t* __restrict__ row_map, T* __restrict__ aux) {
+  constexpr bool GELU = EPI == kEpiGelu;
   using Cfg = GemmCfg<BN, PEER>;
   // fused all-gather: a warp's 32 x 32 sub-tile is turned around in shared memory so that its remote
   // stores are contiguous 64-byte row segments (4 lanes x 16 B) instead of 32 scattered 16-byte
@@ -305,11 +327,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if ((PEER || (row < m && dst_row >= 0)) && gcol < n) {
           uint32_t packed[16];
           if (gcol + 32 <= n) {
-            const uint4* bsrc = reinterpret_cast<const uint4*>(bias + gcol);   // warp-uniform: broadcast
+            const uint4* bsrc = reinterpret_cast<const uint4*>(bias + gcol);   // warp-uniform: broadcast (bias may be null)
+            T* aux_row = (EPI != kEpiNone && aux != nullptr && row < m) ? aux + size_t(row) * n + gcol : nullptr;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-              const uint4 bq = __ldg(bsrc + q4);
+              const uint4 bq = bias != nullptr ? __ldg(bsrc + q4) : make_uint4(0u, 0u, 0u, 0u);
               const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+              uint4 zq = make_uint4(0u, 0u, 0u, 0u);
+              if (EPI == kEpiGeluBwd && aux_row != nullptr) zq = *reinterpret_cast<const uint4*>(aux_row + q4 * 8);
+              const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+              uint32_t zout[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 bf = Pack8<T>::unpack(bw[j]);
@@ -317,11 +344,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 float a = __uint_as_float(v[i]) + bf.x;
                 float b = __uint_as_float(v[i + 1]) + bf.y;
                 if (GELU) {   // the reference rounds to the model dtype before and after GELU
-                  a = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(a)));
-                  b = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(b)));
+                  const float za = Elem<T>::to_f32(Elem<T>::from_f32(a)), zb = Elem<T>::to_f32(Elem<T>::from_f32(b));
+                  zout[j] = Pack8<T>::two(za, zb);
+                  a = gelu_erf_16bit(za);
+                  b = gelu_erf_16bit(zb);
+                }
+                if (EPI == kEpiGeluBwd) {   // dgrad through GELU: the incoming gradient times GELU'(pre-activation)
+                  const float2 z = Pack8<T>::unpack(zw[j]);
+                  a *= gelu_erf_grad_16bit(z.x);
+                  b *= gelu_erf_grad_16bit(z.y);
                 }
                 packed[i >> 1] = Pack8<T>::two(a, b);
               }
+              if (GELU && aux_row != nullptr)     // training forward: keep the pre-activation for the backward pass
+                *reinterpret_cast<uint4*>(aux_row + q4 * 8) = make_uint4(zout[0], zout[1], zout[2], zout[3]);
             }
             if (PEER) {                  // fused all-gather: the tile goes to every rank's gathered buffer
               uint4(*stage)[5] = s_stage[warp - 2];
@@ -350,8 +386,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (gcol + i < n) {
-                float a = __uint_as_float(v[i]) + Elem<T>::to_f32(bias[gcol + i]);
-                if (GELU) a = gelu_erf_16bit(Elem<T>::to_f32(Elem<T>::from_f32(a)));
+                float a = __uint_as_float(v[i]) + (bias != nullptr ? Elem<T>::to_f32(bias[gcol + i]) : 0.0f);
+                if (GELU) {
+                  const float za = Elem<T>::to_f32(Elem<T>::from_f32(a));
+                  if (aux != nullptr) aux[size_t(row) * n + gcol + i] = Elem<T>::from_f32(za);
+                  a = gelu_erf_16bit(za);
+                }
+                if (EPI == kEpiGeluBwd) a *= gelu_erf_grad_16bit(Elem<T>::to_f32(aux[size_t(row) * n + gcol + i]));
                 dst[i] = Elem<T>::from_f32(a);
               }
             }
@@ -646,8 +687,8 @@ static int sm_count() {
 
 template <typename T, int BN>
 static int launch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
-                     int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, const int32_t* row_map,
-                     cudaStream_t stream) {
+                     int epi, const ufv_peer_args* peer, const ufv_dyn_args* dyn, const int32_t* row_map,
+                     void* aux, cudaStream_t stream) {
   const int smem_bytes = peer != nullptr ? GemmCfg<BN, true>::kSmem : GemmCfg<BN, false>::kSmem;
   CUtensorMap tx, tw;
   int rc = make_tensor_map_2d(&tx, x, Elem<T>::kDtype, uint64_t(m), uint64_t(k), kBM, kBK, 1);
@@ -657,11 +698,12 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
   const int tiles_m = (m + kBM - 1) / kBM;
   const int n_tiles = tiles_m * ((n + BN - 1) / BN);
   const dim3 grid(n_tiles < sm_count() ? n_tiles : sm_count());
-  const int variant = peer != nullptr ? 2 : gelu ? 1 : 0;
-  auto kernel = variant == 2   ? linear_tc_kernel<T, BN, false, true>
-                : variant == 1 ? linear_tc_kernel<T, BN, true, false>
-                               : linear_tc_kernel<T, BN, false, false>;
-  static bool configured[3] = {false, false, false};   // idempotent attribute; a benign race sets it twice
+  const int variant = peer != nullptr ? 3 : epi;
+  auto kernel = variant == 3   ? linear_tc_kernel<T, BN, kEpiNone, true>
+                : variant == 2 ? linear_tc_kernel<T, BN, kEpiGeluBwd, false>
+                : variant == 1 ? linear_tc_kernel<T, BN, kEpiGelu, false>
+                               : linear_tc_kernel<T, BN, kEpiNone, false>;
+  static bool configured[4] = {false, false, false, false};   // idempotent attribute; a benign race sets it twice
   if (!configured[variant]) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     configured[variant] = true;
@@ -670,7 +712,7 @@ static int launch_tc(const void* x, const void* w, const void* bias, void* y, in
   return check_launch("ufv_linear (tcgen05)",
                       launch_kernel(kernel, grid, dim3(kGemmThreads), smem_bytes, stream, tx, tw,
                                     static_cast<const T*>(bias), static_cast<T*>(y), m, n, k, tiles_m, n_tiles,
-                                    peer != nullptr ? *peer : no_peer, dyn, row_map));
+                                    peer != nullptr ? *peer : no_peer, dyn, row_map, static_cast<T*>(aux)));
 }
 
 // N-tile choice.  A launch costs (waves over the SMs) x (time of one tile).  Tile times per 64-deep
@@ -772,9 +814,10 @@ static int launch_splitk(const void* x, const void* w, const void* bias, void* y
 template <typename T>
 static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
                        int gelu, const ufv_peer_args* peer, const ufv_dyn_args* dyn, void* ws, int64_t ws_bytes,
-                       const int32_t* row_map, cudaStream_t stream) {
+                       const int32_t* row_map, cudaStream_t stream, void* aux = nullptr) {
   const SplitChoice sc = choose_split(m, n, k);
-  if (sc.s > 1 && ws != nullptr && size_t(ws_bytes) >= split_ws_bytes(m, n, k)) {
+  if (sc.s > 1 && ws != nullptr && size_t(ws_bytes) >= split_ws_bytes(m, n, k) && gelu <= 1 && aux == nullptr &&
+      bias != nullptr) {
     float* slab = static_cast<float*>(ws);
     switch (sc.bn) {
       case 256: return launch_splitk<T, 256>(x, w, bias, y, m, n, k, gelu, sc.s, slab, peer, dyn, row_map, stream);
@@ -783,10 +826,10 @@ static int dispatch_tc(const void* x, const void* w, const void* bias, void* y, 
     }
   }
   switch (choose_bn(m, n)) {
-    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
-    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
-    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
-    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, stream);
+    case 256: return launch_tc<T, 256>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, aux, stream);
+    case 128: return launch_tc<T, 128>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, aux, stream);
+    case 64: return launch_tc<T, 64>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, aux, stream);
+    default: return launch_tc<T, 32>(x, w, bias, y, m, n, k, gelu, peer, dyn, row_map, aux, stream);
   }
 }
 
@@ -945,6 +988,86 @@ extern "C" int ufv_linear_scatter(const void* x, const void* w, const void* bias
 extern "C" int ufv_linear(const void* x, const void* w, const void* bias, void* y, int m, int n, int k,
                           int dtype, int gelu, void* ws, int64_t ws_bytes, void* stream) {
   return ufv_linear_scatter(x, w, bias, y, m, n, k, dtype, gelu, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int ufv_linear_ex(const void* x, const void* w, const void* bias, void* y, int m, int n, int k, int dtype,
+                             int epilogue, void* aux, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(m >= 0 && n >= 1 && k >= 1, UFV_E_SHAPE, "ufv_linear_ex: m=%d n=%d k=%d", m, n, k);
+  if (m == 0) return 0;
+  UFV_REQUIRE(dtype == UFV_BF16 || dtype == UFV_F16, UFV_E_DTYPE, "ufv_linear_ex: dtype %d (bf16 / fp16 only)", dtype);
+  UFV_REQUIRE(epilogue >= kEpiNone && epilogue <= kEpiGeluBwd, UFV_E_SHAPE, "ufv_linear_ex: epilogue %d", epilogue);
+  UFV_REQUIRE(x && w && y && (epilogue != kEpiGeluBwd || aux), UFV_E_NULL, "ufv_linear_ex: null pointer");
+  UFV_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(aux) && aligned16(bias), UFV_E_ALIGN,
+              "ufv_linear_ex: buffers must be 16-byte aligned");
+  UFV_REQUIRE(k % 8 == 0 && n % 8 == 0, UFV_E_SHAPE, "ufv_linear_ex: k=%d and n=%d must be multiples of 8", k, n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == UFV_BF16)
+    return dispatch_tc<__nv_bfloat16>(x, w, bias, y, m, n, k, epilogue, nullptr, nullptr, nullptr, 0, nullptr, st, aux);
+  return dispatch_tc<__half>(x, w, bias, y, m, n, k, epilogue, nullptr, nullptr, nullptr, 0, nullptr, st, aux);
+}
+
+// ---- helpers of the projector's backward pass ---------------------------------------------------------------
+namespace ufv {
+// out[c, r] = in[r, c] for 2-byte elements; out has `out_pitch` elements per row (>= rows; the columns
+// [rows, out_pitch) are zero-filled so that the transposed matrix can serve as a K-major GEMM operand whose
+// contraction length is padded to a multiple of 8).  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                          int rows, int cols, int out_pitch) {
+  __shared__ uint16_t tile[32][34];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[size_t(r) * cols + c] : uint16_t(0);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;                         // out row = c, out column = r
+    if (c < cols && r < out_pitch) out[size_t(c) * out_pitch + r] = tile[tx][i];
+  }
+}
+
+// out[c] = sum over rows of x[r, c], fp32 accumulation in ascending row order, rounded to T (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, T* __restrict__ out, int m, int n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= n) return;
+  float acc = 0.f;
+  for (int r = 0; r < m; ++r) acc += Elem<T>::to_f32(x[size_t(r) * n + c]);
+  out[c] = Elem<T>::from_f32(acc);
+}
+}  // namespace ufv
+
+extern "C" int ufv_transpose16(const void* in, void* out, int rows, int cols, int out_pitch, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(rows >= 0 && cols >= 0 && out_pitch >= rows, UFV_E_SHAPE, "ufv_transpose16: rows=%d cols=%d out_pitch=%d",
+              rows, cols, out_pitch);
+  if (rows == 0 || cols == 0) return 0;
+  UFV_REQUIRE(in && out, UFV_E_NULL, "ufv_transpose16: null pointer");
+  const dim3 grid((cols + 31) / 32, (out_pitch + 31) / 32);
+  return check_launch("ufv_transpose16",
+                      launch_kernel(transpose16_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                    static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), rows, cols, out_pitch));
+}
+
+extern "C" int ufv_colsum(const void* x, void* out, int m, int n, int dtype, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(m >= 0 && n >= 1, UFV_E_SHAPE, "ufv_colsum: m=%d n=%d", m, n);
+  UFV_REQUIRE(x && out, UFV_E_NULL, "ufv_colsum: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((n + 255) / 256);
+  if (dtype == UFV_BF16)
+    return check_launch("ufv_colsum", launch_kernel(colsum_kernel<__nv_bfloat16>, grid, dim3(256), 0, st,
+                                                    static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), m, n));
+  if (dtype == UFV_F16)
+    return check_launch("ufv_colsum", launch_kernel(colsum_kernel<__half>, grid, dim3(256), 0, st,
+                                                    static_cast<const __half*>(x), static_cast<__half*>(out), m, n));
+  return fail(UFV_E_DTYPE, "ufv_colsum: dtype %d (bf16 / fp16 only)", dtype);
 }
 
 namespace ufv {

@@ -70,29 +70,41 @@ __device__ __forceinline__ bool window_is_tile(int win, uint32_t u, int n_patch,
   return use_tmap && 32 * win + 32 <= n_patch && __popc(u) >= tile_min;
 }
 
-// advances `win` past the chunk; false when the frame is exhausted
-__device__ __forceinline__ bool next_chunk(const uint32_t* s_union, int n_win, int n_patch, int use_tmap, int tile_min,
-                                           int& win, PoolChunk& ch) {
-  while (win < n_win && s_union[win] == 0u) ++win;
-  if (win >= n_win) return false;
-  const uint32_t u = s_union[win];
-  ch.w0 = win;
-  ch.rows = __popc(u);
-  ch.tile = window_is_tile(win, u, n_patch, use_tmap, tile_min);
-  int e = win + 1;
-  if (!ch.tile) {
-    while (e < n_win) {
-      const uint32_t u2 = s_union[e];
-      if (u2 != 0u) {
-        if (window_is_tile(e, u2, n_patch, use_tmap, tile_min) || ch.rows + __popc(u2) > kPoolRows) break;
-        ch.rows += __popc(u2);
+// The chunk table of a frame, built once per CTA by one thread (at most 23 windows): entry = w0 | w1 << 8 |
+// rows << 16 | tile << 24.  Returns the number of chunks.
+__device__ __forceinline__ int build_chunk_table(const uint32_t* s_union, int n_win, int n_patch, int use_tmap,
+                                                 int tile_min, uint32_t* s_chunk) {
+  int n = 0, win = 0;
+  while (true) {
+    while (win < n_win && s_union[win] == 0u) ++win;
+    if (win >= n_win) break;
+    const uint32_t u = s_union[win];
+    int rows = __popc(u);
+    const bool tile = window_is_tile(win, u, n_patch, use_tmap, tile_min);
+    int e = win + 1;
+    if (!tile) {
+      while (e < n_win) {
+        const uint32_t u2 = s_union[e];
+        if (u2 != 0u) {
+          if (window_is_tile(e, u2, n_patch, use_tmap, tile_min) || rows + __popc(u2) > kPoolRows) break;
+          rows += __popc(u2);
+        }
+        ++e;
       }
-      ++e;
     }
+    s_chunk[n++] = uint32_t(win) | (uint32_t(e) << 8) | (uint32_t(rows) << 16) | (tile ? 1u << 24 : 0u);
+    win = e;
   }
-  ch.w1 = e;
-  win = e;
-  return true;
+  return n;
+}
+
+__device__ __forceinline__ PoolChunk unpack_chunk(uint32_t v) {
+  PoolChunk ch;
+  ch.w0 = int(v & 0xffu);
+  ch.w1 = int((v >> 8) & 0xffu);
+  ch.rows = int((v >> 16) & 0xffu);
+  ch.tile = (v >> 24) != 0u;
+  return ch;
 }
 
 // slot of patch (win, r) inside a packed chunk whose earlier windows hold `base` rows
@@ -156,6 +168,8 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
   __shared__ uint32_t s_bits[8][UFV_BITS_WORDS];                           // members' patch bitmasks
   __shared__ uint32_t s_union[UFV_BITS_WORDS];
+  __shared__ uint32_t s_chunk[UFV_BITS_WORDS];                             // chunk table of the frame
+  __shared__ int s_n_chunks;
   __shared__ __align__(16) uint8_t s_omask[S][R];                          // member masks of the staged rows
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t empty_bar[S];
@@ -195,19 +209,19 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     s_union[tid] = u;
   }
   __syncthreads();
-  const int n_win = (n_patch + R - 1) / R;
+  if (tid == 0) s_n_chunks = build_chunk_table(s_union, (n_patch + R - 1) / R, n_patch, use_tmap, tile_min, s_chunk);
+  __syncthreads();
+  const int n_chunks = s_n_chunks;
   const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == kPoolConsumers) {
     // ---------------- producer warp: windows -> TMA engine -> shared-memory ring ------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    int k = 0, win = 0;                                        // stages used so far, next window
-    PoolChunk ch;
-    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
+    for (int k = 0; k < n_chunks; ++k) {
+      const PoolChunk ch = unpack_chunk(s_chunk[k]);
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
-      ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
       // member masks of the stage's slots: which of the <= 8 members pool the patch sitting in slot i
       if (ch.tile) {
@@ -249,12 +263,9 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       out_row[o] = o < n_mem ? grp_member[m0 + o] : -1;
       denorm[o] = out_row[o] >= 0 ? __fadd_rn(float(cnt[out_row[o]]), 1e-8f) : 1.0f;   // layer.py:145
     }
-    int k = 0, win = 0;
-    PoolChunk ch;
-    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
+    for (int k = 0; k < n_chunks; ++k) {
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
-      ++k;
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
       uint32_t mk[R / 4];
@@ -326,6 +337,8 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
   __shared__ uint32_t s_bits[PM][UFV_BITS_WORDS];                          // members' patch bitmasks
   __shared__ uint32_t s_union[UFV_BITS_WORDS];
+  __shared__ uint32_t s_chunk[UFV_BITS_WORDS];                             // chunk table of the frame
+  __shared__ int s_n_chunks;
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t empty_bar[S];
 
@@ -362,19 +375,19 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     s_union[tid] = u;
   }
   __syncthreads();
-  const int n_win = (n_patch + R - 1) / R;
+  if (tid == 0) s_n_chunks = build_chunk_table(s_union, (n_patch + R - 1) / R, n_patch, use_tmap, tile_min, s_chunk);
+  __syncthreads();
+  const int n_chunks = s_n_chunks;
   const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == NW) {
     // ---------------- producer warp ---------------------------------------------------------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    int k = 0, win = 0;
-    PoolChunk ch;
-    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
+    for (int k = 0; k < n_chunks; ++k) {
+      const PoolChunk ch = unpack_chunk(s_chunk[k]);
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
-      ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
       produce_chunk<T>(&tmap, feats, row_base, c, ch0, slice_bytes, ch, s_union, ring + size_t(s) * R * kPoolCh,
                        &full_bar[s], lane);
@@ -386,33 +399,48 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     for (int mi = 0; mi < MPW; ++mi) acc[mi] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int my_ch = lane * 4;
     const bool live = my_ch < slice_ch;
-    int k = 0, win = 0;
-    PoolChunk ch;
-    while (next_chunk(s_union, n_win, n_patch, use_tmap, tile_min, win, ch)) {
+    for (int k = 0; k < n_chunks; ++k) {
+      const PoolChunk ch = unpack_chunk(s_chunk[k]);
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
-      ++k;
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
-      int base = 0;
-      for (int w = ch.w0; w < ch.w1; ++w) {
-        const uint32_t u = s_union[w];
-        if (u == 0u) continue;
+      if (ch.tile) {
+        // one window, patch 32 w0 + r in slot r: the tight loop (the kernel is bound by its instruction count)
 #pragma unroll
         for (int mi = 0; mi < MPW; ++mi) {
-          uint32_t word = s_bits[mi * NW + warp][w];         // warp-uniform: the rows of this window the member pools
+          uint32_t word = s_bits[mi * NW + warp][ch.w0];     // warp-uniform: the rows of this window the member pools
           while (word != 0u) {
             const int r = __ffs(word) - 1;
             word &= word - 1u;
-            const int slot = ch.tile ? r : packed_slot(base, u, r);
-            const float4 f = Quad<T>::load(src + slot * kPoolCh);
+            const float4 f = Quad<T>::load(src + r * kPoolCh);
             float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
             add2(lo, make_float2(f.x, f.y));
             add2(hi, make_float2(f.z, f.w));
             acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
         }
-        base += __popc(u);
+      } else {
+        // several sparse windows packed into the stage: slot = rank of the patch among the chunk's needed rows
+        int base = 0;
+        for (int w = ch.w0; w < ch.w1; ++w) {
+          const uint32_t u = s_union[w];
+          if (u == 0u) continue;
+#pragma unroll
+          for (int mi = 0; mi < MPW; ++mi) {
+            uint32_t word = s_bits[mi * NW + warp][w];
+            while (word != 0u) {
+              const int r = __ffs(word) - 1;
+              word &= word - 1u;
+              const float4 f = Quad<T>::load(src + packed_slot(base, u, r) * kPoolCh);
+              float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
+              add2(lo, make_float2(f.x, f.y));
+              add2(hi, make_float2(f.z, f.w));
+              acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+          }
+          base += __popc(u);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);

@@ -680,6 +680,12 @@ class MaskExtractor(nn.Module):
         if nums.tobytes() != plan.slots_bytes:                    # merge ties: drop the zero-filled slots
             keep = np.concatenate([np.arange(s, s + n) for s, n in zip(plan.host["slot_off"], nums)])
             merged = merged[torch.from_numpy(keep).to(device)]
+        if (len(linears) == 2 and merged.dtype in (torch.bfloat16, torch.float16) and merged.shape[0] > 0
+                and os.environ.get("UFV_TORCH_PROJECTOR_BACKWARD") is None):
+            # forward and backward of the projector on the tcgen05 kernel (UFV_TORCH_PROJECTOR_BACKWARD=1: developer
+            # A/B knob that puts the projector back under torch autograd / cuBLAS)
+            l0, l1 = linears
+            return _Projector.apply(merged, l0.weight, l0.bias, l1.weight, l1.bias), [int(n) for n in nums]
         return self.feat_linear(merged), [int(n) for n in nums]
 
     # -- the reference's forward -----------------------------------------------------------------
@@ -787,6 +793,63 @@ class _PoolMerge(torch.autograd.Function):
             n_rows, int(per_row.max()) if q else 0, n_patch, c, d_feats.data_ptr(),
             packer.FEAT_DTYPES[ctx.feat_dtype], _stream_ptr(dev)))
         return d_feats, None, None, None
+
+
+def _linear_ex(x, w, bias, epilogue=0, aux=None):
+    """ufv_linear_ex: epilogue(x @ w.T + bias) on the tcgen05 kernel (bf16 / fp16); see include/ufv_b200.h."""
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    _cabi.check(_cabi.lib().ufv_linear_ex(
+        x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, y.data_ptr(), m, n, k,
+        _feat_dtype(x), epilogue, aux.data_ptr() if aux is not None else None, _stream_ptr(x.device)))
+    return y
+
+
+def _transpose16(x, pad_to=8):
+    """[r, c] -> [c, ceil(r / pad_to) * pad_to] (zero-padded columns), 2-byte elements, one kernel."""
+    r, c = x.shape
+    pitch = -(-r // pad_to) * pad_to
+    out = torch.empty((c, pitch), dtype=x.dtype, device=x.device)
+    _cabi.check(_cabi.lib().ufv_transpose16(x.data_ptr(), out.data_ptr(), r, c, pitch, _stream_ptr(x.device)))
+    return out
+
+
+def _colsum(x):
+    out = torch.empty((x.shape[1],), dtype=x.dtype, device=x.device)
+    _cabi.check(_cabi.lib().ufv_colsum(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _feat_dtype(x),
+                                       _stream_ptr(x.device)))
+    return out
+
+
+class _Projector(torch.autograd.Function):
+    """feat_linear (Linear -> GELU -> Linear, layer.py:55-59) for training in bf16 / fp16, forward AND backward on
+    the tcgen05 kernel.  Forward keeps the rounded pre-activation Z1 (written by the
+    GELU epilogue) and H.  Backward: dZ1 = (dY . W2) * GELU'(Z1) in one GEMM with the GELU-backward epilogue,
+    dW2 = dY^T . H, dX = dZ1 . W1, dW1 = dZ1^T . X, bias gradients by column sums.  The kernel contracts K-major
+    operands, so W2, W1, dY, H, dZ1 and X are transposed by a small kernel first (the weights: 34 MB, ~15 us)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x = x.contiguous()
+        z1 = torch.empty((x.shape[0], w1.shape[0]), dtype=x.dtype, device=x.device)
+        h = _linear_ex(x, w1, b1, epilogue=1, aux=z1)
+        y = _linear_ex(h, w2, b2, epilogue=0)
+        ctx.save_for_backward(x, w1, w2, z1, h)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, z1, h = ctx.saved_tensors
+        dy = dy.contiguous().to(x.dtype)
+        need = ctx.needs_input_grad
+        dz1 = _linear_ex(dy, _transpose16(w2), None, epilogue=2, aux=z1)            # [M, hid]
+        dw2 = _linear_ex(_transpose16(dy), _transpose16(h), None) if need[3] else None   # [hid, hid]
+        db2 = _colsum(dy) if need[4] else None
+        dx = _linear_ex(dz1, _transpose16(w1), None) if need[0] else None           # [M, C]
+        dw1 = _linear_ex(_transpose16(dz1), _transpose16(x), None) if need[1] else None  # [hid, C]
+        db1 = _colsum(dz1) if need[2] else None
+        return dx, dw1, db1, dw2, db2
 
 
 def build_region_encoder(config, image_aspect_ratio):
