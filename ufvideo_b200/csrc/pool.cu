@@ -107,6 +107,41 @@ __device__ __forceinline__ PoolChunk unpack_chunk(uint32_t v) {
   return ch;
 }
 
+// Frames whose needed rows are spread thinly over many windows take the packed path (chunk table, several
+// windows per stage); everything else walks the windows directly, one stage per non-empty window -- the two
+// paths are separate loops so that the common, dense one carries none of the packing machinery.
+// Called by ONE thread after the union words are complete; returns the number of chunks, or 0 for the direct path.
+__device__ __forceinline__ int plan_frame(const uint32_t* s_union, int n_win, int n_patch, int use_tmap, int tile_min,
+                                          uint32_t* s_chunk) {
+  int windows = 0, rows = 0;
+  for (int w = 0; w < n_win; ++w) {
+    const uint32_t u = s_union[w];
+    windows += u != 0u;
+    rows += __popc(u);
+  }
+  if (windows <= 2 * ((rows + kPoolRows - 1) / kPoolRows)) return 0;
+  return build_chunk_table(s_union, n_win, n_patch, use_tmap, tile_min, s_chunk);
+}
+
+// Direct path, per non-empty window: the producer warp's part.  `u` = union word of the window (bit r = patch
+// 32 * win + r is needed by some member; it sits in slot r of the stage).
+template <typename T>
+__device__ __forceinline__ void produce_window(const CUtensorMap* tmap, int use_tmap, const T* __restrict__ feats,
+                                               int64_t row_base, int c, int ch0, uint32_t slice_bytes, int win,
+                                               int n_patch, uint32_t u, int tile_min, T* dst, uint64_t* full_bar,
+                                               int lane) {
+  const bool tile = window_is_tile(win, u, n_patch, use_tmap, tile_min);
+  if (lane == 0) {
+    mbar_arrive_expect_tx(full_bar, tile ? uint32_t(kPoolRows) * kPoolCh * sizeof(T) : uint32_t(__popc(u)) * slice_bytes);
+    if (tile) tma_load_2d(dst, tmap, ch0, int(row_base + 32 * win), full_bar);
+  }
+  if (!tile) {
+    __syncwarp();
+    if ((u >> lane) & 1u)
+      bulk_g2s(dst + lane * kPoolCh, feats + (row_base + 32 * win + lane) * int64_t(c) + ch0, slice_bytes, full_bar);
+  }
+}
+
 // slot of patch (win, r) inside a packed chunk whose earlier windows hold `base` rows
 __device__ __forceinline__ int packed_slot(int base, uint32_t u, int r) { return base + __popc(u & ((1u << r) - 1u)); }
 
@@ -156,7 +191,7 @@ template <> struct Pair<__half> {
 };
 
 template <typename T, int OT>
-__global__ void __launch_bounds__(kPoolThreads)
+__global__ void __launch_bounds__(kPoolThreads, sizeof(T) == 4 ? 4 : 8)
 mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
                  int n_patch, int c, int n_slices, const uint32_t* __restrict__ bits,
                  const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,
@@ -209,15 +244,34 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
     s_union[tid] = u;
   }
   __syncthreads();
-  if (tid == 0) s_n_chunks = build_chunk_table(s_union, (n_patch + R - 1) / R, n_patch, use_tmap, tile_min, s_chunk);
+  const int n_win = (n_patch + R - 1) / R;
+  if (tid == 0) s_n_chunks = plan_frame(s_union, n_win, n_patch, use_tmap, tile_min, s_chunk);
   __syncthreads();
-  const int n_chunks = s_n_chunks;
+  const int n_chunks = s_n_chunks;                             // 0: direct path (one stage per non-empty window)
   const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == kPoolConsumers) {
     // ---------------- producer warp: windows -> TMA engine -> shared-memory ring ------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
+    if (n_chunks == 0) {
+      int k = 0;                                               // stages used so far (non-empty windows)
+      for (int win = 0; win < n_win; ++win) {
+        const uint32_t u = s_union[win];
+        if (u == 0u) continue;                                 // no member needs any row of this window
+        const int s = k % S;
+        const uint32_t ph = (k / S) & 1;
+        ++k;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint32_t m = 0;                                        // lane r: which members pool patch 32 win + r
+#pragma unroll
+        for (int o = 0; o < 8; ++o) m |= ((s_bits[o][win] >> lane) & 1u) << o;
+        s_omask[s][lane] = static_cast<uint8_t>(m);
+        __syncwarp();                                          // the masks precede lane 0's (releasing) arrive
+        produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
+                          ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
+      }
+    }
     for (int k = 0; k < n_chunks; ++k) {
       const PoolChunk ch = unpack_chunk(s_chunk[k]);
       const int s = k % S;
@@ -263,7 +317,10 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
       out_row[o] = o < n_mem ? grp_member[m0 + o] : -1;
       denorm[o] = out_row[o] >= 0 ? __fadd_rn(float(cnt[out_row[o]]), 1e-8f) : 1.0f;   // layer.py:145
     }
-    for (int k = 0; k < n_chunks; ++k) {
+    int n_stages = n_chunks;
+    if (n_chunks == 0)
+      for (int win = 0; win < n_win; ++win) n_stages += s_union[win] != 0u;
+    for (int k = 0; k < n_stages; ++k) {                        // the stage's member masks say everything a consumer needs
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
       mbar_wait(&full_bar[s], ph);
@@ -375,15 +432,29 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     s_union[tid] = u;
   }
   __syncthreads();
-  if (tid == 0) s_n_chunks = build_chunk_table(s_union, (n_patch + R - 1) / R, n_patch, use_tmap, tile_min, s_chunk);
+  const int n_win = (n_patch + R - 1) / R;
+  if (tid == 0) s_n_chunks = plan_frame(s_union, n_win, n_patch, use_tmap, tile_min, s_chunk);
   __syncthreads();
-  const int n_chunks = s_n_chunks;
+  const int n_chunks = s_n_chunks;                             // 0: direct path (one stage per non-empty window)
   const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == NW) {
     // ---------------- producer warp ---------------------------------------------------------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
+    if (n_chunks == 0) {
+      int k = 0;
+      for (int win = 0; win < n_win; ++win) {
+        const uint32_t u = s_union[win];
+        if (u == 0u) continue;
+        const int s = k % S;
+        const uint32_t ph = (k / S) & 1;
+        ++k;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
+                          ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
+      }
+    }
     for (int k = 0; k < n_chunks; ++k) {
       const PoolChunk ch = unpack_chunk(s_chunk[k]);
       const int s = k % S;
@@ -399,6 +470,34 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     for (int mi = 0; mi < MPW; ++mi) acc[mi] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int my_ch = lane * 4;
     const bool live = my_ch < slice_ch;
+    if (n_chunks == 0) {
+      // direct path: one stage per non-empty window, patch 32 win + r in slot r -- the tight loop (this kernel is
+      // bound by its instruction count)
+      int k = 0;
+      for (int win = 0; win < n_win; ++win) {
+        if (s_union[win] == 0u) continue;
+        const int s = k % S;
+        const uint32_t ph = (k / S) & 1;
+        ++k;
+        mbar_wait(&full_bar[s], ph);
+        const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
+#pragma unroll
+        for (int mi = 0; mi < MPW; ++mi) {
+          uint32_t word = s_bits[mi * NW + warp][win];       // warp-uniform: the rows of this window the member pools
+          while (word != 0u) {
+            const int r = __ffs(word) - 1;
+            word &= word - 1u;
+            const float4 f = Quad<T>::load(src + r * kPoolCh);
+            float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
+            add2(lo, make_float2(f.x, f.y));
+            add2(hi, make_float2(f.z, f.w));
+            acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+    }
     for (int k = 0; k < n_chunks; ++k) {
       const PoolChunk ch = unpack_chunk(s_chunk[k]);
       const int s = k % S;
