@@ -54,6 +54,13 @@ constexpr int kPoolConsumers = 2;             // dense kernel: consumer warps, 6
 constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
 constexpr int kSparseConsumers = 8;           // sparse kernel: consumer warps, 128 channels each, members interleaved
 constexpr int kSparseThreads = 32 * (kSparseConsumers + 1);
+// 288 threads at full occupancy would leave 32 registers per thread (spills in the bit-iteration loop); fewer CTAs
+// per SM with a deeper ring keep ~150 KB in flight per SM and give the compiler 40 - 75 registers.
+// More members per warp need more accumulator registers: fewer CTAs per SM, deeper rings.
+template <int MPW> struct SparseCfg {
+  static constexpr int kMinCtas = MPW <= 2 ? 5 : MPW <= 4 ? 4 : 3;
+  static constexpr int kStages = MPW <= 2 ? 4 : MPW <= 4 ? 5 : 6;
+};
 static_assert(kPoolRows == 32, "a window is one 32-bit word of the patch bitmasks");
 
 // One ring stage holds a CHUNK of the frame: either one full window that is mostly needed, fetched as a 2-D tile
@@ -383,13 +390,13 @@ template <> struct Quad<__half> {
 // that member pools (set bits of the member word, ascending) -- the accumulation order per (object, channel) is
 // the same ascending-patch sequence as in the dense kernel and in the oracle.
 template <typename T, int MPW>
-__global__ void __launch_bounds__(kSparseThreads)
+__global__ void __launch_bounds__(kSparseThreads, sizeof(T) == 4 ? (MPW <= 4 ? 3 : 2) : SparseCfg<MPW>::kMinCtas)
 mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
                         int n_patch, int c, int n_slices, const uint32_t* __restrict__ bits,
                         const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,
                         const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member, int tile_min,
                         float* __restrict__ pooled) {
-  constexpr int S = kPoolStages, R = kPoolRows, NW = kSparseConsumers, PM = MPW * NW;
+  constexpr int S = SparseCfg<MPW>::kStages, R = kPoolRows, NW = kSparseConsumers, PM = MPW * NW;
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
   __shared__ uint32_t s_bits[PM][UFV_BITS_WORDS];                          // members' patch bitmasks
@@ -651,7 +658,7 @@ static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
 template <typename T, int MPW>
 static int launch_pool_sparse(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a, cudaStream_t stream) {
   const int n_slices = (a.c + kPoolCh - 1) / kPoolCh;
-  const size_t smem = size_t(kPoolStages) * kPoolRows * kPoolCh * sizeof(T);
+  const size_t smem = size_t(SparseCfg<MPW>::kStages) * kPoolRows * kPoolCh * sizeof(T);
   auto kernel = mask_pool_sparse_kernel<T, MPW>;
   static bool configured = false;
   if (!configured) {
