@@ -220,3 +220,101 @@ def test_plan_matches_a_direct_restatement_of_the_reference_loop(batch):
         d = h["mask_desc"][off:off + q]
         assert (d["addr"] == m.data_ptr() + np.arange(q, dtype=np.uint64) * 99).all() and (d["pitch"] == 11).all()
         off += q
+
+
+# ---------------------------------------------------------------------------------------------
+# host logic added in round 2
+# ---------------------------------------------------------------------------------------------
+def _consumer_layout(seq_lens, region_pos, counts):
+    """The region part of prepare_inputs_labels_for_multimodal (videorefer_arch.py:291-368) on symbolic rows:
+    ('t', i) = text row i of the flattened batch, ('r', j) = flattened object-token row j, None = padding."""
+    out, off, row, obj = [], 0, 0, 0
+    for n, pos in zip(seq_lens, region_pos):
+        if not pos:                                  # no placeholder: the cursor still advances (:263-264, :300-305)
+            out.append([("t", off + i) for i in range(n)])
+            row += counts[obj]
+            obj += 1
+        else:
+            seq, last = [], 0
+            for p in pos:
+                seq += [("t", off + i) for i in range(last, p)]
+                seq += [("r", row + j) for j in range(counts[obj])]
+                row += counts[obj]
+                obj += 1
+                last = p + 1
+            seq += [("t", off + i) for i in range(last, n)]
+            out.append(seq)
+        off += n
+    l_max = max(len(x) for x in out)
+    return [x + [None] * (l_max - len(x)) for x in out], l_max
+
+
+def test_region_layout_equals_the_reference_consumer_on_symbolic_rows():
+    from hypothesis import given, settings, strategies as st
+    from ufvideo_b200.layer import RegionLayout
+
+    @settings(max_examples=150, deadline=None, derandomize=True)
+    @given(st.lists(st.tuples(st.integers(1, 12), st.lists(st.integers(0, 11), max_size=4, unique=True)), min_size=1,
+                    max_size=5), st.integers(0, 10_000))
+    def check(samples, seed):
+        seq_lens = [n for n, _ in samples]
+        region_pos = [sorted(p for p in pos if p < n) for n, pos in samples]
+        n_obj = sum(max(len(p), 1) for p in region_pos)
+        g = np.random.default_rng(seed)
+        slots = g.integers(1, 5, n_obj)
+        lay = RegionLayout(seq_lens, region_pos, slots)
+        want, l_max = _consumer_layout(seq_lens, region_pos, slots.tolist())
+        assert lay.l_max == l_max and lay.new_lens == [sum(x is not None for x in row) for row in want]
+        src = lay.src_map.reshape(len(seq_lens), l_max)
+        slot_off = np.concatenate([[0], np.cumsum(slots)])
+        dest_of_token = {int(d): r for r, d in enumerate(lay.token_row_map) if d >= 0}
+        for i, row in enumerate(want):
+            for l, cell in enumerate(row):
+                if cell is None:
+                    assert src[i, l] == -1
+                elif cell[0] == "t":
+                    assert src[i, l] == cell[1]
+                else:
+                    assert src[i, l] == -2 and dest_of_token[i * l_max + l] == cell[1]
+        # tokens of objects consumed by placeholder-less samples are dropped, all others placed exactly once
+        placed = sum(len(p) for p in region_pos)
+        assert (lay.token_row_map >= 0).sum() == sum(int(slots[o]) for o in _objects_with_placeholder(region_pos))
+        assert len(dest_of_token) == (lay.token_row_map >= 0).sum() and placed <= n_obj
+        assert slot_off[-1] == lay.token_row_map.size
+
+    check()
+
+
+def _objects_with_placeholder(region_pos):
+    objs, obj = [], 0
+    for pos in region_pos:
+        if not pos:
+            obj += 1
+        else:
+            objs += list(range(obj, obj + len(pos)))
+            obj += len(pos)
+    return objs
+
+
+def test_region_layout_rejects_inconsistent_inputs():
+    from ufvideo_b200.layer import RegionLayout
+    with pytest.raises(ValueError):
+        RegionLayout([4], [[1, 1]], [2, 2])              # duplicate placeholder
+    with pytest.raises(ValueError):
+        RegionLayout([4], [[5]], [2])                    # outside the sequence
+    with pytest.raises(ValueError):
+        RegionLayout([4, 4], [[1], [2]], [2])            # fewer objects than placeholders
+    with pytest.raises(ValueError):
+        RegionLayout([4], [[1]], [2, 2])                 # more objects than the samples consume
+
+
+def test_algorithmic_pool_bytes_counts_each_feature_row_once_per_frame():
+    """union over ALL object-frames of a feature row, however the packer grouped them."""
+    masks = [torch.zeros((70, 8, 8), dtype=torch.uint8)]
+    plan = packer.build_plan(masks, [[[0]]], 1, 4, CPU)          # 70 objects on one frame: two groups (64 + 6)
+    assert plan.n_groups == 2
+    bits = np.zeros((70, 24), np.uint32)
+    bits[:, 0] = 0b1111                                           # every object: patches 0..3
+    bits[65, 1] = 1                                               # one object of the second group: patch 32 too
+    got = packer.algorithmic_pool_bytes(plan, bits, 1152, 2)
+    assert got == 5 * 1152 * 2 + 70 * 1152 * 4 + 70 * 96

@@ -607,7 +607,7 @@ class MaskExtractor(nn.Module):
                 raise ValueError(f"text_embeds must be [rows, {hid}] of the projector dtype")
             text_embeds = text_embeds.contiguous()
             lkey = (tuple(int(n) for n in seq_lens), tuple(tuple(int(p) for p in r) for r in region_pos))
-            layouts = plan.__dict__.setdefault("_layouts", {})
+            layouts = plan.layouts
             hit = layouts.get(lkey)
             if hit is None:
                 lay = RegionLayout(seq_lens, region_pos, plan.slots)

@@ -90,6 +90,7 @@ class EncodePlan:
     plane_off: np.ndarray | None = None           # int64 [q] byte offset of its plane in that sample
     base_ptrs: tuple = ()                         # mask tensor base addresses baked into ``buffer``
     run: dict | None = None                       # run state of the latest call (introspection; layer.py)
+    layouts: dict = field(default_factory=dict)   # (seq_lens, region_pos) -> RegionLayout + its device maps (layer.forward_into)
     runs: dict = field(default_factory=dict)      # (module id, stream) -> workspace, EncodeArgs, pinned counts
                                                   # words, captured graphs of that pair (layer.py)
     keepalive: object = None                      # buffers the packer itself created for the last call (copies of
