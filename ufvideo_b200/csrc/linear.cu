@@ -249,20 +249,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = s_tmem_base;
-  // The WEIGHTS are nobody's output in this stream: the producer requests the weight halves of the first ring
-  // fill before it waits for the previous kernel (their HBM latency then runs under that kernel's tail), and
-  // only the token halves after it.
-  uint32_t pre = 0;
-  if (warp == 0 && elect_one() && int(blockIdx.x) < n_tiles) {
-    int m0, n0;
-    tile_origin(blockIdx.x, tiles_m, tiles_n, BN, m0, n0);
-    const uint32_t n_pre = uint32_t(min(Cfg::kStages, num_kb));
-    for (uint32_t kb = 0; kb < n_pre; ++kb) {
-      mbar_arrive_expect_tx(&full_bar[kb], Cfg::kStageBytes);
-      tma_load_2d(tiles + size_t(kb) * Cfg::kStageBytes + Cfg::kABytes, &tmap_w, int(kb) * kBK, n0, &full_bar[kb]);
-    }
-    pre = n_pre;
-  }
   pdl_wait();                  // x (and, transitively, the parameters) come from earlier kernels
   pdl_launch_dependents();
   // graph replay: the output pointer / all-gather destinations of this call come through the device block
@@ -281,13 +267,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* a_dst = tiles + size_t(s) * Cfg::kStageBytes;
           uint8_t* b_dst = a_dst + Cfg::kABytes;
-          if (it < pre) {              // stage opened and its weight half requested before the wait
-            tma_load_2d(a_dst, &tmap_x, kb * kBK, m0, &full_bar[s]);
-            continue;
-          }
-          mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
           tma_load_2d(a_dst, &tmap_x, kb * kBK, m0, &full_bar[s]);
           tma_load_2d(b_dst, &tmap_w, kb * kBK, n0, &full_bar[s]);

@@ -54,12 +54,11 @@ constexpr int kPoolConsumers = 2;             // dense kernel: consumer warps, 6
 constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
 constexpr int kSparseConsumers = 8;           // sparse kernel: consumer warps, 128 channels each, members interleaved
 constexpr int kSparseThreads = 32 * (kSparseConsumers + 1);
-// 288 threads at full occupancy would leave 32 registers per thread (spills in the bit-iteration loop); fewer CTAs
-// per SM with a deeper ring keep ~150 KB in flight per SM and give the compiler 40 - 75 registers.
-// More members per warp need more accumulator registers: fewer CTAs per SM, deeper rings.
+// Measured (c4 / c5-wide): seven CTAs per SM at 32 registers with a 3-stage ring (238 / 82 us) beat five CTAs at 40
+// registers with 4 stages (256 us) and three at 71 with 6 stages (111 us): what this kernel needs is warps in flight.
 template <int MPW> struct SparseCfg {
-  static constexpr int kMinCtas = MPW <= 2 ? 5 : MPW <= 4 ? 4 : 3;
-  static constexpr int kStages = MPW <= 2 ? 4 : MPW <= 4 ? 5 : 6;
+  static constexpr int kMinCtas = 7;
+  static constexpr int kStages = UFV_POOL_STAGES;
 };
 static_assert(kPoolRows == 32, "a window is one 32-bit word of the patch bitmasks");
 
@@ -390,7 +389,7 @@ template <> struct Quad<__half> {
 // that member pools (set bits of the member word, ascending) -- the accumulation order per (object, channel) is
 // the same ascending-patch sequence as in the dense kernel and in the oracle.
 template <typename T, int MPW>
-__global__ void __launch_bounds__(kSparseThreads, sizeof(T) == 4 ? (MPW <= 4 ? 3 : 2) : SparseCfg<MPW>::kMinCtas)
+__global__ void __launch_bounds__(kSparseThreads, sizeof(T) == 4 ? 4 : SparseCfg<MPW>::kMinCtas)
 mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
                         int n_patch, int c, int n_slices, const uint32_t* __restrict__ bits,
                         const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,

@@ -411,38 +411,6 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   UFV_TRACE(4);
   // ---- 2. adjacent cosine similarities: one warp per pair ----------------------------------------
   const int n_sim = t_len - 1;
-  if (staged && stage_rows >= 2) {
-    // Room for a second copy: every row is normalised ONCE, by all threads (T * C exact divisions instead of
-    // 2 * (T - 1) * C done by T - 1 warps), and the dots multiply the stored quotients -- the same rounded
-    // values in the same order, so the similarities do not change by a bit.
-    float* s_unit = s_rows + size_t(max_len) * c;
-    for (int u = tid; u < t_len * c4; u += kTtmThreads) {
-      const int t = u / c4, q = u - t * c4;
-      const float4 v = *reinterpret_cast<const float4*>(s_rows + size_t(t) * c + q * 4);
-      const float mt = s_norm[t];
-      *reinterpret_cast<float4*>(s_unit + size_t(t) * c + q * 4) =
-          make_float4(__fdiv_rn(v.x, mt), __fdiv_rn(v.y, mt), __fdiv_rn(v.z, mt), __fdiv_rn(v.w, mt));
-    }
-    __syncthreads();
-    for (int i = warp; i < n_sim; i += kTtmWarps) {
-      const float* ra = s_unit + size_t(i) * c;
-      const float* rb = ra + c;
-      float acc = 0.f;
-      for (int e0 = lane * 4; e0 < c; e0 += 128) {
-        const float4 a = *reinterpret_cast<const float4*>(ra + e0);
-        const float4 b = *reinterpret_cast<const float4*>(rb + e0);
-        acc = __fadd_rn(acc, __fmul_rn(a.x, b.x));
-        acc = __fadd_rn(acc, __fmul_rn(a.y, b.y));
-        acc = __fadd_rn(acc, __fmul_rn(a.z, b.z));
-        acc = __fadd_rn(acc, __fmul_rn(a.w, b.w));
-      }
-      acc = butterfly_sum(acc);
-      if (lane == 0) {
-        s_sim[i] = acc;
-        if (sims_out != nullptr) sims_out[size_t(o) * sims_pitch + i] = acc;
-      }
-    }
-  } else
   for (int i = warp; i < n_sim; i += kTtmWarps) {
     const float* ra = x + size_t(i) * c;
     const float* rb = ra + c;
@@ -572,9 +540,8 @@ static int launch_ttm(const float* pooled, int c, const int32_t* obj_start, cons
     const size_t small = (size_t(max_len) * 8 + size_t(len_words) * 8 + 4 + size_t(k_keep + 1) * 4 + 127) & ~size_t(127);
     const size_t rows = size_t(max_len) * c * sizeof(float);
     static const bool no_stage = getenv("UFV_TTM_NO_STAGE") != nullptr;      // developer A/B knob
-    // 0: rows stay in L2; 1: rows staged in shared memory; 2: staged + a second, normalised copy
-    const int stage_rows = no_stage || c % 4 != 0 || small + rows > kTtmMaxSmem ? 0 : small + 2 * rows <= kTtmMaxSmem ? 2 : 1;
-    const size_t smem = small + size_t(stage_rows) * rows;
+    const int stage_rows = !no_stage && c % 4 == 0 && small + rows <= kTtmMaxSmem ? 1 : 0;
+    const size_t smem = small + (stage_rows ? rows : 0);
     auto kernel = ttm_fused_kernel<T>;
     static size_t configured = 48 * 1024;     // the attribute only ever grows; a benign race sets it twice
     if (smem > configured) {
