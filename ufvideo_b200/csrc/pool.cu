@@ -52,13 +52,15 @@ static_assert(kPoolRows % 16 == 0 && kPoolRows <= 32, "stage rows: one producer 
 constexpr int kPoolStages = UFV_POOL_STAGES;
 constexpr int kPoolConsumers = 2;             // dense kernel: consumer warps, 64 channels each
 constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
-constexpr int kSparseConsumers = 8;           // sparse kernel: consumer warps, 128 channels each, members interleaved
-constexpr int kSparseThreads = 32 * (kSparseConsumers + 1);
-// Measured (c4 / c5-wide): seven CTAs per SM at 32 registers with a 3-stage ring (238 / 82 us) beat five CTAs at 40
-// registers with 4 stages (256 us) and three at 71 with 6 stages (111 us): what this kernel needs is warps in flight.
-template <int MPW> struct SparseCfg {
-  static constexpr int kMinCtas = 7;
-  static constexpr int kStages = UFV_POOL_STAGES;
+// Sparse kernel: NW consumer warps (128 channels each), member j belongs to warp j % NW, slot j / NW.  What the
+// kernel needs is warps in flight and accumulators that stay in registers: up to 32 members run 8 warps with 2 / 4
+// members each at seven CTAs per SM and 32 registers (measured on c4: 238 us, against 256 us at five CTAs with 40
+// registers and a deeper ring); 33 .. 64 members run 16 warps with 4 members each (8 members per warp at 32
+// registers keep the accumulators in local memory), three CTAs per SM with an 8-stage ring.
+template <int MPW, int NW> struct SparseCfg {
+  static constexpr int kThreads = 32 * (NW + 1);
+  static constexpr int kMinCtas = NW <= 8 ? 7 : 3;
+  static constexpr int kStages = NW <= 8 ? UFV_POOL_STAGES : 8;
 };
 static_assert(kPoolRows == 32, "a window is one 32-bit word of the patch bitmasks");
 
@@ -384,18 +386,18 @@ template <> struct Quad<__half> {
 };
 
 // ---- many objects on a frame: bit-iterating consumers ------------------------------------------------------
-// MPW = members per consumer warp (member j belongs to warp j % 8, its slot there is j / 8): 2 / 4 / 8 for groups of
-// up to 16 / 32 / 64 members.  A warp visits, per staged 32-row chunk and per member it owns, exactly the rows
+// MPW = members per consumer warp, NW = consumer warps (member j belongs to warp j % NW, its slot there is j / NW):
+// 2 x 8, 4 x 8, 4 x 16 for groups of up to 16 / 32 / 64 members.  A warp visits, per staged 32-row chunk and per member it owns, exactly the rows
 // that member pools (set bits of the member word, ascending) -- the accumulation order per (object, channel) is
 // the same ascending-patch sequence as in the dense kernel and in the oracle.
-template <typename T, int MPW>
-__global__ void __launch_bounds__(kSparseThreads, sizeof(T) == 4 ? 4 : SparseCfg<MPW>::kMinCtas)
+template <typename T, int MPW, int NW>
+__global__ void __launch_bounds__(SparseCfg<MPW, NW>::kThreads, sizeof(T) == 4 ? (NW <= 8 ? 4 : 1) : SparseCfg<MPW, NW>::kMinCtas)
 mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
                         int n_patch, int c, int n_slices, const uint32_t* __restrict__ bits,
                         const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,
                         const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member, int tile_min,
                         float* __restrict__ pooled) {
-  constexpr int S = SparseCfg<MPW>::kStages, R = kPoolRows, NW = kSparseConsumers, PM = MPW * NW;
+  constexpr int S = SparseCfg<MPW, NW>::kStages, R = kPoolRows, PM = MPW * NW, kSparseThreads = SparseCfg<MPW, NW>::kThreads;
   extern __shared__ __align__(1024) uint8_t dyn_smem[];
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
   __shared__ uint32_t s_bits[PM][UFV_BITS_WORDS];                          // members' patch bitmasks
@@ -654,11 +656,12 @@ static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
                     a.grp_off, a.grp_member, a.tile_min, a.pooled));
 }
 
-template <typename T, int MPW>
+template <typename T, int MPW, int NW>
 static int launch_pool_sparse(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a, cudaStream_t stream) {
   const int n_slices = (a.c + kPoolCh - 1) / kPoolCh;
-  const size_t smem = size_t(SparseCfg<MPW>::kStages) * kPoolRows * kPoolCh * sizeof(T);
-  auto kernel = mask_pool_sparse_kernel<T, MPW>;
+  const size_t smem = size_t(SparseCfg<MPW, NW>::kStages) * kPoolRows * kPoolCh * sizeof(T);
+  constexpr int kSparseThreads = SparseCfg<MPW, NW>::kThreads;
+  auto kernel = mask_pool_sparse_kernel<T, MPW, NW>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -676,9 +679,9 @@ static int dispatch_group(int max_group, const CUtensorMap& tmap, int use_tmap, 
                           cudaStream_t stream) {
   if (max_group <= 4) return launch_pool<T, 4>(tmap, use_tmap, a, stream);
   if (max_group <= 8) return launch_pool<T, 8>(tmap, use_tmap, a, stream);
-  if (max_group <= 16) return launch_pool_sparse<T, 2>(tmap, use_tmap, a, stream);
-  if (max_group <= 32) return launch_pool_sparse<T, 4>(tmap, use_tmap, a, stream);
-  return launch_pool_sparse<T, 8>(tmap, use_tmap, a, stream);
+  if (max_group <= 16) return launch_pool_sparse<T, 2, 8>(tmap, use_tmap, a, stream);
+  if (max_group <= 32) return launch_pool_sparse<T, 4, 8>(tmap, use_tmap, a, stream);
+  return launch_pool_sparse<T, 4, 16>(tmap, use_tmap, a, stream);
 }
 
 // ---- adjoint of the mask pool (training) --------------------------------------------
