@@ -53,10 +53,10 @@ constexpr int kPoolStages = UFV_POOL_STAGES;
 constexpr int kPoolConsumers = 2;             // dense kernel: consumer warps, 64 channels each
 constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
 // Sparse kernel: NW consumer warps (128 channels each), member j belongs to warp j % NW, slot j / NW.  What the
-// kernel needs is warps in flight and accumulators that stay in registers: up to 32 members run 8 warps with 2 / 4
-// members each at seven CTAs per SM and 32 registers (measured on c4: 238 us, against 256 us at five CTAs with 40
-// registers and a deeper ring); 33 .. 64 members run 16 warps with 4 members each (8 members per warp at 32
-// registers keep the accumulators in local memory), three CTAs per SM with an 8-stage ring.
+// kernel needs is warps in flight: 8 warps with 2 / 4 / 8 members each at seven CTAs per SM and 32 registers
+// (measured on c4: 238 us, against 256 us at five CTAs with 40 registers and a deeper ring; on c5-wide, 64 members:
+// 82 us with 8 x 8 at seven CTAs -- accumulators partly in local memory -- against 103 us with 16 warps x 4 members at
+// three CTAs and an 8-stage ring, and 111 us with 8 x 8 at three CTAs and 71 registers).
 template <int MPW, int NW> struct SparseCfg {
   static constexpr int kThreads = 32 * (NW + 1);
   static constexpr int kMinCtas = NW <= 8 ? 7 : 3;
@@ -387,7 +387,7 @@ template <> struct Quad<__half> {
 
 // ---- many objects on a frame: bit-iterating consumers ------------------------------------------------------
 // MPW = members per consumer warp, NW = consumer warps (member j belongs to warp j % NW, its slot there is j / NW):
-// 2 x 8, 4 x 8, 4 x 16 for groups of up to 16 / 32 / 64 members.  A warp visits, per staged 32-row chunk and per member it owns, exactly the rows
+// 2 x 8, 4 x 8, 8 x 8 for groups of up to 16 / 32 / 64 members.  A warp visits, per staged 32-row chunk and per member it owns, exactly the rows
 // that member pools (set bits of the member word, ascending) -- the accumulation order per (object, channel) is
 // the same ascending-patch sequence as in the dense kernel and in the oracle.
 template <typename T, int MPW, int NW>
@@ -402,8 +402,6 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
   T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
   __shared__ uint32_t s_bits[PM][UFV_BITS_WORDS];                          // members' patch bitmasks
   __shared__ uint32_t s_union[UFV_BITS_WORDS];
-  __shared__ uint32_t s_chunk[UFV_BITS_WORDS];                             // chunk table of the frame
-  __shared__ int s_n_chunks;
   __shared__ __align__(8) uint64_t full_bar[S];
   __shared__ __align__(8) uint64_t empty_bar[S];
 
@@ -440,36 +438,25 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     s_union[tid] = u;
   }
   __syncthreads();
+  // (No packed path here: with 9 .. 64 objects on a frame the union is rarely thin, and the packing code's registers
+  // would push this instruction-bound kernel's hot loop into local memory at the 32 registers seven CTAs per SM allow.)
   const int n_win = (n_patch + R - 1) / R;
-  if (tid == 0) s_n_chunks = plan_frame(s_union, n_win, n_patch, use_tmap, tile_min, s_chunk);
-  __syncthreads();
-  const int n_chunks = s_n_chunks;                             // 0: direct path (one stage per non-empty window)
   const int slice_ch = min(kPoolCh, c - ch0);
 
   if (warp == NW) {
     // ---------------- producer warp ---------------------------------------------------------------------
     const int64_t row_base = int64_t(row) * n_patch;
     const uint32_t slice_bytes = uint32_t(slice_ch) * sizeof(T);
-    if (n_chunks == 0) {
-      int k = 0;
-      for (int win = 0; win < n_win; ++win) {
-        const uint32_t u = s_union[win];
-        if (u == 0u) continue;
-        const int s = k % S;
-        const uint32_t ph = (k / S) & 1;
-        ++k;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
-                          ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
-      }
-    }
-    for (int k = 0; k < n_chunks; ++k) {
-      const PoolChunk ch = unpack_chunk(s_chunk[k]);
+    int k = 0;
+    for (int win = 0; win < n_win; ++win) {
+      const uint32_t u = s_union[win];
+      if (u == 0u) continue;
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
+      ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      produce_chunk<T>(&tmap, feats, row_base, c, ch0, slice_bytes, ch, s_union, ring + size_t(s) * R * kPoolCh,
-                       &full_bar[s], lane);
+      produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
+                        ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
     }
   } else {
     // ---------------- consumer warps: members warp, warp + 8, ..., all 128 channels, 4 per lane -------------
@@ -478,75 +465,27 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
     for (int mi = 0; mi < MPW; ++mi) acc[mi] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int my_ch = lane * 4;
     const bool live = my_ch < slice_ch;
-    if (n_chunks == 0) {
-      // direct path: one stage per non-empty window, patch 32 win + r in slot r -- the tight loop (this kernel is
-      // bound by its instruction count)
-      int k = 0;
-      for (int win = 0; win < n_win; ++win) {
-        if (s_union[win] == 0u) continue;
-        const int s = k % S;
-        const uint32_t ph = (k / S) & 1;
-        ++k;
-        mbar_wait(&full_bar[s], ph);
-        const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
-#pragma unroll
-        for (int mi = 0; mi < MPW; ++mi) {
-          uint32_t word = s_bits[mi * NW + warp][win];       // warp-uniform: the rows of this window the member pools
-          while (word != 0u) {
-            const int r = __ffs(word) - 1;
-            word &= word - 1u;
-            const float4 f = Quad<T>::load(src + r * kPoolCh);
-            float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
-            add2(lo, make_float2(f.x, f.y));
-            add2(hi, make_float2(f.z, f.w));
-            acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-      }
-    }
-    for (int k = 0; k < n_chunks; ++k) {
-      const PoolChunk ch = unpack_chunk(s_chunk[k]);
+    // one stage per non-empty window, patch 32 win + r in slot r -- the tight loop (this kernel is bound by its
+    // instruction count)
+    int k = 0;
+    for (int win = 0; win < n_win; ++win) {
+      if (s_union[win] == 0u) continue;
       const int s = k % S;
       const uint32_t ph = (k / S) & 1;
+      ++k;
       mbar_wait(&full_bar[s], ph);
       const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
-      if (ch.tile) {
-        // one window, patch 32 w0 + r in slot r: the tight loop (the kernel is bound by its instruction count)
 #pragma unroll
-        for (int mi = 0; mi < MPW; ++mi) {
-          uint32_t word = s_bits[mi * NW + warp][ch.w0];     // warp-uniform: the rows of this window the member pools
-          while (word != 0u) {
-            const int r = __ffs(word) - 1;
-            word &= word - 1u;
-            const float4 f = Quad<T>::load(src + r * kPoolCh);
-            float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
-            add2(lo, make_float2(f.x, f.y));
-            add2(hi, make_float2(f.z, f.w));
-            acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
-          }
-        }
-      } else {
-        // several sparse windows packed into the stage: slot = rank of the patch among the chunk's needed rows
-        int base = 0;
-        for (int w = ch.w0; w < ch.w1; ++w) {
-          const uint32_t u = s_union[w];
-          if (u == 0u) continue;
-#pragma unroll
-          for (int mi = 0; mi < MPW; ++mi) {
-            uint32_t word = s_bits[mi * NW + warp][w];
-            while (word != 0u) {
-              const int r = __ffs(word) - 1;
-              word &= word - 1u;
-              const float4 f = Quad<T>::load(src + packed_slot(base, u, r) * kPoolCh);
-              float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
-              add2(lo, make_float2(f.x, f.y));
-              add2(hi, make_float2(f.z, f.w));
-              acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
-            }
-          }
-          base += __popc(u);
+      for (int mi = 0; mi < MPW; ++mi) {
+        uint32_t word = s_bits[mi * NW + warp][win];         // warp-uniform: the rows of this window the member pools
+        while (word != 0u) {
+          const int r = __ffs(word) - 1;
+          word &= word - 1u;
+          const float4 f = Quad<T>::load(src + r * kPoolCh);
+          float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
+          add2(lo, make_float2(f.x, f.y));
+          add2(hi, make_float2(f.z, f.w));
+          acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
       }
       __syncwarp();
@@ -681,7 +620,7 @@ static int dispatch_group(int max_group, const CUtensorMap& tmap, int use_tmap, 
   if (max_group <= 8) return launch_pool<T, 8>(tmap, use_tmap, a, stream);
   if (max_group <= 16) return launch_pool_sparse<T, 2, 8>(tmap, use_tmap, a, stream);
   if (max_group <= 32) return launch_pool_sparse<T, 4, 8>(tmap, use_tmap, a, stream);
-  return launch_pool_sparse<T, 4, 16>(tmap, use_tmap, a, stream);
+  return launch_pool_sparse<T, 8, 8>(tmap, use_tmap, a, stream);
 }
 
 // ---- adjoint of the mask pool (training) --------------------------------------------
