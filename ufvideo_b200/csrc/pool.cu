@@ -55,11 +55,11 @@ constexpr int kPoolThreads = 32 * (kPoolConsumers + 1);
 // Sparse kernel: NW consumer warps (128 channels each), member j belongs to warp j % NW, slot j / NW.  What the
 // kernel needs is warps in flight: 8 warps with 2 / 4 / 8 members each at seven CTAs per SM and 32 registers
 // (measured on c4: 238 us, against 256 us at five CTAs with 40 registers and a deeper ring; on c5-wide, 64 members:
-// 82 us with 8 x 8 at seven CTAs -- accumulators partly in local memory -- against 103 us with 16 warps x 4 members at
-// three CTAs and an 8-stage ring, and 111 us with 8 x 8 at three CTAs and 71 registers).
+// 82 us with 8 x 8 at four to five CTAs and ~50 registers, 123 us at seven CTAs with the accumulators in local
+// memory, 103 us with 16 warps x 4 members at three CTAs and an 8-stage ring, 111 us with 8 x 8 at three CTAs).
 template <int MPW, int NW> struct SparseCfg {
   static constexpr int kThreads = 32 * (NW + 1);
-  static constexpr int kMinCtas = NW <= 8 ? 7 : 3;
+  static constexpr int kMinCtas = NW > 8 ? 3 : MPW <= 4 ? 7 : 4;   // 8 members per warp: 32 accumulator registers alone
   static constexpr int kStages = NW <= 8 ? UFV_POOL_STAGES : 8;
 };
 static_assert(kPoolRows == 32, "a window is one 32-bit word of the patch bitmasks");
