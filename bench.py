@@ -39,6 +39,10 @@ METRIC = "object_frames_per_s"
 UNIT = "object-frames/s"
 WORKLOAD = dict(clips_per_gpu=8, frames=16, objects=4, k=8, family="dense", mask_hw=(384, 384))
 L2_BYTES = 126 * 1024 * 1024
+# result collection at N > 1: "push" (side-stream peer push, overlapped with the next step), "fused" (stores fused into
+# the last Linear's epilogue: lowest latency for one step, but the NVLink transfer sits on the stream's critical
+# path), "nccl" (one asynchronous all-gather per step), "none"; UFV_BENCH_GATHER overrides
+GATHER_DEFAULT = "push"
 
 
 def parse_args():
@@ -372,7 +376,11 @@ def run_sweep(enc, dev, rank, world, peak, steps=10, warmup=3):
                 enc(feats, masks, None, ann, None)
                 return
             peer, tok_view, cnt_view, s = pg.begin(slots)
-            enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
+            if os.environ.get("UFV_BENCH_GATHER", GATHER_DEFAULT) == "push":
+                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view)
+                pg.push(s, peer, int(slots.sum()))
+            else:
+                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
             last[0] = s
 
         def sharded():
@@ -460,16 +468,23 @@ def run_ours(a):
     slots = packer.build_plan(masks_dev, ann, feats_dev.shape[0], k, dev).slots
     pending = collections.deque()
     pg, gather_kind = None, "none (1 GPU)"
+    push_mode = os.environ.get("UFV_BENCH_GATHER", GATHER_DEFAULT) == "push"
+    m_pad_rows = int(slots.sum())
     if world > 1:
         # Preferred: the all-gather fused into the last Linear (ufv_linear_gather): its epilogue stores
         # every tile into all ranks' gathered buffers over NVLink.  UFV_BENCH_GATHER=nccl (or a failed
         # symmetric-memory rendezvous) falls back to one asynchronous NCCL all-gather of the payload.
-        if os.environ.get("UFV_BENCH_GATHER", "fused") not in ("nccl", "none"):
+        if os.environ.get("UFV_BENCH_GATHER", GATHER_DEFAULT) not in ("nccl", "none"):
             try:
                 pg = sharding.PeerGather(pad_rows, pad_objs, 3584, torch.bfloat16, dev)
-                gather_kind = ("fused into the last Linear: tcgen05 epilogue stores tiles to every rank over NVLink ("
-                               + ("multimem.st via NVSwitch multicast" if pg.multimem else "one st per peer")
-                               + "), arrival flags, no NCCL on the data path")
+                how = "multimem.st via NVSwitch multicast" if pg.multimem else "one st per peer"
+                if push_mode:
+                    gather_kind = ("peer push: the last Linear writes this rank's rows into its slice of the symmetric "
+                                   f"buffer, a side-stream kernel (ufv_peer_push) stores them to every rank over NVLink ({how}), "
+                                   "arrival flags, overlapped with the next step, no NCCL on the data path")
+                else:
+                    gather_kind = (f"fused into the last Linear: tcgen05 epilogue stores tiles to every rank over NVLink ({how}), "
+                                   "arrival flags, no NCCL on the data path")
             except Exception as exc:   # noqa: BLE001 -- report and fall back
                 print(f"[bench] symmetric-memory gather unavailable ({exc!r}); using NCCL", file=sys.stderr)
         if pg is None:
@@ -479,7 +494,11 @@ def run_ours(a):
     def gather_step(feats, masks):
         if pg is not None:
             peer, tok_view, cnt_view, step = pg.begin(slots)
-            enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
+            if push_mode:
+                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view)
+                pg.push(step, peer, m_pad_rows)
+            else:
+                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
             pending.append(step)
             while len(pending) > 1:
                 pending.popleft()
@@ -633,7 +652,7 @@ def run_ours(a):
                                      "structure and the captured launch sequence (CUDA graph) are reused across steps")},
         "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-        "gpu_launches": (6 if pg is not None else 5) * a.steps,   # kernels 1, 2, 3, 4a, 4b (+ flag wait)
+        "gpu_launches": (6 if pg is not None else 5) * a.steps,   # kernels 1, 2, 3, 4a, 4b (+ peer push / flag wait)
         "roofline": {"kernel": "mask_pool_kernel<bf16>", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": pool_bytes, "us_per_launch": ms_pool * 1e3,

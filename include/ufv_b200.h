@@ -234,6 +234,12 @@ typedef struct ufv_peer_args {
 int ufv_linear_gather(const void* x, const void* w, const void* bias, int m, int n, int k, int dtype,
                       const ufv_peer_args* peer_host, void* ws, int64_t ws_bytes, void* stream);
 
+/* The same collection as a separate step: push `bytes` (multiple of 16) starting at `src` -- rows the last Linear
+ * wrote locally, normally this rank's own slice of the symmetric gathered buffer -- to every peer->dst, forward the
+ * tail and raise the flags exactly as ufv_linear_gather does.  Launched on a side stream it takes the NVLink
+ * transfer (world x payload per link and step) off the compute stream's critical path. */
+int ufv_peer_push(const void* src, int64_t bytes, const ufv_peer_args* peer_host, void* stream);
+
 /* Block the stream until flags[0 .. n) (int32, local memory) have all reached `value` (>=, acquire.sys
  * loads; step counters only grow).  Gives up after ~timeout_ms (0 = 2000) and stores 1 to *timed_out
  * (optional int32 in device memory or device-mapped pinned host memory, where the host can poll it

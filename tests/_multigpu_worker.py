@@ -2,8 +2,9 @@
 
 Checks, on every rank:
   1. the all-gather fused into the last Linear (PeerGather: multimem.st over NVSwitch multicast when the
-     fabric offers it, one st per peer otherwise) delivers bit-identical gathered buffers to an NCCL
-     all-gather of the same payload, over several steps with different data and ragged shards;
+     fabric offers it, one st per peer otherwise) and its side-stream variant (PeerGather.push of locally written
+     rows) deliver bit-identical gathered buffers to an NCCL all-gather of the same payload, over several steps
+     with different data and ragged / empty shards;
   2. world-size invariance: tokens and counts gathered from the clip-sharded run
      equal, bit for bit, what ONE GPU computes for the union of the clips.
 Exit code 0 and a line "MULTIGPU OK" on rank 0 mean success.
@@ -60,9 +61,13 @@ def main():
             ft = torch.from_numpy(feats).to(dev).bfloat16()
             md = [torch.from_numpy(m).to(dev) for m in masks]
             slots = packer.build_plan(md, ann, ft.shape[0], K, dev).slots
-            # (1) fused gather
+            # (1) fused gather (even steps) / side-stream peer push of locally written rows (odd steps)
             peer, tok_view, cnt_view, s = pg.begin(slots)
-            enc.forward_padded(ft, md, ann, out=tok_view, counts_out=cnt_view, peer=peer)
+            if step % 2 == 0:
+                enc.forward_padded(ft, md, ann, out=tok_view, counts_out=cnt_view, peer=peer)
+            else:
+                enc.forward_padded(ft, md, ann, out=tok_view, counts_out=cnt_view)
+                pg.push(s, peer, int(slots.sum()))
             pg.wait(s)
             fused = pg.gathered(s).clone()
             # (2) NCCL all-gather of the same payload

@@ -90,6 +90,7 @@ _SIGNATURES = {
     "ufv_splice_static": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _i64, _p]),
     "ufv_linear_gather": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PeerArgs), _p, _i64,
                                     _p]),
+    "ufv_peer_push": (C.c_int, [_p, _i64, C.POINTER(PeerArgs), _p]),
     "ufv_wait_flags": (C.c_int, [_p, C.c_int, _i32, C.c_int, _p, _p]),
     "ufv_encode_graph_create": (C.c_int, [C.POINTER(EncodeArgs), C.POINTER(_p)]),
     "ufv_encode_graph_launch": (C.c_int, [_p, _p]),

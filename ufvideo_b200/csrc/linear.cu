@@ -649,6 +649,25 @@ __global__ void peer_tail_only_kernel(const __grid_constant__ ufv_peer_args peer
   }
 }
 
+// ---- the same collection as a separate push, for callers that want it OFF the critical path --------------------
+// With the stores fused into the last Linear, a rank's stream cannot move on before its 8 copies have crossed
+// NVLink (a kernel is complete only when its stores are): at 8 GPUs every link has to absorb 8 x 1.8 MB per step,
+// ~20 us that the next step's kernels -- which do not touch NVLink -- could be running under.  This kernel pushes
+// rows the Linear wrote LOCALLY (this rank's slice of the symmetric buffer) to every destination and closes with
+// the same protocol; launched on a side stream it overlaps the next step.  A few CTAs saturate the link.
+__global__ void __launch_bounds__(kGemmThreads)
+peer_push_kernel(const uint4* __restrict__ src, long long n_vec, const __grid_constant__ ufv_peer_args peer) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const bool mm = peer.multimem != 0;
+  const uint64_t dst0 = peer.dst[0];
+  const long long stride = (long long)gridDim.x * kGemmThreads;
+  for (long long i = (long long)blockIdx.x * kGemmThreads + threadIdx.x; i < n_vec; i += stride)
+    peer_store16(peer, mm, dst0, size_t(i) * 16, __ldcg(src + i));
+  __syncthreads();
+  peer_finish(peer, gridDim.x);
+}
+
 // ---- receiver side of the fused all-gather: spin until every rank's flag has reached `value` ---------
 __global__ void wait_flags_kernel(const int32_t* __restrict__ flags, int n, int32_t value, long long timeout_ns,
                                   int32_t* __restrict__ timed_out) {
@@ -1111,6 +1130,22 @@ extern "C" int ufv_linear_gather(const void* x, const void* w, const void* bias,
   if (dtype == UFV_BF16)
     return dispatch_tc<__nv_bfloat16>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, nullptr, st);
   return dispatch_tc<__half>(x, w, bias, nullptr, m, n, k, 0, peer, nullptr, ws, ws_bytes, nullptr, st);
+}
+
+extern "C" int ufv_peer_push(const void* src, int64_t bytes, const ufv_peer_args* peer, void* stream) {
+  using namespace ufv;
+  UFV_REQUIRE(peer != nullptr && bytes >= 0 && bytes % 16 == 0, UFV_E_SHAPE, "ufv_peer_push: bytes=%lld", (long long)bytes);
+  UFV_REQUIRE(bytes == 0 || (src != nullptr && aligned16(src)), UFV_E_NULL, "ufv_peer_push: src is null or unaligned");
+  UFV_REQUIRE(peer->n_dst >= 1 && peer->n_dst <= UFV_MAX_PEER_DST && (!peer->multimem || peer->n_dst == 1),
+              UFV_E_SHAPE, "ufv_peer_push: n_dst=%d multimem=%d", peer->n_dst, peer->multimem);
+  UFV_REQUIRE(peer->ticket != nullptr && (peer->tail_words == 0 || peer->tail_src != nullptr), UFV_E_NULL,
+              "ufv_peer_push: ticket / tail_src is null");
+  const long long n_vec = bytes / 16;
+  long long ctas = (n_vec + kGemmThreads * 8 - 1) / (kGemmThreads * 8);      // >= 8 vectors per thread
+  ctas = ctas < 1 ? 1 : ctas > 16 ? 16 : ctas;
+  return check_launch("ufv_peer_push",
+                      launch_kernel(peer_push_kernel, dim3(unsigned(ctas)), dim3(kGemmThreads), 0,
+                                    static_cast<cudaStream_t>(stream), static_cast<const uint4*>(src), n_vec, *peer));
 }
 
 extern "C" int ufv_wait_flags(const int32_t* flags, int n, int32_t value, int timeout_ms, int32_t* timed_out,

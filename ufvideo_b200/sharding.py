@@ -200,6 +200,7 @@ class PeerGather:
         self.step = 0
         self._wait_fn = _cabi.lib().ufv_wait_flags
         self._flags_ptr, self._timed_out_ptr = self.flags.data_ptr(), self._timed_out_dev
+        self._side = None                         # side stream + events of push(), created on first use
         self._static = {}                         # slot -> (slots bytes, tokens view, counts view)
         self._args = [self._make_args(s) for s in range(ring)]
 
@@ -246,6 +247,23 @@ class PeerGather:
         a = self._args[slot]
         a.flag_value = step + 1
         return a, cached[1], cached[2], step
+
+    def push(self, step: int, peer, n_rows: int) -> None:
+        """Collection off the critical path: the last Linear wrote this rank's rows LOCALLY (``out=`` the tokens view
+        ``begin`` returned, no ``peer=``); push them, the tail and the arrival flag to every rank from a side stream,
+        ordered after what the current stream has enqueued so far.  The current stream does not wait for NVLink."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+            self._events = [torch.cuda.Event() for _ in range(self.ring)]
+            self._push_fn = _cabi.lib().ufv_peer_push
+        slot = step % self.ring
+        ev = self._events[slot]
+        ev.record(torch.cuda.current_stream(self.device))
+        self._side.wait_event(ev)
+        src = self.buf.data_ptr() + (slot * self.world + self.rank) * self.rows * self._row_bytes()
+        rc = self._push_fn(src, n_rows * self._row_bytes(), ctypes.byref(peer), self._side.cuda_stream)
+        if rc:
+            _cabi.check(rc)
 
     def wait(self, step: int) -> None:
         """Make the current stream wait until every rank's rows of ``step`` are in this rank's copy.
