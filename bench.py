@@ -377,8 +377,8 @@ def run_sweep(enc, dev, rank, world, peak, steps=10, warmup=3):
                 return
             peer, tok_view, cnt_view, s = pg.begin(slots)
             if os.environ.get("UFV_BENCH_GATHER", GATHER_DEFAULT) == "push":
-                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view)
-                pg.push(s, peer, int(slots.sum()))
+                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view,
+                                   after_enqueue=lambda: pg.push(s, peer, int(slots.sum())))
             else:
                 enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
             last[0] = s
@@ -494,9 +494,9 @@ def run_ours(a):
     def gather_step(feats, masks):
         if pg is not None:
             peer, tok_view, cnt_view, step = pg.begin(slots)
-            if push_mode:
-                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view)
-                pg.push(step, peer, m_pad_rows)
+            if push_mode:      # the push is enqueued while the host would otherwise idle waiting for the counts
+                enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view,
+                                   after_enqueue=lambda: pg.push(step, peer, m_pad_rows))
             else:
                 enc.forward_padded(feats, masks, ann, out=tok_view, counts_out=cnt_view, peer=peer)
             pending.append(step)

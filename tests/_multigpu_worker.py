@@ -66,8 +66,8 @@ def main():
             if step % 2 == 0:
                 enc.forward_padded(ft, md, ann, out=tok_view, counts_out=cnt_view, peer=peer)
             else:
-                enc.forward_padded(ft, md, ann, out=tok_view, counts_out=cnt_view)
-                pg.push(s, peer, int(slots.sum()))
+                enc.forward_padded(ft, md, ann, out=tok_view, counts_out=cnt_view,
+                                   after_enqueue=lambda: pg.push(s, peer, int(slots.sum())))
             pg.wait(s)
             fused = pg.gathered(s).clone()
             # (2) NCCL all-gather of the same payload

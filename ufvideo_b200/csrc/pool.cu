@@ -237,12 +237,24 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   const int m0 = grp_off[g];
   const int n_mem = grp_off[g + 1] - m0;
   const int row = grp_row[g];
+  // 8 members x 24 words = 192 bitmask words for 96 threads: each thread's two member indices are plan data too
+  constexpr int kBitLoads = (8 * UFV_BITS_WORDS + kPoolThreads - 1) / kPoolThreads;
+  int member_row[kBitLoads];
+#pragma unroll
+  for (int j = 0; j < kBitLoads; ++j) {
+    const int o = (tid + j * kPoolThreads) / UFV_BITS_WORDS;
+    member_row[j] = o < n_mem && o < 8 ? grp_member[m0 + o] : -1;
+  }
   __syncthreads();
   pdl_wait();                  // patch bitmasks and counts come from kernel 1
   pdl_launch_dependents();
-  for (int i = tid; i < 8 * UFV_BITS_WORDS; i += kPoolThreads) {
-    const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
-    s_bits[o][w] = o < n_mem ? bits[size_t(grp_member[m0 + o]) * UFV_BITS_WORDS + w] : 0u;
+#pragma unroll
+  for (int j = 0; j < kBitLoads; ++j) {
+    const int i = tid + j * kPoolThreads;
+    if (i < 8 * UFV_BITS_WORDS) {
+      const int o = i / UFV_BITS_WORDS, w = i - o * UFV_BITS_WORDS;
+      s_bits[o][w] = member_row[j] >= 0 ? bits[size_t(member_row[j]) * UFV_BITS_WORDS + w] : 0u;
+    }
   }
   __syncthreads();
   if (tid < UFV_BITS_WORDS) {

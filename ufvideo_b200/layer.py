@@ -567,12 +567,17 @@ class MaskExtractor(nn.Module):
             return torch.cuda.device(dev)
         return _NULL_CONTEXT
 
-    def forward_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None):
+    def forward_padded(self, feats, masks, ann_indices, out=None, counts_out=None, peer=None, after_enqueue=None):
         """forward() without the compaction: (tokens [m_pad, hidden] with object o's rows at
         plan.host['slot_off'][o], region_token_nums as an int32 numpy array read back from the merge
-        kernel, plan).  What the clip-sharded driver gathers (sharding.all_gather_payload)."""
+        kernel, plan).  What the clip-sharded driver gathers (sharding.all_gather_payload).
+        ``after_enqueue`` (optional callable) runs right after the kernels have been enqueued and before the
+        host starts waiting for the counts -- ~60 us in which the host is otherwise idle, e.g. to enqueue the
+        side-stream push of the result (sharding.PeerGather.push) without delaying the next call."""
         with self._on_module_device():
             tokens, counts, plan = self.encode_padded(feats, masks, ann_indices, out, counts_out, peer, _awaited=True)
+            if after_enqueue is not None:
+                after_enqueue()
             run = self._last_run
             if run.get("args") is not None and plan.n_obj > 0:
                 return tokens, _await_counts(plan, run, tokens.device), plan
