@@ -28,6 +28,7 @@ CONFIGS = {
     "c4": (2, 256, 16, "blob", False, "configs[3]: 2 clips x 256 frames x 16 objects (merge-heavy, r = 248)"),
     "c5-small": (16, 8, 1, "blob", False, "configs[4] corner: 16 clips x 8 frames x 1 object"),
     "c5-wide": (1, 64, 64, "blob", True, "configs[4] corner: 1 clip x 64 frames x 64 objects, ragged T_o"),
+    "c5-mid": (2, 64, 32, "blob", True, "configs[4] interior: 2 clips x 64 frames x 32 objects, ragged T_o"),
     "c5-long": (1, 512, 4, "dense", False, "configs[4] corner: 1 clip x 512 frames x 4 objects"),
 }
 

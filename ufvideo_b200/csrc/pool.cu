@@ -61,6 +61,11 @@ template <int MPW, int NW> struct SparseCfg {
   static constexpr int kThreads = 32 * (NW + 1);
   static constexpr int kMinCtas = NW > 8 ? 3 : MPW <= 4 ? 7 : 4;   // 8 members per warp: 32 accumulator registers alone
   static constexpr int kStages = NW <= 8 ? UFV_POOL_STAGES : 8;
+  // 256-channel slices (16-bit features, up to 32 members).  Measured on c4 (16 members) and on 2 x 64 frames x 32
+  // members, stages x CTAs per SM: 2 members per warp  3x4 210 us, 2x5 213, 2x6 201 (32 registers, 16 B of spill),
+  // 4x3 236;  4 members per warp  3x4 92.6 us, 4x3 86.4 (64 registers), 2x5 102, 2x6 232 (spills in the loop).
+  static constexpr int kWideStages = MPW <= 2 ? 2 : 4;
+  static constexpr int kWideCtas = MPW <= 2 ? 6 : 3;
 };
 static_assert(kPoolRows == 32, "a window is one 32-bit word of the patch bitmasks");
 
@@ -133,20 +138,20 @@ __device__ __forceinline__ int plan_frame(const uint32_t* s_union, int n_win, in
 
 // Direct path, per non-empty window: the producer warp's part.  `u` = union word of the window (bit r = patch
 // 32 * win + r is needed by some member; it sits in slot r of the stage).
-template <typename T>
+template <typename T, int CH = kPoolCh>
 __device__ __forceinline__ void produce_window(const CUtensorMap* tmap, int use_tmap, const T* __restrict__ feats,
                                                int64_t row_base, int c, int ch0, uint32_t slice_bytes, int win,
                                                int n_patch, uint32_t u, int tile_min, T* dst, uint64_t* full_bar,
                                                int lane) {
   const bool tile = window_is_tile(win, u, n_patch, use_tmap, tile_min);
   if (lane == 0) {
-    mbar_arrive_expect_tx(full_bar, tile ? uint32_t(kPoolRows) * kPoolCh * sizeof(T) : uint32_t(__popc(u)) * slice_bytes);
+    mbar_arrive_expect_tx(full_bar, tile ? uint32_t(kPoolRows) * CH * sizeof(T) : uint32_t(__popc(u)) * slice_bytes);
     if (tile) tma_load_2d(dst, tmap, ch0, int(row_base + 32 * win), full_bar);
   }
   if (!tile) {
     __syncwarp();
     if ((u >> lane) & 1u)
-      bulk_g2s(dst + lane * kPoolCh, feats + (row_base + 32 * win + lane) * int64_t(c) + ch0, slice_bytes, full_bar);
+      bulk_g2s(dst + lane * CH, feats + (row_base + 32 * win + lane) * int64_t(c) + ch0, slice_bytes, full_bar);
   }
 }
 
@@ -376,24 +381,45 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T
   }
 }
 
-// four adjacent channels of one staged row -> fp32 quad
-template <typename T> struct Quad;
-template <> struct Quad<float> {
-  __device__ static float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
-};
-template <> struct Quad<__nv_bfloat16> {
-  __device__ static float4 load(const __nv_bfloat16* p) {
-    const uint2 r = *reinterpret_cast<const uint2*>(p);
-    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
-                       __uint_as_float(r.y & 0xffff0000u));
+// VEC adjacent channels of one staged row -> fp32 pairs
+template <typename T, int VEC> struct Lanes;
+template <> struct Lanes<float, 4> {
+  __device__ static void load(const float* p, float2 (&f)[2]) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    f[0] = make_float2(r.x, r.y);
+    f[1] = make_float2(r.z, r.w);
   }
 };
-template <> struct Quad<__half> {
-  __device__ static float4 load(const __half* p) {
+template <> struct Lanes<__nv_bfloat16, 4> {
+  __device__ static void load(const __nv_bfloat16* p, float2 (&f)[2]) {
     const uint2 r = *reinterpret_cast<const uint2*>(p);
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-    return make_float4(a.x, a.y, b.x, b.y);
+    f[0] = Pair<__nv_bfloat16>::cvt(r.x);
+    f[1] = Pair<__nv_bfloat16>::cvt(r.y);
+  }
+};
+template <> struct Lanes<__half, 4> {
+  __device__ static void load(const __half* p, float2 (&f)[2]) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    f[0] = Pair<__half>::cvt(r.x);
+    f[1] = Pair<__half>::cvt(r.y);
+  }
+};
+template <> struct Lanes<__nv_bfloat16, 8> {
+  __device__ static void load(const __nv_bfloat16* p, float2 (&f)[4]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    f[0] = Pair<__nv_bfloat16>::cvt(r.x);
+    f[1] = Pair<__nv_bfloat16>::cvt(r.y);
+    f[2] = Pair<__nv_bfloat16>::cvt(r.z);
+    f[3] = Pair<__nv_bfloat16>::cvt(r.w);
+  }
+};
+template <> struct Lanes<__half, 8> {
+  __device__ static void load(const __half* p, float2 (&f)[4]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    f[0] = Pair<__half>::cvt(r.x);
+    f[1] = Pair<__half>::cvt(r.y);
+    f[2] = Pair<__half>::cvt(r.z);
+    f[3] = Pair<__half>::cvt(r.w);
   }
 };
 
@@ -402,27 +428,23 @@ template <> struct Quad<__half> {
 // 2 x 8, 4 x 8, 8 x 8 for groups of up to 16 / 32 / 64 members.  A warp visits, per staged 32-row chunk and per member it owns, exactly the rows
 // that member pools (set bits of the member word, ascending) -- the accumulation order per (object, channel) is
 // the same ascending-patch sequence as in the dense kernel and in the oracle.
-template <typename T, int MPW, int NW>
-__global__ void __launch_bounds__(SparseCfg<MPW, NW>::kThreads, sizeof(T) == 4 ? (NW <= 8 ? 4 : 1) : SparseCfg<MPW, NW>::kMinCtas)
-mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, const T* __restrict__ feats,
-                        int n_patch, int c, int n_slices, const uint32_t* __restrict__ bits,
-                        const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,
-                        const int32_t* __restrict__ grp_off, const int32_t* __restrict__ grp_member, int tile_min,
-                        float* __restrict__ pooled) {
-  constexpr int S = SparseCfg<MPW, NW>::kStages, R = kPoolRows, PM = MPW * NW, kSparseThreads = SparseCfg<MPW, NW>::kThreads;
-  extern __shared__ __align__(1024) uint8_t dyn_smem[];
-  T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][kPoolCh]
-  __shared__ uint32_t s_bits[PM][UFV_BITS_WORDS];                          // members' patch bitmasks
-  __shared__ uint32_t s_union[UFV_BITS_WORDS];
-  __shared__ __align__(8) uint64_t full_bar[S];
-  __shared__ __align__(8) uint64_t empty_bar[S];
-
+// CH = channels per CTA slice, CH / 32 per lane.  The kernel is bound by its instruction count, and of the 15
+// instructions one (member, row) costs at 4 channels per lane, 8 find the row and close the loop: with 16-bit features
+// and up to 32 members the slices are 256 channels wide (8 per lane, one 16-byte shared load: 21 instructions per
+// 8 channels), and a frame's odd 128 channels (1152 = 4 x 256 + 128) go to a CTA that runs the 128-wide body.
+template <typename T, int MPW, int NW, int CH, int S>
+__device__ __forceinline__ void pool_sparse_body(const CUtensorMap& tmap, int use_tmap, const T* __restrict__ feats,
+                                                 int n_patch, int c, int g, int ch0, const uint32_t* __restrict__ bits,
+                                                 const int32_t* __restrict__ cnt, const int32_t* __restrict__ grp_row,
+                                                 const int32_t* __restrict__ grp_off,
+                                                 const int32_t* __restrict__ grp_member, int tile_min,
+                                                 float* __restrict__ pooled, T* ring, uint32_t (*s_bits)[UFV_BITS_WORDS],
+                                                 uint32_t* s_union, uint64_t* full_bar, uint64_t* empty_bar) {
+  constexpr int R = kPoolRows, PM = MPW * NW, kSparseThreads = SparseCfg<MPW, NW>::kThreads;
+  constexpr int VEC = CH / 32;                                            // channels per lane
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int g = blockIdx.x / n_slices;
-  const int slice = blockIdx.x - g * n_slices;
-  const int ch0 = slice * kPoolCh;
 
   if (tid == 0) {
 #pragma unroll
@@ -453,7 +475,7 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
   // (No packed path here: with 9 .. 64 objects on a frame the union is rarely thin, and the packing code's registers
   // would push this instruction-bound kernel's hot loop into local memory at the 32 registers seven CTAs per SM allow.)
   const int n_win = (n_patch + R - 1) / R;
-  const int slice_ch = min(kPoolCh, c - ch0);
+  const int slice_ch = min(CH, c - ch0);
 
   if (warp == NW) {
     // ---------------- producer warp ---------------------------------------------------------------------
@@ -467,15 +489,17 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
       const uint32_t ph = (k / S) & 1;
       ++k;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      produce_window<T>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
-                        ring + size_t(s) * R * kPoolCh, &full_bar[s], lane);
+      produce_window<T, CH>(&tmap, use_tmap, feats, row_base, c, ch0, slice_bytes, win, n_patch, u, tile_min,
+                            ring + size_t(s) * R * CH, &full_bar[s], lane);
     }
   } else {
-    // ---------------- consumer warps: members warp, warp + 8, ..., all 128 channels, 4 per lane -------------
-    float4 acc[MPW];
+    // ---------------- consumer warps: members warp, warp + 8, ..., all CH channels, VEC per lane ---------------
+    float2 acc[MPW][VEC / 2];
 #pragma unroll
-    for (int mi = 0; mi < MPW; ++mi) acc[mi] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int my_ch = lane * 4;
+    for (int mi = 0; mi < MPW; ++mi)
+#pragma unroll
+      for (int v = 0; v < VEC / 2; ++v) acc[mi][v] = make_float2(0.f, 0.f);
+    const int my_ch = lane * VEC;
     const bool live = my_ch < slice_ch;
     // one stage per non-empty window, patch 32 win + r in slot r -- the tight loop (this kernel is bound by its
     // instruction count)
@@ -486,18 +510,17 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
       const uint32_t ph = (k / S) & 1;
       ++k;
       mbar_wait(&full_bar[s], ph);
-      const T* src = ring + size_t(s) * R * kPoolCh + my_ch;
+      const T* src = ring + size_t(s) * R * CH + my_ch;
 #pragma unroll
       for (int mi = 0; mi < MPW; ++mi) {
         uint32_t word = s_bits[mi * NW + warp][win];         // warp-uniform: the rows of this window the member pools
         while (word != 0u) {
           const int r = __ffs(word) - 1;
           word &= word - 1u;
-          const float4 f = Quad<T>::load(src + r * kPoolCh);
-          float2 lo = make_float2(acc[mi].x, acc[mi].y), hi = make_float2(acc[mi].z, acc[mi].w);
-          add2(lo, make_float2(f.x, f.y));
-          add2(hi, make_float2(f.z, f.w));
-          acc[mi] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          float2 f[VEC / 2];
+          Lanes<T, VEC>::load(src + r * CH, f);
+#pragma unroll
+          for (int v = 0; v < VEC / 2; ++v) add2(acc[mi][v], f[v]);
         }
       }
       __syncwarp();
@@ -509,15 +532,48 @@ mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, int use_tmap, 
       if (j < n_mem && live) {
         const int out_row = grp_member[m0 + j];
         const float denorm = __fadd_rn(float(cnt[out_row]), 1e-8f);   // layer.py:145
-        float4 out;
-        out.x = __fdiv_rn(acc[mi].x, denorm);
-        out.y = __fdiv_rn(acc[mi].y, denorm);
-        out.z = __fdiv_rn(acc[mi].z, denorm);
-        out.w = __fdiv_rn(acc[mi].w, denorm);
-        *reinterpret_cast<float4*>(pooled + size_t(out_row) * c + ch0 + my_ch) = out;
+        float* dst = pooled + size_t(out_row) * c + ch0 + my_ch;
+#pragma unroll
+        for (int v = 0; v < VEC / 4; ++v) {
+          float4 out;
+          out.x = __fdiv_rn(acc[mi][2 * v].x, denorm);
+          out.y = __fdiv_rn(acc[mi][2 * v].y, denorm);
+          out.z = __fdiv_rn(acc[mi][2 * v + 1].x, denorm);
+          out.w = __fdiv_rn(acc[mi][2 * v + 1].y, denorm);
+          reinterpret_cast<float4*>(dst)[v] = out;
+        }
       }
     }
   }
+}
+
+// WIDE: 256-channel slices; the CTA of a frame's last, 128-channel-or-narrower slice runs the 128-wide body on it
+// (tmap_narrow: 128-channel boxes).  Work item = (group, slice): blockIdx.x = g * n_slices + slice.
+template <typename T, int MPW, int NW, bool WIDE>
+__global__ void __launch_bounds__(SparseCfg<MPW, NW>::kThreads,
+                                  sizeof(T) == 4 ? (NW <= 8 ? 4 : 1) : WIDE ? SparseCfg<MPW, NW>::kWideCtas : SparseCfg<MPW, NW>::kMinCtas)
+mask_pool_sparse_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_narrow,
+                        int use_tmap, const T* __restrict__ feats, int n_patch, int c, int n_slices,
+                        const uint32_t* __restrict__ bits, const int32_t* __restrict__ cnt,
+                        const int32_t* __restrict__ grp_row, const int32_t* __restrict__ grp_off,
+                        const int32_t* __restrict__ grp_member, int tile_min, float* __restrict__ pooled) {
+  constexpr int S = WIDE ? SparseCfg<MPW, NW>::kWideStages : SparseCfg<MPW, NW>::kStages, PM = MPW * NW;
+  constexpr int CH = WIDE ? 2 * kPoolCh : kPoolCh;
+  extern __shared__ __align__(1024) uint8_t dyn_smem[];
+  T* ring = reinterpret_cast<T*>(dyn_smem);                               // [S][R][CH]
+  __shared__ uint32_t s_bits[PM][UFV_BITS_WORDS];                          // members' patch bitmasks
+  __shared__ uint32_t s_union[UFV_BITS_WORDS];
+  __shared__ __align__(8) uint64_t full_bar[S];
+  __shared__ __align__(8) uint64_t empty_bar[S];
+  const int g = blockIdx.x / n_slices;
+  const int slice = blockIdx.x - g * n_slices;
+  const int ch0 = slice * CH;
+  if (WIDE && c - ch0 <= kPoolCh)
+    pool_sparse_body<T, MPW, NW, kPoolCh, S>(tmap_narrow, use_tmap, feats, n_patch, c, g, ch0, bits, cnt, grp_row, grp_off,
+                                          grp_member, tile_min, pooled, ring, s_bits, s_union, full_bar, empty_bar);
+  else
+    pool_sparse_body<T, MPW, NW, CH, S>(tmap, use_tmap, feats, n_patch, c, g, ch0, bits, cnt, grp_row, grp_off, grp_member,
+                                     tile_min, pooled, ring, s_bits, s_union, full_bar, empty_bar);
 }
 
 // ---- host -----------------------------------------------------------------------------------------
@@ -588,6 +644,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t r
 struct PoolArgs {
   const void* feats; int n_patch; int c; const uint32_t* bits; const int32_t* cnt; const int32_t* grp_row;
   const int32_t* grp_off; const int32_t* grp_member; int n_groups; int tile_min; float* pooled;
+  int feat_dtype; uint64_t tmap_rows;
 };
 
 template <typename T, int OT>
@@ -607,20 +664,26 @@ static int launch_pool(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a,
                     a.grp_off, a.grp_member, a.tile_min, a.pooled));
 }
 
-template <typename T, int MPW, int NW>
+template <typename T, int MPW, int NW, bool WIDE>
 static int launch_pool_sparse(const CUtensorMap& tmap, int use_tmap, const PoolArgs& a, cudaStream_t stream) {
-  const int n_slices = (a.c + kPoolCh - 1) / kPoolCh;
-  const size_t smem = size_t(SparseCfg<MPW, NW>::kStages) * kPoolRows * kPoolCh * sizeof(T);
+  constexpr int CH = WIDE ? 2 * kPoolCh : kPoolCh;
+  const int n_slices = (a.c + CH - 1) / CH;
+  const size_t smem = size_t(WIDE ? SparseCfg<MPW, NW>::kWideStages : SparseCfg<MPW, NW>::kStages) * kPoolRows * CH * sizeof(T);
   constexpr int kSparseThreads = SparseCfg<MPW, NW>::kThreads;
-  auto kernel = mask_pool_sparse_kernel<T, MPW, NW>;
+  auto kernel = mask_pool_sparse_kernel<T, MPW, NW, WIDE>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     configured = true;
   }
+  CUtensorMap wide = tmap;                      // tmap: 128-channel boxes (also the narrow last slice of a wide launch)
+  if (WIDE && use_tmap) {
+    const int rc = make_tensor_map_2d(&wide, a.feats, a.feat_dtype, a.tmap_rows, uint64_t(a.c), kPoolRows, CH, 0);
+    if (rc != 0) return rc;
+  }
   return check_launch(
       "ufv_mask_pool (many objects per frame)",
-      launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(kSparseThreads), smem, stream, tmap,
+      launch_kernel(kernel, dim3(unsigned(a.n_groups) * n_slices), dim3(kSparseThreads), smem, stream, wide, tmap,
                     use_tmap, static_cast<const T*>(a.feats), a.n_patch, a.c, n_slices, a.bits, a.cnt, a.grp_row,
                     a.grp_off, a.grp_member, a.tile_min, a.pooled));
 }
@@ -630,9 +693,16 @@ static int dispatch_group(int max_group, const CUtensorMap& tmap, int use_tmap, 
                           cudaStream_t stream) {
   if (max_group <= 4) return launch_pool<T, 4>(tmap, use_tmap, a, stream);
   if (max_group <= 8) return launch_pool<T, 8>(tmap, use_tmap, a, stream);
-  if (max_group <= 16) return launch_pool_sparse<T, 2, 8>(tmap, use_tmap, a, stream);
-  if (max_group <= 32) return launch_pool_sparse<T, 4, 8>(tmap, use_tmap, a, stream);
-  return launch_pool_sparse<T, 8, 8>(tmap, use_tmap, a, stream);
+  // 256-channel slices for 16-bit features and up to 32 members (UFV_POOL_NARROW=1: developer A/B knob)
+  static const bool wide_ok = getenv("UFV_POOL_NARROW") == nullptr;
+  constexpr bool kHalf = sizeof(T) == 2;
+  if (kHalf && wide_ok && a.c > kPoolCh) {
+    if (max_group <= 16) return launch_pool_sparse<T, 2, 8, kHalf>(tmap, use_tmap, a, stream);
+    if (max_group <= 32) return launch_pool_sparse<T, 4, 8, kHalf>(tmap, use_tmap, a, stream);
+  }
+  if (max_group <= 16) return launch_pool_sparse<T, 2, 8, false>(tmap, use_tmap, a, stream);
+  if (max_group <= 32) return launch_pool_sparse<T, 4, 8, false>(tmap, use_tmap, a, stream);
+  return launch_pool_sparse<T, 8, 8, false>(tmap, use_tmap, a, stream);
 }
 
 // ---- adjoint of the mask pool (training) --------------------------------------------
@@ -789,7 +859,8 @@ extern "C" int ufv_mask_pool(const void* feats, int feat_dtype, int64_t n_rows, 
     const int v = e ? atoi(e) : 20;
     return v < 1 ? 1 : v > 33 ? 33 : v;
   }();
-  const PoolArgs a{feats, n_patch, c, bits, cnt, grp_row, grp_off, grp_member, n_groups, tile_min, pooled_out};
+  const PoolArgs a{feats, n_patch, c, bits, cnt, grp_row, grp_off, grp_member, n_groups, tile_min, pooled_out,
+                   feat_dtype, uint64_t(n_rows) * n_patch};
   switch (feat_dtype) {
     case UFV_F32:
       return dispatch_group<float>(max_group, tmap, use_tile, a, st);

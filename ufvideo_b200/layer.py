@@ -131,14 +131,22 @@ def gather_rows(x: torch.Tensor, row_map: torch.Tensor):
 
 def _await_counts(plan: packer.EncodePlan, run: dict, device, idle_work=None) -> np.ndarray:
     """Poll the pinned words kernel 3 writes, (epoch << 16) | count per object, until all of them
-    carry this call's epoch; returns the int32 counts.  ``idle_work`` (optional callable) runs once
-    first: the host has ~60 us to kill here, which is where the next call's output tensor gets allocated."""
+    carry this call's epoch; returns the int32 counts (``plan.slots`` itself -- do not modify -- when no
+    object tied below its reserved count).  ``idle_work`` (optional callable) runs once first: the host has
+    ~60 us to kill here, which is where the next call's output tensor gets allocated.
+
+    The return of this function starts the critical path to the next call's first kernel (the projector of
+    this call is still running), so the common case is ONE bytes compare per poll against the words a
+    tie-free call must publish, computed before the polling starts."""
     words, epoch = run["counts_np"][:plan.n_obj], run["epoch"]
     if idle_work is not None:
         idle_work()
+    want = (plan.slots | np.int32(epoch << 16)).tobytes()
     last = plan.n_obj - 1
     spins = 0
     while True:
+        if words.tobytes() == want:              # every object published, none tied: the common case
+            return plan.slots
         if (int(words[last]) >> 16) == epoch:    # cheap scalar pre-check before the vector compare
             snap = words.copy()
             if ((snap >> 16) == epoch).all():
@@ -580,7 +588,7 @@ class MaskExtractor(nn.Module):
                 after_enqueue()
             run = self._last_run
             if run.get("args") is not None and plan.n_obj > 0:
-                return tokens, _await_counts(plan, run, tokens.device), plan
+                return tokens, _await_counts(plan, run, tokens.device).copy(), plan
             return tokens, counts.cpu().numpy(), plan
 
     def forward_into(self, feats, masks, ann_indices, text_embeds, seq_lens, region_pos, labels=None,
@@ -721,8 +729,8 @@ class MaskExtractor(nn.Module):
                 lambda: run.__setitem__("spare_out", torch.empty_like(tokens)) if "spare_out" not in run else None)
         else:
             region_token_nums = counts.cpu().numpy()
-        if region_token_nums.tobytes() == plan.slots_bytes:   # no ties: every object kept min(T, K) tokens
-            return tokens, list(plan.expect_counts)
+        if region_token_nums is plan.slots or region_token_nums.tobytes() == plan.slots_bytes:
+            return tokens, list(plan.expect_counts)           # no ties: every object kept min(T, K) tokens
         # ties at the merge threshold left some object with fewer than min(T, K) tokens:
         # drop the zero-filled slots (rare; exact ties only)
         nums = region_token_nums.tolist()
