@@ -237,18 +237,22 @@ def test_mask_pooling_module_matches_reference_signature(dev, golden_dir):
     assert np.abs(out.cpu().numpy() - g["dense384"]).max() <= 1e-5
 
 
-@pytest.mark.parametrize("n_obj,groups", [(5, 1), (9, 1), (17, 1), (33, 1), (64, 1), (70, 2)])
+@pytest.mark.parametrize("split", [16, 64])
+@pytest.mark.parametrize("n_obj", [5, 9, 17, 33, 64, 70])
 @pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
-def test_pool_many_objects_on_one_frame(dev, n_obj, groups, dtype):
-    """Many objects on one frame (PixRQA broadcast shape): the frame is one group of up to 64 members, streamed
-    once; beyond 8 members the bit-iterating consumers run (2 / 4 / 8 members per warp), beyond 64 the frame is
-    split.  A second frame with fewer members rides in the same call."""
+def test_pool_many_objects_on_one_frame(dev, n_obj, split, dtype, monkeypatch):
+    """Many objects on one frame (PixRQA broadcast shape): beyond 8 members the bit-iterating consumers run
+    (2 / 4 / 8 members per warp, 256-channel slices for 16-bit features up to 32 members); the packer cuts a
+    frame into equal sub-groups of at most GROUP_SPLIT members (16 by default; 64 = the kernel's limit, which
+    keeps the 4- and 8-members-per-warp variants covered).  A second frame with fewer members rides in the same call."""
+    monkeypatch.setattr(packer, "GROUP_SPLIT", split)
+    groups = -(-n_obj // split)
     feats = R.round_to(synth.features(77, 2), dtype)
     masks = np.concatenate([synth.masks_blob(78, n_obj, 1, 100, 120), synth.masks_sparse(79, 3, 100, 120)])
     rows = [0] * n_obj + [1] * 3
     ann = [[[r] for r in rows]]
-    plan = packer.build_plan([torch.from_numpy(masks).to(dev)], ann, 2, 4, dev)
-    assert plan.n_groups == groups + 1 and plan.max_group == min(n_obj, 64)
+    plan = packer.build_plan([torch.from_numpy(masks).to(dev)], ann, 2, 4, dev, use_cache=False)
+    assert plan.n_groups == groups + 1 and plan.max_group == max(-(-n_obj // groups), 3)
     patches = layer.mask_to_patches(plan, dev)
     pooled = layer.mask_pool(torch.from_numpy(feats).to(dev).to(TORCH_DT[dtype]), plan, patches).cpu().numpy()
     on = np.stack([R.mask_to_patches(m) for m in masks])

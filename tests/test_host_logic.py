@@ -90,8 +90,11 @@ def test_plan_groups_objects_by_frame_and_reserves_token_slots():
 def test_plan_splits_frames_with_many_objects():
     masks = [torch.zeros((150, 8, 8), dtype=torch.uint8)]
     plan = packer.build_plan(masks, [[[0]]], 1, 4, CPU)          # PixRQA broadcast: one feature row
-    assert plan.n_groups == 3 and plan.max_group == 64
-    assert np.diff(plan.host["grp_off"]).tolist() == [64, 64, 22]
+    sizes = np.diff(plan.host["grp_off"]).tolist()             # equal sub-groups of at most GROUP_SPLIT members
+    n = -(-150 // packer.GROUP_SPLIT)
+    assert plan.n_groups == n and sum(sizes) == 150 and max(sizes) - min(sizes) <= 1
+    assert plan.max_group == max(sizes) <= packer.GROUP_SPLIT
+    assert sorted(plan.host["grp_member"].tolist()) == list(range(150))
     assert plan.host["obj_len"].tolist() == [1] and plan.m_pad == 1
 
 
@@ -311,10 +314,10 @@ def test_region_layout_rejects_inconsistent_inputs():
 def test_algorithmic_pool_bytes_counts_each_feature_row_once_per_frame():
     """union over ALL object-frames of a feature row, however the packer grouped them."""
     masks = [torch.zeros((70, 8, 8), dtype=torch.uint8)]
-    plan = packer.build_plan(masks, [[[0]]], 1, 4, CPU)          # 70 objects on one frame: two groups (64 + 6)
-    assert plan.n_groups == 2
+    plan = packer.build_plan(masks, [[[0]]], 1, 4, CPU)          # 70 objects on one frame: several sub-groups
+    assert plan.n_groups == -(-70 // packer.GROUP_SPLIT) > 1
     bits = np.zeros((70, 24), np.uint32)
     bits[:, 0] = 0b1111                                           # every object: patches 0..3
-    bits[65, 1] = 1                                               # one object of the second group: patch 32 too
+    bits[65, 1] = 1                                               # one object of a later sub-group: patch 32 too
     got = packer.algorithmic_pool_bytes(plan, bits, 1152, 2)
     assert got == 5 * 1152 * 2 + 70 * 1152 * 4 + 70 * 96

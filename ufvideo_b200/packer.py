@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes
 import itertools
 import marshal
+import os
 import threading
 import weakref
 from collections import OrderedDict
@@ -205,6 +206,12 @@ def _same_indices(a, b) -> bool:
         return False
 
 
+# Object-frames per pool group (one CTA per group and channel slice).  The kernel takes up to MAX_GROUP = 64, but
+# with many objects on a frame it is bound by instructions and warps in flight, not by bytes: sub-groups of 16 (two
+# members per consumer warp, six CTAs per SM) measured 74 us against 86 us for 2 x 64 frames x 32 objects and 72
+# against 80 us for 64 frames x 64 objects; 8 is worse (285 against 201 us on c4).  UFV_GROUP_SPLIT: developer sweeps.
+GROUP_SPLIT = min(_cabi.MAX_GROUP, max(1, int(os.environ.get("UFV_GROUP_SPLIT", 16))))
+
 _last_call: list = [None]     # (mask tensor objects, their data_ptrs and shapes, scalar args, ann bytes, plan)
 
 
@@ -353,9 +360,14 @@ def _build(masks, ann_indices, n_feat_rows, k_keep, device, pad_square, n_out, p
     else:
         run_start = np.zeros(0, np.int64)
     run_len = np.diff(np.r_[run_start, q_total])
-    if q_total and run_len.max() > _cabi.MAX_GROUP:
-        pieces = [(s + o, min(_cabi.MAX_GROUP, l - o)) for s, l in zip(run_start, run_len)
-                  for o in range(0, l, _cabi.MAX_GROUP)]
+    if q_total and run_len.max() > GROUP_SPLIT:
+        # a frame with more object-frames than one CTA takes is cut into equal sub-groups (each re-reads the rows
+        # it needs; they run side by side, so the re-reads are L2 hits)
+        pieces = []
+        for s, l in zip(run_start.tolist(), run_len.tolist()):
+            n = -(-l // GROUP_SPLIT)
+            cuts = [s + (l * i) // n for i in range(n + 1)]
+            pieces.extend((a, b - a) for a, b in zip(cuts[:-1], cuts[1:]))
         run_start = np.array([p[0] for p in pieces], dtype=np.int64)
         run_len = np.array([p[1] for p in pieces], dtype=np.int64)
     n_groups = int(run_start.size)
