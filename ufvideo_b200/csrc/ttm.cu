@@ -57,9 +57,27 @@ __device__ __forceinline__ bool ranks_above(float a, float b) {
   return a > b || (a != a && b == b);
 }
 
-// canonical 32-lane strided sum of squares of one row (oracle/restatement.py::_rowsum)
+// ---- exact quotients with the reciprocal hoisted ------------------------------------------------------------
+// F.normalize divides every element by the row norm (true division).  The IEEE quotient RN(a / m) costs ~10
+// instructions apiece, and the similarity phase needs 2 x 1152 of them per pair.  With r = RN(1 / m) computed once
+// per row,  q = RN(a r);  e = fma(-q, m, a) (the exact remainder);  q' = fma(e, r, q)  IS RN(a / m) as long as
+// nothing underflows: checked bit for bit on 8e10 pairs with 2^-60 <= |a| < 2^41 and 2^-40 <= m < 2^47, random and
+// all-ones / all-zeros / +-1-ulp significands (tools/div_probe.cu).  Whether a row qualifies is found while its norm
+// is computed (one integer max per element); rows holding a zero, a denormal, a huge value, an inf or a NaN take the
+// IEEE division.  A row's norm is kept with the flag in its sign: +norm = every element in range.
+constexpr uint32_t kFastLo = 67u << 23;                          // 2^-60
+constexpr uint32_t kFastSpan = (168u << 23) - 1u - kFastLo;      // up to the largest value below 2^41
+__device__ __forceinline__ uint32_t range_excess(float x) { return (__float_as_uint(x) & 0x7fffffffu) - kFastLo; }
+__device__ __forceinline__ float quot_hoisted(float a, float m, float r) {
+  const float q = __fmul_rn(a, r);
+  return __fmaf_rn(__fmaf_rn(-q, m, a), r, q);
+}
+
+// canonical 32-lane strided sum of squares of one row (oracle/restatement.py::_rowsum); returns
+// max(||x||, 1e-12) (F.normalize), negated when some element is outside the hoisted-reciprocal range
 __device__ __forceinline__ float row_norm(const float* __restrict__ row, int c, int lane) {
   float acc = 0.f;
+  uint32_t worst = 0u;
   for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
     float4 v[kTtmBatch];
 #pragma unroll
@@ -72,10 +90,62 @@ __device__ __forceinline__ float row_norm(const float* __restrict__ row, int c, 
         acc = __fadd_rn(acc, __fmul_rn(v[u].y, v[u].y));
         acc = __fadd_rn(acc, __fmul_rn(v[u].z, v[u].z));
         acc = __fadd_rn(acc, __fmul_rn(v[u].w, v[u].w));
+        worst = max(max(worst, range_excess(v[u].x)), max(range_excess(v[u].y), max(range_excess(v[u].z), range_excess(v[u].w))));
       }
     }
   }
-  return fmaxf(__fsqrt_rn(butterfly_sum(acc)), 1e-12f);   // F.normalize: max(||x||, eps)
+  const float norm = fmaxf(__fsqrt_rn(butterfly_sum(acc)), 1e-12f);
+  return __all_sync(0xffffffffu, worst <= kFastSpan) ? norm : -norm;
+}
+
+// <x_a / |x_a|, x_b / |x_b|> of two rows in the canonical order; sa / sb = their signed norms (row_norm)
+__device__ __forceinline__ float pair_dot(const float* __restrict__ ra, const float* __restrict__ rb, float sa,
+                                          float sb, int c, int lane) {
+  const float ma = fabsf(sa), mb = fabsf(sb);
+  float acc = 0.f;
+  if (sa > 0.f && sb > 0.f) {                                    // warp-uniform
+    const float ia = __frcp_rn(ma), ib = __frcp_rn(mb);
+    for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
+      float4 a[kTtmBatch], b[kTtmBatch];
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u) {
+        if (e0 + u * 128 < c) {
+          a[u] = *reinterpret_cast<const float4*>(ra + e0 + u * 128);
+          b[u] = *reinterpret_cast<const float4*>(rb + e0 + u * 128);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u) {
+        if (e0 + u * 128 < c) {
+          acc = __fadd_rn(acc, __fmul_rn(quot_hoisted(a[u].x, ma, ia), quot_hoisted(b[u].x, mb, ib)));
+          acc = __fadd_rn(acc, __fmul_rn(quot_hoisted(a[u].y, ma, ia), quot_hoisted(b[u].y, mb, ib)));
+          acc = __fadd_rn(acc, __fmul_rn(quot_hoisted(a[u].z, ma, ia), quot_hoisted(b[u].z, mb, ib)));
+          acc = __fadd_rn(acc, __fmul_rn(quot_hoisted(a[u].w, ma, ia), quot_hoisted(b[u].w, mb, ib)));
+        }
+      }
+    }
+  } else {
+    for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
+      float4 a[kTtmBatch], b[kTtmBatch];
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u) {
+        if (e0 + u * 128 < c) {
+          a[u] = *reinterpret_cast<const float4*>(ra + e0 + u * 128);
+          b[u] = *reinterpret_cast<const float4*>(rb + e0 + u * 128);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kTtmBatch; ++u) {
+        if (e0 + u * 128 < c) {
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].x, ma), __fdiv_rn(b[u].x, mb)));
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].y, ma), __fdiv_rn(b[u].y, mb)));
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].z, ma), __fdiv_rn(b[u].z, mb)));
+          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].w, ma), __fdiv_rn(b[u].w, mb)));
+        }
+      }
+    }
+  }
+  return butterfly_sum(acc);
 }
 
 // ---- kernel 3a: adjacent cosine similarities, one warp per (object, pair) --------------------------
@@ -93,29 +163,7 @@ ttm_sims_kernel(const float* __restrict__ pooled, int c, const int32_t* __restri
   if (t_len <= k_keep || i >= t_len - 1) return;     // layer.py:115: nothing to merge / no such pair
   const float* ra = pooled + (size_t(obj_start[o]) + i) * c;
   const float* rb = ra + c;
-  const float ma = row_norm(ra, c, lane);
-  const float mb = row_norm(rb, c, lane);
-  float acc = 0.f;
-  for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
-    float4 a[kTtmBatch], b[kTtmBatch];
-#pragma unroll
-    for (int u = 0; u < kTtmBatch; ++u) {
-      if (e0 + u * 128 < c) {
-        a[u] = *reinterpret_cast<const float4*>(ra + e0 + u * 128);   // L1 hits: just read by row_norm
-        b[u] = *reinterpret_cast<const float4*>(rb + e0 + u * 128);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kTtmBatch; ++u) {
-      if (e0 + u * 128 < c) {
-        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].x, ma), __fdiv_rn(b[u].x, mb)));
-        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].y, ma), __fdiv_rn(b[u].y, mb)));
-        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].z, ma), __fdiv_rn(b[u].z, mb)));
-        acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].w, ma), __fdiv_rn(b[u].w, mb)));
-      }
-    }
-  }
-  acc = butterfly_sum(acc);
+  const float acc = pair_dot(ra, rb, row_norm(ra, c, lane), row_norm(rb, c, lane), c, lane);   // L1 hits the second time
   if (lane == 0) sims[size_t(o) * sims_pitch + i] = acc;
 }
 
@@ -290,11 +338,20 @@ ttm_merge_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
         acc.z = __fadd_rn(acc.z, v.z);
         acc.w = __fadd_rn(acc.w, v.w);
       }
-      const float n = float(last - first + 1);
-      acc.x = __fdiv_rn(acc.x, n);
-      acc.y = __fdiv_rn(acc.y, n);
-      acc.z = __fdiv_rn(acc.z, n);
-      acc.w = __fdiv_rn(acc.w, n);
+      const int len = last - first + 1;
+      const float n = float(len);
+      if ((len & (len - 1)) == 0) {         // 1, 2, 4, ...: scaling by 2^-k rounds exactly like the division
+        const float inv = __frcp_rn(n);
+        acc.x = __fmul_rn(acc.x, inv);
+        acc.y = __fmul_rn(acc.y, inv);
+        acc.z = __fmul_rn(acc.z, inv);
+        acc.w = __fmul_rn(acc.w, inv);
+      } else {
+        acc.x = __fdiv_rn(acc.x, n);
+        acc.y = __fdiv_rn(acc.y, n);
+        acc.z = __fdiv_rn(acc.z, n);
+        acc.w = __fdiv_rn(acc.w, n);
+      }
     }
     store_token<T>(tokens_out, tokens_f32_out, out_row + q * 4, acc);
   }
@@ -386,25 +443,8 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
 
   // ---- 1. norms: one warp per token (kTtmBatch float4 loads in flight per lane) -----------------
   for (int t = warp; t < t_len; t += kTtmWarps) {
-    const float* row = x + size_t(t) * c;
-    float acc = 0.f;
-    for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
-      float4 v[kTtmBatch];
-#pragma unroll
-      for (int u = 0; u < kTtmBatch; ++u)
-        if (e0 + u * 128 < c) v[u] = *reinterpret_cast<const float4*>(row + e0 + u * 128);
-#pragma unroll
-      for (int u = 0; u < kTtmBatch; ++u) {
-        if (e0 + u * 128 < c) {
-          acc = __fadd_rn(acc, __fmul_rn(v[u].x, v[u].x));
-          acc = __fadd_rn(acc, __fmul_rn(v[u].y, v[u].y));
-          acc = __fadd_rn(acc, __fmul_rn(v[u].z, v[u].z));
-          acc = __fadd_rn(acc, __fmul_rn(v[u].w, v[u].w));
-        }
-      }
-    }
-    acc = butterfly_sum(acc);
-    if (lane == 0) s_norm[t] = fmaxf(__fsqrt_rn(acc), 1e-12f);
+    const float sn = row_norm(x + size_t(t) * c, c, lane);       // signed: see row_norm
+    if (lane == 0) s_norm[t] = sn;
   }
   __syncthreads();
 
@@ -413,29 +453,7 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   const int n_sim = t_len - 1;
   for (int i = warp; i < n_sim; i += kTtmWarps) {
     const float* ra = x + size_t(i) * c;
-    const float* rb = ra + c;
-    const float ma = s_norm[i], mb = s_norm[i + 1];
-    float acc = 0.f;
-    for (int e0 = lane * 4; e0 < c; e0 += 128 * kTtmBatch) {
-      float4 a[kTtmBatch], b[kTtmBatch];
-#pragma unroll
-      for (int u = 0; u < kTtmBatch; ++u) {
-        if (e0 + u * 128 < c) {
-          a[u] = *reinterpret_cast<const float4*>(ra + e0 + u * 128);
-          b[u] = *reinterpret_cast<const float4*>(rb + e0 + u * 128);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kTtmBatch; ++u) {
-        if (e0 + u * 128 < c) {
-          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].x, ma), __fdiv_rn(b[u].x, mb)));
-          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].y, ma), __fdiv_rn(b[u].y, mb)));
-          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].z, ma), __fdiv_rn(b[u].z, mb)));
-          acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(a[u].w, ma), __fdiv_rn(b[u].w, mb)));
-        }
-      }
-    }
-    acc = butterfly_sum(acc);
+    const float acc = pair_dot(ra, ra + c, s_norm[i], s_norm[i + 1], c, lane);
     if (lane == 0) {
       s_sim[i] = acc;
       if (sims_out != nullptr) sims_out[size_t(o) * sims_pitch + i] = acc;
@@ -444,62 +462,92 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   __syncthreads();
 
   UFV_TRACE(5);
-  // ---- 3. r-th largest by rank counting -------------------------------------------------------------
   const int r = t_len - k_keep;
-  for (int i = tid; i < n_sim; i += kTtmThreads) {
-    const float si = s_sim[i];
-    int above = 0, not_below = 0;
-    for (int j = 0; j < n_sim; ++j) {
-      const float sj = s_sim[j];          // broadcast read
-      above += ranks_above(sj, si);
-      not_below += !ranks_above(si, sj);
-    }
-    if (above < r && r <= not_below) s_kth = si;   // every writer holds an equal value
-  }
-  __syncthreads();
-
-  // ---- 4. cuts -> run ends ------------------------------------------------------------------------------
-  const float kth = s_kth;
-  for (int base = 0; base < len_words * 32; base += kTtmThreads) {
-    const int i = base + tid;
-    const bool cut = i < n_sim && s_sim[i] < kth;
-    const uint32_t word = __ballot_sync(0xffffffffu, cut);
-    if (lane == 0 && (i >> 5) < len_words) s_cutw[i >> 5] = word;
-  }
-  __syncthreads();
-  if (warp == 0) {   // exclusive prefix over the cut words
-    int carry = 0;
-    for (int w0 = 0; w0 < len_words; w0 += 32) {
-      const int w = w0 + lane;
-      const int mine = w < len_words ? __popc(s_cutw[w]) : 0;
-      int incl = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += up;
+  if (n_sim <= 32) {
+    // ---- 3 + 4 for short objects: one warp, one similarity per lane, no block-wide barriers in between -----
+    if (warp == 0) {
+      const float si = lane < n_sim ? s_sim[lane] : 0.f;
+      int above = 0, not_below = 0;
+      for (int j = 0; j < n_sim; ++j) {
+        const float sj = __shfl_sync(0xffffffffu, si, j);
+        above += ranks_above(sj, si);
+        not_below += !ranks_above(si, sj);
       }
-      if (w < len_words) s_wpre[w] = carry + incl - mine;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+      const uint32_t holders = __ballot_sync(0xffffffffu, lane < n_sim && above < r && r <= not_below);
+      const float kth = __shfl_sync(0xffffffffu, si, __ffs(holders) - 1);   // every holder has an equal value
+      const uint32_t word = __ballot_sync(0xffffffffu, lane < n_sim && si < kth);
+      const int n_cut = __popc(word);
+      for (int w = lane; w < len_words; w += 32) {
+        s_cutw[w] = w == 0 ? word : 0u;
+        s_wpre[w] = w == 0 ? 0 : n_cut;
+      }
+      if ((word >> lane) & 1u) s_gend[__popc(word & ((1u << lane) - 1u))] = lane;
+      if (lane == 0) {
+        s_wpre[len_words] = n_cut;
+        s_gend[n_cut] = t_len - 1;          // the last run always ends at the last token (:29-31)
+        publish_count(counts_out, counts_host, epoch, o, n_cut + 1);
+      }
+      if (cuts_out != nullptr)
+        for (int w = lane; w < min(len_words, cut_pitch_words); w += 32)
+          cuts_out[size_t(o) * cut_pitch_words + w] = w == 0 ? word : 0u;
     }
-    if (lane == 0) s_wpre[len_words] = carry;
-  }
-  __syncthreads();
-  const int n_cut = s_wpre[len_words];
-  const int count = n_cut + 1;            // <= k_keep because at least r sims are >= kth
-  for (int i = tid; i < n_sim; i += kTtmThreads) {
-    const uint32_t word = s_cutw[i >> 5];
-    const uint32_t bit = 1u << (i & 31);
-    if (word & bit) s_gend[s_wpre[i >> 5] + __popc(word & (bit - 1u))] = i;
-  }
-  if (tid == 0) {
-    s_gend[n_cut] = t_len - 1;            // the last run always ends at the last token (:29-31)
-    publish_count(counts_out, counts_host, epoch, o, count);
-  }
-  if (cuts_out != nullptr)
-    for (int w = tid; w < min(len_words, cut_pitch_words); w += kTtmThreads)
-      cuts_out[size_t(o) * cut_pitch_words + w] = s_cutw[w];
-  __syncthreads();
+    __syncthreads();
+  } else {
+    // ---- 3. r-th largest by rank counting -------------------------------------------------------------
+    for (int i = tid; i < n_sim; i += kTtmThreads) {
+      const float si = s_sim[i];
+      int above = 0, not_below = 0;
+      for (int j = 0; j < n_sim; ++j) {
+        const float sj = s_sim[j];          // broadcast read
+        above += ranks_above(sj, si);
+        not_below += !ranks_above(si, sj);
+      }
+      if (above < r && r <= not_below) s_kth = si;   // every writer holds an equal value
+    }
+    __syncthreads();
 
+    // ---- 4. cuts -> run ends ------------------------------------------------------------------------------
+    const float kth = s_kth;
+    for (int base = 0; base < len_words * 32; base += kTtmThreads) {
+      const int i = base + tid;
+      const bool cut = i < n_sim && s_sim[i] < kth;
+      const uint32_t word = __ballot_sync(0xffffffffu, cut);
+      if (lane == 0 && (i >> 5) < len_words) s_cutw[i >> 5] = word;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive prefix over the cut words
+      int carry = 0;
+      for (int w0 = 0; w0 < len_words; w0 += 32) {
+        const int w = w0 + lane;
+        const int mine = w < len_words ? __popc(s_cutw[w]) : 0;
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += up;
+        }
+        if (w < len_words) s_wpre[w] = carry + incl - mine;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) s_wpre[len_words] = carry;
+    }
+    __syncthreads();
+    const int n_cut = s_wpre[len_words];
+    for (int i = tid; i < n_sim; i += kTtmThreads) {
+      const uint32_t word = s_cutw[i >> 5];
+      const uint32_t bit = 1u << (i & 31);
+      if (word & bit) s_gend[s_wpre[i >> 5] + __popc(word & (bit - 1u))] = i;
+    }
+    if (tid == 0) {
+      s_gend[n_cut] = t_len - 1;            // the last run always ends at the last token (:29-31)
+      publish_count(counts_out, counts_host, epoch, o, n_cut + 1);
+    }
+    if (cuts_out != nullptr)
+      for (int w = tid; w < min(len_words, cut_pitch_words); w += kTtmThreads)
+        cuts_out[size_t(o) * cut_pitch_words + w] = s_cutw[w];
+    __syncthreads();
+  }
+  const int count = s_wpre[len_words] + 1;  // <= k_keep because at least r sims are >= kth
   UFV_TRACE(6);
   // ---- 5. run means, ascending token order; unused slots are zero-filled -----------------------------------
   for (int u = tid; u < n_slots * c4; u += kTtmThreads) {
@@ -517,11 +565,20 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
         acc.z = __fadd_rn(acc.z, v.z);
         acc.w = __fadd_rn(acc.w, v.w);
       }
-      const float n = float(last - first + 1);
-      acc.x = __fdiv_rn(acc.x, n);
-      acc.y = __fdiv_rn(acc.y, n);
-      acc.z = __fdiv_rn(acc.z, n);
-      acc.w = __fdiv_rn(acc.w, n);
+      const int len = last - first + 1;
+      const float n = float(len);
+      if ((len & (len - 1)) == 0) {         // 1, 2, 4, ...: scaling by 2^-k rounds exactly like the division
+        const float inv = __frcp_rn(n);
+        acc.x = __fmul_rn(acc.x, inv);
+        acc.y = __fmul_rn(acc.y, inv);
+        acc.z = __fmul_rn(acc.z, inv);
+        acc.w = __fmul_rn(acc.w, inv);
+      } else {
+        acc.x = __fdiv_rn(acc.x, n);
+        acc.y = __fdiv_rn(acc.y, n);
+        acc.z = __fdiv_rn(acc.z, n);
+        acc.w = __fdiv_rn(acc.w, n);
+      }
     }
     store_token<T>(tokens_out, tokens_f32_out, size_t(slot + g) * c + q * 4, acc);
   }
