@@ -315,6 +315,33 @@ def test_ttm_bit_exact_vs_oracle_on_coherent_tokens(dev, family):
         assert n == o_tok.shape[0] and np.array_equal(tok[:n], o_tok)
 
 
+@pytest.mark.parametrize("t,k", [(16, 8), (33, 4), (40, 8), (100, 8)])
+def test_ttm_quotient_paths_bit_exact_on_mixed_magnitudes(dev, t, k):
+    """The merge kernel divides by the row norm with the reciprocal hoisted where that is provably the IEEE quotient
+    and with the IEEE division elsewhere (ttm.cu, tools/div_probe.cu).  Rows that hold a zero, a value below 2^-60,
+    above 2^41, or whose elements span the whole admitted range sit next to ordinary rows, so adjacent pairs take
+    every combination of the two paths; similarities, cuts and merged tokens equal the oracle's bit for bit.
+    t = 16 / 33: the one-warp threshold phase (T <= 33); 40: the block-wide one; 100: the split kernels."""
+    g = synth.rng_for(977 + t)
+    x = g.standard_normal((t, 1152), dtype=np.float32)
+    x[1, 7] = 0.0                                             # a zero: IEEE path
+    x[2] *= np.float32(2.0 ** -70)                            # whole row below the fast range
+    x[3, 100] = np.float32(1e-25)                             # one tiny element
+    x[5] *= np.float32(2.0 ** 43)                             # whole row above the fast range
+    x[6, 5] = np.float32(3e12)                                # one element just above 2^41
+    x[7] *= np.float32(2.0 ** 30)                             # large but inside: fast path
+    x[8] *= np.float32(2.0 ** -45)                            # small but inside: fast path
+    x[9, ::2] *= np.float32(2.0 ** -55)                       # wide dynamic range inside: fast path
+    x[9, 1::2] *= np.float32(2.0 ** 35)
+    x[10] = 0.0                                               # all-zero row: norm clamps to 1e-12
+    x[12] = x[11]                                             # an exact duplicate: similarity near 1
+    tok, n, cut, sims = run_ttm(dev, x, k)
+    o_tok, o_cut, o_sims = R.token_merge(x, k)
+    assert np.array_equal(sims.view(np.uint32), o_sims.view(np.uint32))
+    assert np.array_equal(cut, o_cut) and n == o_tok.shape[0]
+    assert np.array_equal(tok[:n].view(np.uint32), o_tok.view(np.uint32))
+
+
 def test_token_merge_function_matches_reference_signature(dev):
     x = gc.ttm_tokens("random", 16, 40003)
     out = token_merge(torch.from_numpy(x).to(dev)[None], 8)            # r = tokens to remove
