@@ -550,8 +550,12 @@ ttm_fused_kernel(const float* __restrict__ pooled, int c, const int32_t* __restr
   const int count = s_wpre[len_words] + 1;  // <= k_keep because at least r sims are >= kth
   UFV_TRACE(6);
   // ---- 5. run means, ascending token order; unused slots are zero-filled -----------------------------------
-  for (int u = tid; u < n_slots * c4; u += kTtmThreads) {
-    const int g = u / c4, q = u - g * c4;
+  // one warp per (output token, 128 channels): the run bounds are warp-uniform (broadcast reads, no divergence in
+  // the row loop), and no per-thread integer division
+  const int chunks = (c4 + 31) >> 5;
+  for (int item = warp; item < n_slots * chunks; item += kTtmWarps) {
+    const int g = item / chunks, q = (item - g * chunks) * 32 + lane;
+    if (q >= c4) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g < count) {
       const int first = g == 0 ? 0 : s_gend[g - 1] + 1;
