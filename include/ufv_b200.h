@@ -117,7 +117,10 @@ int ufv_mask_to_patches(const ufv_mask_desc* desc, const int32_t* taps, int n_ma
  *           bitmasks, skips windows nobody needs, fetches mostly-needed windows as one 2-D tile and
  *           sparse ones row by row.  Up to 8 members: every staged row is added into the members whose
  *           bit is set (warp-uniform predicates).  9 .. 64 members: each consumer warp owns a few members
- *           and walks only the rows its members pool.
+ *           and walks only the rows its members pool (16-bit features, up to 32 members: 256-channel
+ *           slices).  Several groups may name the same feature row: with many object-frames on a frame
+ *           the kernel is bound by instructions, not bytes, and equal sub-groups of <= 16 run faster
+ *           than one group of 64 (what ufvideo_b200/packer.py builds; every split gives the same bits).
  *           max_group = the largest group size in this call (selects the kernel variant)
  *   pooled_out fp32 [n_masks, c]:  sum over on patches in ascending patch order, divided by
  *           (float(cnt) + 1e-8f); an all-off mask gives an exact zero row.

@@ -321,3 +321,35 @@ def test_algorithmic_pool_bytes_counts_each_feature_row_once_per_frame():
     bits[65, 1] = 1                                               # one object of a later sub-group: patch 32 too
     got = packer.algorithmic_pool_bytes(plan, bits, 1152, 2)
     assert got == 5 * 1152 * 2 + 70 * 1152 * 4 + 70 * 96
+
+
+@settings(max_examples=40, deadline=None, derandomize=True)
+@given(st.lists(st.integers(1, 90), min_size=1, max_size=4), st.integers(1, 64), st.integers(0, 10_000))
+def test_plan_groups_partition_object_frames_for_any_split(objs_per_frame, split, seed):
+    """Pool groups for any GROUP_SPLIT: every object-frame sits in exactly one group, a group's members read one
+    feature row, no group exceeds the split, the sub-groups of a frame differ in size by at most one, and
+    SURVEY 8(d)'s algorithmic bytes (union per FRAME) do not depend on the split."""
+    import unittest.mock as mock
+    g = synth.rng_for(seed)
+    n_frames = len(objs_per_frame)
+    ann, n_masks = [], 0
+    for f, n in enumerate(objs_per_frame):                     # n objects annotated on frame f only
+        ann.extend([f] for _ in range(n))
+        n_masks += n
+    masks = [torch.zeros((n_masks, 8, 8), dtype=torch.uint8)]
+    bits = g.integers(0, 2 ** 32, size=(n_masks, 24), dtype=np.uint64).astype(np.uint32)
+    with mock.patch.object(packer, "GROUP_SPLIT", split):
+        plan = packer.build_plan(masks, [ann], n_frames, 4, CPU, use_cache=False)
+    off, mem, row = plan.host["grp_off"], plan.host["grp_member"], plan.host["grp_row"]
+    assert sorted(mem.tolist()) == list(range(n_masks))
+    sizes = np.diff(off)
+    assert sizes.min() >= 1 and sizes.max() == plan.max_group <= split
+    frame_of = np.repeat(np.arange(n_frames), objs_per_frame)
+    for gi in range(plan.n_groups):
+        assert (frame_of[mem[off[gi]:off[gi + 1]]] == row[gi]).all()
+    for f, n in enumerate(objs_per_frame):
+        mine = sizes[row == f]
+        assert mine.sum() == n and mine.size == -(-n // split) and mine.max() - mine.min() <= 1
+    with mock.patch.object(packer, "GROUP_SPLIT", 64):
+        whole = packer.build_plan(masks, [ann], n_frames, 4, CPU, use_cache=False)
+    assert packer.algorithmic_pool_bytes(plan, bits, 1152, 2) == packer.algorithmic_pool_bytes(whole, bits, 1152, 2)
