@@ -2,6 +2,7 @@
 the tap-table helper equals the oracle, and the packer restates the reference's bookkeeping."""
 import os
 import re
+import types
 
 import numpy as np
 import pytest
@@ -353,3 +354,35 @@ def test_plan_groups_partition_object_frames_for_any_split(objs_per_frame, split
     with mock.patch.object(packer, "GROUP_SPLIT", 64):
         whole = packer.build_plan(masks, [ann], n_frames, 4, CPU, use_cache=False)
     assert packer.algorithmic_pool_bytes(plan, bits, 1152, 2) == packer.algorithmic_pool_bytes(whole, bits, 1152, 2)
+
+
+def test_await_counts_host_protocol(monkeypatch):
+    """layer._await_counts without a GPU: the merge kernel publishes (epoch << 16) | count per object into pinned
+    words; the host returns plan.slots itself on the tie-free fast path (one bytes compare), the real counts when
+    an object tied below its reserved count, and keeps polling while any word still carries an older epoch."""
+    import threading
+    import time
+    from ufvideo_b200 import layer
+    masks = [torch.zeros((6, 8, 8), dtype=torch.uint8)]
+    plan = packer.build_plan(masks, [[[0, 1, 2], [0, 1, 2]]], 3, 2, CPU, use_cache=False)     # 2 objects, T = 3, K = 2
+    assert plan.slots.tolist() == [2, 2]
+    words = np.zeros(2, np.int32)
+    run = {"counts_np": words, "epoch": 7}
+    words[:] = (7 << 16) | plan.slots
+    assert layer._await_counts(plan, run, CPU) is plan.slots
+    words[:] = [(7 << 16) | 2, (7 << 16) | 1]                      # the second object tied: one token
+    got = layer._await_counts(plan, run, CPU)
+    assert got is not plan.slots and got.tolist() == [2, 1]
+    words[:] = [(7 << 16) | 2, (6 << 16) | 2]                      # second word still from the previous call
+    idle = []
+
+    def publish():
+        time.sleep(0.05)
+        words[1] = (7 << 16) | 2
+    # every 65536 polls the loop asks the stream whether the launch is still running: here it always is
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: types.SimpleNamespace(query=lambda: False))
+    t = threading.Thread(target=publish)
+    t.start()
+    got = layer._await_counts(plan, run, CPU, idle_work=lambda: idle.append(1))
+    t.join()
+    assert got is plan.slots and idle == [1]
